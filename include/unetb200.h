@@ -1,0 +1,79 @@
+/* libunetb200 — C ABI of the B200-native U-Net(ResNet-34) hot path.
+ *
+ * This is the drop-in boundary for the one path BASELINE.json names: what the reference reaches through
+ *   segmentation_models_pytorch.Unet("resnet34", in_channels=3, classes=1)(x)
+ *     (/root/reference/train.py:372-378,436 ; infer_pth_gui.py:31-33,50-51 ; ui_infer_rectangle.py:496-499,556-559 ;
+ *      ui_infer_quadrilateral.py:638-641,704-707)
+ *   nn.BCEWithLogitsLoss() + smp.losses.DiceLoss(mode="binary")      (/root/reference/train.py:600-601,438)
+ *   loss.backward() / torch.optim.AdamW(...).step()                   (/root/reference/train.py:441-449,606)
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; every pointer named *_dev is a device pointer owned by the caller
+ *     (PyTorch) and valid for the duration of the stream-ordered call; the library never frees or retains it.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous.
+ *   - every function returns 0 on success, non-zero on error; unetb200_last_error() gives the message.
+ *   - there is no CPU or cuDNN fallback: a non-sm_100 device, a bad shape or a missing weight load is an error.
+ *   - one ctx per (process, device); calls on one ctx are not re-entrant.
+ *
+ * Tensor table: the library defines the canonical order (== state_dict order of smp.Unet("resnet34"), 278 entries,
+ * SURVEY.md section 8b).  kind 0 = fp32 parameter (offset into the flat parameter array, 24,436,369 floats),
+ * kind 1 = fp32 buffer running_mean/var (offset into the flat buffer array), kind 2 = int64 num_batches_tracked
+ * (offset = index into the counter array).
+ */
+#ifndef UNETB200_H
+#define UNETB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct unetb200_ctx unetb200_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------------ */
+/* replaces: smp.Unet(...).to(device)  (train.py:595, infer_pth_gui.py:43).  H, W: input size, multiples of 32. */
+int unetb200_create(unetb200_ctx** out, int device, int max_batch, int H, int W);
+void unetb200_destroy(unetb200_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed unetb200_create on this thread. */
+const char* unetb200_last_error(unetb200_ctx* ctx);
+/* device-side pipeline watchdog flag (0 = healthy); synchronises the device. */
+int unetb200_check_device_error(unetb200_ctx* ctx, int* flag_out);
+
+/* ---- tensor table (state_dict layout) ---------------------------------------------------------------------------- */
+int unetb200_num_tensors(void);
+int unetb200_tensor_info(int index, char* name_out, int name_cap, int* ndim_out, int shape_out[4],
+                         long long* offset_out, int* kind_out);
+long long unetb200_num_params(void);   /* 24,436,369 */
+long long unetb200_num_buffers(void);  /* 19,008 fp32 running statistics */
+int unetb200_num_counters(void);       /* 46 int64 num_batches_tracked */
+
+/* ---- weights ----------------------------------------------------------------------------------------------------- */
+/* replaces: model.load_state_dict(sd) (infer_pth_gui.py:42) / the implicit use of current parameters by forward.
+ * Re-packs the fp32 master tensors into the bf16 K-major operand caches and folds eval-mode BatchNorm. */
+int unetb200_load_weights(unetb200_ctx* ctx, const float* params_dev, const float* buffers_dev, void* stream);
+
+/* ---- inference: model.eval(); torch.sigmoid(model(x)) >= t  (infer_pth_gui.py:50-52) ---------------------------- */
+/* x_dev: fp32 NCHW [N,3,H,W].  Any of logits/prob/mask may be NULL (at least one must not be):
+ *   logits_dev fp32 [N,1,H,W]; prob_dev fp32 sigmoid(logits); mask_dev uint8 {0,255} = prob >= thresh. */
+int unetb200_forward_infer(unetb200_ctx* ctx, const float* x_dev, float* logits_dev, float* prob_dev,
+                           uint8_t* mask_dev, float thresh, int N, void* stream);
+/* Same through HOST buffers (pinned or pageable): H2D of x, forward, D2H of the requested outputs, synchronous.
+ * This is the end-to-end call a non-PyTorch host (the reference GUIs' numpy path) would bind. */
+int unetb200_infer_host(unetb200_ctx* ctx, const float* x_host, float* logits_host, float* prob_host,
+                        uint8_t* mask_host, float thresh, int N);
+/* number of kernel launches one forward_infer call issues at batch N (after the plan for N exists) */
+int unetb200_infer_launch_count(unetb200_ctx* ctx, int N);
+
+/* ---- per-kernel entry points for unit parity tests --------------------------------------------------------------- */
+/* conv + folded scale/shift (+residual) (+ReLU) on NHWC bf16: w_dev fp32 OIHW [cout,cin,k,k], k in {1,3},
+ * stride in {1,2}, padding k/2.  scale/shift/residual may be NULL.  stats_dev (optional) fp32 [cout][2] receives
+ * per-channel sum / sum-of-squares of the bf16 output. */
+int unetb200_conv_nhwc(unetb200_ctx* ctx, const void* in_bf16_dev, const float* w_dev, const float* scale_dev,
+                       const float* shift_dev, const void* residual_bf16_dev, int relu, void* out_bf16_dev,
+                       float* stats_dev, int N, int H, int W, int cin, int cout, int k, int stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETB200_H */

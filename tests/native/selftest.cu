@@ -1,0 +1,479 @@
+// Native GPU self-test for the igemm conv kernel and helper kernels (no torch needed; runs in seconds on a B200).
+// Each case compares against a straightforward CPU convolution (fp32 accumulate over bf16-rounded operands).
+// Usage: selftest [case-filter-substring]
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../vickers_hardness_unet_b200/csrc/unet.cuh"
+
+using namespace ub;
+
+#define CK(x)                                                                         \
+    do {                                                                              \
+        cudaError_t e_ = (x);                                                         \
+        if (e_ != cudaSuccess) {                                                      \
+            printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            exit(2);                                                                  \
+        }                                                                             \
+    } while (0)
+
+static uint32_t rng_state = 12345;
+static float frand() {  // uniform in [-1, 1)
+    rng_state = rng_state * 1664525u + 1013904223u;
+    return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct HostT {  // NHWC fp32 mirror of a bf16 device tensor
+    int N, H, W, C;
+    std::vector<float> v;
+    HostT(int n, int h, int w, int c) : N(n), H(h), W(w), C(c), v((size_t)n * h * w * c) {}
+    float& at(int n, int h, int w, int c) { return v[(((size_t)n * H + h) * W + w) * C + c]; }
+    float get(int n, int h, int w, int c) const {
+        if (h < 0 || h >= H || w < 0 || w >= W) return 0.f;
+        return v[(((size_t)n * H + h) * W + w) * C + c];
+    }
+};
+static __nv_bfloat16* to_dev_bf16(const std::vector<float>& v) {
+    std::vector<__nv_bfloat16> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16(v[i]);
+    __nv_bfloat16* d;
+    CK(cudaMalloc(&d, v.size() * 2 + 256));
+    CK(cudaMemcpy(d, h.data(), v.size() * 2, cudaMemcpyHostToDevice));
+    return d;
+}
+static float* to_dev_f32(const std::vector<float>& v) {
+    float* d;
+    CK(cudaMalloc(&d, v.size() * 4 + 256));
+    CK(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    return d;
+}
+static std::vector<float> from_dev_bf16(const __nv_bfloat16* d, size_t n) {
+    std::vector<__nv_bfloat16> h(n);
+    CK(cudaMemcpy(h.data(), d, n * 2, cudaMemcpyDeviceToHost));
+    std::vector<float> v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = __bfloat162float(h[i]);
+    return v;
+}
+static void fill_rand_bf16(std::vector<float>& v, float scale) {
+    for (auto& x : v) x = bf16r(frand() * scale);
+}
+
+// CPU conv: in NHWC, w OIHW (already rounded as the GPU sees it), out NHWC fp32
+static HostT cpu_conv(const HostT& in, const std::vector<float>& w, int cout, int k, int stride, int pad) {
+    const int Ho = (in.H + 2 * pad - k) / stride + 1, Wo = (in.W + 2 * pad - k) / stride + 1;
+    HostT out(in.N, Ho, Wo, cout);
+    // re-layout weights to [co][r][s][ci] for speed
+    std::vector<float> wr((size_t)cout * k * k * in.C);
+    for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < in.C; ++ci)
+            for (int r = 0; r < k; ++r)
+                for (int s = 0; s < k; ++s)
+                    wr[(((size_t)co * k + r) * k + s) * in.C + ci] = w[(((size_t)co * in.C + ci) * k + r) * k + s];
+#pragma omp parallel for collapse(2)
+    for (int n = 0; n < in.N; ++n)
+        for (int ho = 0; ho < Ho; ++ho)
+            for (int wo = 0; wo < Wo; ++wo)
+                for (int co = 0; co < cout; ++co) {
+                    double acc = 0;
+                    for (int r = 0; r < k; ++r) {
+                        const int h = ho * stride - pad + r;
+                        if (h < 0 || h >= in.H) continue;
+                        for (int s = 0; s < k; ++s) {
+                            const int ww = wo * stride - pad + s;
+                            if (ww < 0 || ww >= in.W) continue;
+                            const float* ip = &in.v[(((size_t)n * in.H + h) * in.W + ww) * in.C];
+                            const float* wp = &wr[(((size_t)co * k + r) * k + s) * in.C];
+                            float a = 0;
+                            for (int ci = 0; ci < in.C; ++ci) a += ip[ci] * wp[ci];
+                            acc += a;
+                        }
+                    }
+                    out.at(n, ho, wo, co) = (float)acc;
+                }
+    return out;
+}
+
+struct Cmp {
+    double max_abs = 0, max_ref = 0, sum_abs = 0;
+    size_t n = 0, worst = 0;
+};
+static Cmp compare(const std::vector<float>& got, const std::vector<float>& ref) {
+    Cmp c;
+    c.n = ref.size();
+    for (size_t i = 0; i < ref.size(); ++i) {
+        const double d = fabs((double)got[i] - ref[i]);
+        if (!(d <= c.max_abs)) {  // also catches NaN
+            c.max_abs = d;
+            c.worst = i;
+        }
+        c.sum_abs += d;
+        c.max_ref = fmax(c.max_ref, fabs(ref[i]));
+    }
+    return c;
+}
+
+static int g_fail = 0, g_run = 0;
+static Ctx* g_ctx = nullptr;
+
+static bool report(const char* name, const Cmp& c, double tol_rel, const std::vector<float>& got,
+                   const std::vector<float>& ref, int C) {
+    const double rel = c.max_abs / (c.max_ref + 1e-30);
+    const bool ok = rel <= tol_rel;
+    printf("[%s] %-44s max_abs %.4g (ref max %.4g, rel %.3g) mean_abs %.3g\n", ok ? "PASS" : "FAIL", name, c.max_abs,
+           c.max_ref, rel, c.sum_abs / (double)c.n);
+    if (!ok) {
+        g_fail++;
+        printf("       worst idx %zu (pixel %zu, ch %zu): got %g ref %g\n", c.worst, c.worst / C, c.worst % C,
+               got[c.worst], ref[c.worst]);
+        // a few samples to help diagnose layout problems
+        for (size_t i = 0; i < 6 && i < ref.size(); ++i) printf("       [%zu] got %g ref %g\n", i, got[i], ref[i]);
+        size_t nbad = 0;
+        for (size_t i = 0; i < ref.size(); ++i)
+            if (!(fabs((double)got[i] - ref[i]) <= tol_rel * c.max_ref)) nbad++;
+        printf("       %zu / %zu elements out of tolerance\n", nbad, ref.size());
+    }
+    g_run++;
+    return ok;
+}
+static int check_err_flag(const char* name) {
+    int e = 0;
+    CK(cudaMemcpy(&e, g_ctx->d_err, 4, cudaMemcpyDeviceToHost));
+    if (e) {
+        printf("[FAIL] %s: pipeline timeout flag = %d (1 producer, 2 mma-tmem, 3 mma-full, 4 epilogue)\n", name, e);
+        CK(cudaMemset(g_ctx->d_err, 0, 4));
+        g_fail++;
+    }
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------ cases
+static void case_conv(const char* name, int N, int H, int W, int cin, int cout, int k, int stride, bool residual,
+                      bool relu, bool scale_shift, bool stats) {
+    HostT in(N, H, W, cin);
+    fill_rand_bf16(in.v, 1.0f);
+    std::vector<float> w((size_t)cout * cin * k * k);
+    const float ws = 1.0f / sqrtf((float)cin * k * k);
+    for (auto& x : w) x = frand() * ws;
+    std::vector<float> wq(w.size());
+    for (size_t i = 0; i < w.size(); ++i) wq[i] = bf16r(w[i]);
+    HostT ref = cpu_conv(in, wq, cout, k, stride, k / 2);
+    std::vector<float> sc(cout, 1.f), sh(cout, 0.f);
+    if (scale_shift)
+        for (int c = 0; c < cout; ++c) {
+            sc[c] = 0.5f + 0.5f * fabsf(frand());
+            sh[c] = 0.3f * frand();
+        }
+    HostT res(N, ref.H, ref.W, cout);
+    if (residual) fill_rand_bf16(res.v, 1.0f);
+    for (size_t i = 0; i < ref.v.size(); ++i) {
+        const int c = i % cout;
+        float v = ref.v[i] * sc[c] + sh[c];
+        if (residual) v += res.v[i];
+        if (relu) v = fmaxf(v, 0.f);
+        ref.v[i] = v;
+    }
+    __nv_bfloat16* d_in = to_dev_bf16(in.v);
+    float* d_w = to_dev_f32(w);
+    __nv_bfloat16* d_wpk;
+    CK(cudaMalloc(&d_wpk, w.size() * 2));
+    pack_conv_w_kernel<<<64, 256>>>(d_w, d_wpk, cout, cin, k, k, 0);
+    __nv_bfloat16* d_out;
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    CK(cudaMemset(d_out, 0xFF, ref.v.size() * 2));  // NaN pattern: unwritten outputs are caught
+    float *d_sc = to_dev_f32(sc), *d_sh = to_dev_f32(sh);
+    __nv_bfloat16* d_res = residual ? to_dev_bf16(res.v) : nullptr;
+    ConvRef c;
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride;
+    EpilogueDesc ep;
+    if (scale_shift) { ep.scale = d_sc; ep.shift = d_sh; }
+    ep.relu = relu;
+    if (residual) ep.residual = nhwc_view(d_res, N, ref.H, ref.W, cout);
+    View4 ov = nhwc_view(d_out, N, ref.H, ref.W, cout);
+    const int mt = igemm_m_tiles(ov);
+    float* d_stats = nullptr;
+    if (stats) {
+        CK(cudaMalloc(&d_stats, (size_t)mt * cout * 2 * 4));
+        CK(cudaMemset(d_stats, 0, (size_t)mt * cout * 2 * 4));
+        ep.stats = d_stats;
+    }
+    IgemmLaunch L;
+    std::string e = build_conv(g_ctx, L, c, d_wpk, d_in, N, H, W, d_out, ep);
+    if (!e.empty()) {
+        printf("[FAIL] %s: build: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %d smem %u stages %d tile %dx%dx%d ntile %d chunk %d taps %d chunks %d\n", name, L.grid,
+           L.smem, L.p.stages, L.p.bw, L.p.bh, L.p.bn, L.p.ntile, L.p.chunk_elems, L.p.num_taps, L.p.total_chunks);
+    CK(igemm_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (check_err_flag(name)) return;
+    std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+    Cmp cm = compare(got, ref.v);
+    report(name, cm, 0.012, got, ref.v, cout);
+    if (stats) {
+        std::vector<float> hs((size_t)mt * cout * 2);
+        CK(cudaMemcpy(hs.data(), d_stats, hs.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<float> s_got(cout * 2, 0.f), s_ref(cout * 2, 0.f);
+        for (int t = 0; t < mt; ++t)
+            for (int ch = 0; ch < cout * 2; ++ch) s_got[ch] += hs[(size_t)t * cout * 2 + ch];
+        for (size_t i = 0; i < got.size(); ++i) {  // statistics are defined over the bf16 output the kernel wrote
+            s_ref[(i % cout) * 2] += got[i];
+            s_ref[(i % cout) * 2 + 1] += got[i] * got[i];
+        }
+        Cmp cs = compare(s_got, s_ref);
+        std::string nm = std::string(name) + " [stats]";
+        report(nm.c_str(), cs, 2e-3, s_got, s_ref, 2);
+    }
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_wpk); cudaFree(d_out); cudaFree(d_sc); cudaFree(d_sh);
+    if (d_res) cudaFree(d_res);
+    if (d_stats) cudaFree(d_stats);
+}
+
+static void case_stem(const char* name, int N, int H, int W) {
+    // input fp32 NCHW
+    std::vector<float> x((size_t)N * 3 * H * W);
+    for (auto& v : x) v = frand() * 2.f;
+    HostT in(N, H, W, 3);
+    for (int n = 0; n < N; ++n)
+        for (int c = 0; c < 3; ++c)
+            for (int h = 0; h < H; ++h)
+                for (int w = 0; w < W; ++w) in.at(n, h, w, c) = bf16r(x[(((size_t)n * 3 + c) * H + h) * W + w]);
+    std::vector<float> w((size_t)64 * 3 * 49), wq(w.size());
+    for (auto& v : w) v = frand() * 0.08f;
+    for (size_t i = 0; i < w.size(); ++i) wq[i] = bf16r(w[i]);
+    HostT ref = cpu_conv(in, wq, 64, 7, 2, 3);
+    for (auto& v : ref.v) v = fmaxf(v, 0.f);
+    float* d_x = to_dev_f32(x);
+    float* d_w = to_dev_f32(w);
+    __nv_bfloat16 *d_xp, *d_wpk, *d_out;
+    CK(cudaMalloc(&d_xp, (size_t)N * H * (W + 8) * 4 * 2));
+    CK(cudaMemset(d_xp, 0xFF, (size_t)N * H * (W + 8) * 4 * 2));
+    CK(cudaMalloc(&d_wpk, 64 * 224 * 2));
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    CK(cudaMemset(d_out, 0xFF, ref.v.size() * 2));
+    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, 148), 256>>>(d_x, d_xp, N, H, W);
+    pack_stem_w_kernel<<<(64 * 224 + 255) / 256, 256>>>(d_w, d_wpk);
+    EpilogueDesc ep;
+    ep.relu = 1;
+    IgemmLaunch L;
+    std::string e = build_stem(g_ctx, L, d_wpk, d_xp, N, H, W, d_out, ep);
+    if (!e.empty()) {
+        printf("[FAIL] %s: build: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    CK(igemm_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (check_err_flag(name)) return;
+    std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+    report(name, compare(got, ref.v), 0.012, got, ref.v, 64);
+    cudaFree(d_x); cudaFree(d_w); cudaFree(d_xp); cudaFree(d_wpk); cudaFree(d_out);
+}
+
+static void case_dec1(const char* name, int N, int Hl, int Wl, int cup, int cskip, int cout) {
+    HostT low(N, Hl, Wl, cup);
+    fill_rand_bf16(low.v, 1.0f);
+    HostT skip(N, 2 * Hl, 2 * Wl, cskip > 0 ? cskip : 1);
+    fill_rand_bf16(skip.v, 1.0f);
+    const int cin = cup + cskip;
+    std::vector<float> w((size_t)cout * cin * 9);
+    const float ws = 1.0f / sqrtf((float)cin * 9);
+    for (auto& x : w) x = frand() * ws;
+    // reference: materialise upsample + concat, full-precision weights (the fused kernel sums weights before rounding)
+    HostT cat(N, 2 * Hl, 2 * Wl, cin);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < 2 * Hl; ++h)
+            for (int ww = 0; ww < 2 * Wl; ++ww) {
+                for (int c = 0; c < cup; ++c) cat.at(n, h, ww, c) = low.get(n, h / 2, ww / 2, c);
+                for (int c = 0; c < cskip; ++c) cat.at(n, h, ww, cup + c) = skip.get(n, h, ww, c);
+            }
+    HostT ref = cpu_conv(cat, w, cout, 3, 1, 1);
+    for (auto& v : ref.v) v = fmaxf(v, 0.f);
+    __nv_bfloat16* d_low = to_dev_bf16(low.v);
+    __nv_bfloat16* d_skip = to_dev_bf16(skip.v);
+    float* d_w = to_dev_f32(w);
+    const long long kt = 9 * cskip + 4 * cup;
+    __nv_bfloat16 *d_wpk, *d_out;
+    CK(cudaMalloc(&d_wpk, 4 * cout * kt * 2));
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    CK(cudaMemset(d_out, 0xFF, ref.v.size() * 2));
+    pack_dec1_w_kernel<<<64, 256>>>(d_w, d_wpk, cout, cup, cskip);
+    NetSpec::Dec d;
+    d.c1 = d.c2 = -1;
+    d.cup = cup; d.cskip = cskip; d.cout = cout;
+    EpilogueDesc ep;
+    ep.relu = 1;
+    for (int par = 0; par < 4; ++par) {
+        IgemmLaunch L;
+        std::string e = build_dec1(g_ctx, L, d, d_wpk, par, d_low, cskip ? d_skip : nullptr, N, Hl, Wl, d_out, ep);
+        if (!e.empty()) {
+            printf("[FAIL] %s: build: %s\n", name, e.c_str());
+            g_fail++;
+            return;
+        }
+        CK(igemm_launch(L, 0));
+    }
+    CK(cudaDeviceSynchronize());
+    if (check_err_flag(name)) return;
+    std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+    report(name, compare(got, ref.v), 0.02, got, ref.v, cout);
+    cudaFree(d_low); cudaFree(d_skip); cudaFree(d_w); cudaFree(d_wpk); cudaFree(d_out);
+}
+
+static void case_maxpool(const char* name, int N, int H, int W, int C) {
+    HostT in(N, H, W, C);
+    fill_rand_bf16(in.v, 1.0f);
+    HostT ref(N, H / 2, W / 2, C);
+    for (int n = 0; n < N; ++n)
+        for (int ho = 0; ho < H / 2; ++ho)
+            for (int wo = 0; wo < W / 2; ++wo)
+                for (int c = 0; c < C; ++c) {
+                    float m = -INFINITY;
+                    for (int r = 0; r < 3; ++r)
+                        for (int s = 0; s < 3; ++s) {
+                            const int h = 2 * ho - 1 + r, w = 2 * wo - 1 + s;
+                            if (h >= 0 && h < H && w >= 0 && w < W) m = fmaxf(m, in.at(n, h, w, c));
+                        }
+                    ref.at(n, ho, wo, c) = m;
+                }
+    __nv_bfloat16* d_in = to_dev_bf16(in.v);
+    __nv_bfloat16* d_out;
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    maxpool3x3s2_kernel<<<ew_grid((long long)ref.v.size() / 8, 256, 148), 256>>>(d_in, d_out, N, H, W, C);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+    report(name, compare(got, ref.v), 0.0, got, ref.v, C);
+    cudaFree(d_in); cudaFree(d_out);
+}
+
+static void case_head(const char* name, int N, int H, int W) {
+    HostT in(N, H, W, 16);
+    fill_rand_bf16(in.v, 1.0f);
+    std::vector<float> w(144), wb(145);
+    for (auto& x : w) x = frand() * 0.1f;
+    const float bias = 0.05f;
+    HostT ref = cpu_conv(in, w, 1, 3, 1, 1);
+    for (auto& v : ref.v) v += bias;
+    __nv_bfloat16* d_in = to_dev_bf16(in.v);
+    for (int i = 0; i < 144; ++i) wb[i] = w[i];
+    wb[144] = bias;
+    float* d_w = to_dev_f32(wb);
+    float* d_out;
+    uint8_t* d_mask;
+    CK(cudaMalloc(&d_out, ref.v.size() * 4));
+    CK(cudaMalloc(&d_mask, ref.v.size()));
+    dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
+    head_conv_kernel<<<grid, 256>>>(d_in, d_w, d_w + 144, d_out, nullptr, d_mask, 0.f, N, H, W);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> got(ref.v.size());
+    CK(cudaMemcpy(got.data(), d_out, got.size() * 4, cudaMemcpyDeviceToHost));
+    report(name, compare(got, ref.v), 1e-4, got, ref.v, 1);
+    std::vector<uint8_t> mk(ref.v.size());
+    CK(cudaMemcpy(mk.data(), d_mask, mk.size(), cudaMemcpyDeviceToHost));
+    size_t bad = 0;
+    for (size_t i = 0; i < mk.size(); ++i) bad += (mk[i] != (got[i] >= 0.f ? 255 : 0));
+    printf("[%s] %s [mask] mismatches %zu\n", bad ? "FAIL" : "PASS", name, bad);
+    g_fail += bad ? 1 : 0;
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_mask);
+}
+
+// ------------------------------------------------------------------------------------------------ timing
+static void bench_conv(const char* name, int N, int H, int W, int cin, int cout, int k, int stride, int iters) {
+    const size_t in_e = (size_t)N * H * W * cin, out_e = (size_t)N * (H / stride) * (W / stride) * cout;
+    __nv_bfloat16 *d_in, *d_out, *d_wpk;
+    CK(cudaMalloc(&d_in, in_e * 2));
+    CK(cudaMalloc(&d_out, out_e * 2));
+    CK(cudaMalloc(&d_wpk, (size_t)cout * cin * k * k * 2));
+    CK(cudaMemset(d_in, 0x3C, in_e * 2));  // 0x3C3C ~ 0.0115
+    CK(cudaMemset(d_wpk, 0x3C, (size_t)cout * cin * k * k * 2));
+    ConvRef c;
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride;
+    EpilogueDesc ep;
+    ep.relu = 1;
+    IgemmLaunch L;
+    std::string e = build_conv(g_ctx, L, c, d_wpk, d_in, N, H, W, d_out, ep);
+    if (!e.empty()) {
+        printf("[FAIL] bench %s: %s\n", name, e.c_str());
+        return;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) CK(igemm_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) CK(igemm_launch(L, 0));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double flops = 2.0 * N * (H / stride) * (W / stride) * (double)cout * cin * k * k;
+    const double bytes = (in_e + out_e) * 2.0;
+    printf("[BENCH] %-34s %8.1f us  %7.1f TFLOP/s  %7.1f GB/s(min traffic)  grid %d stages %d\n", name, ms * 1e3,
+           flops / ms * 1e-9, bytes / ms * 1e-6, L.grid, L.p.stages);
+    check_err_flag(name);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_wpk);
+}
+
+int main(int argc, char** argv) {
+    const char* filt = argc > 1 ? argv[1] : "";
+    auto want = [&](const char* n) { return strstr(n, filt) != nullptr; };
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("device: %s sm_%d%d, %d SMs, smem/block optin %zu\n", prop.name, prop.major, prop.minor,
+           prop.multiProcessorCount, prop.sharedMemPerBlockOptin);
+    g_ctx = new Ctx();
+    g_ctx->num_sms = prop.multiProcessorCount;
+    CK(cudaMalloc(&g_ctx->d_err, 4));
+    CK(cudaMemset(g_ctx->d_err, 0, 4));
+
+    if (want("pool")) case_maxpool("maxpool 2x32x32x64", 2, 32, 32, 64);
+    if (want("head")) case_head("head 2x40x48", 2, 40, 48);
+    // ---- igemm basic: smallest possible pipeline first
+    if (want("conv")) {
+        case_conv("conv 1x1 s1 64->64 1x8x16 (1 chunk)", 1, 8, 16, 64, 64, 1, 1, false, false, false, false);
+        case_conv("conv 3x3 s1 64->64 2x32x32", 2, 32, 32, 64, 64, 3, 1, false, false, false, false);
+        case_conv("conv 3x3 s1 64->64 +ss+relu", 2, 32, 32, 64, 64, 3, 1, false, true, true, false);
+        case_conv("conv 3x3 s1 64->64 +res+relu", 2, 32, 32, 64, 64, 3, 1, true, true, true, false);
+        case_conv("conv 3x3 s1 64->64 +stats", 2, 32, 32, 64, 64, 3, 1, false, false, false, true);
+        case_conv("conv 3x3 s1 128->128 1x16x16", 1, 16, 16, 128, 128, 3, 1, false, true, true, false);
+        case_conv("conv 3x3 s1 256->256 2x16x16", 2, 16, 16, 256, 256, 3, 1, true, true, true, true);
+        case_conv("conv 3x3 s1 512->512 2x16x16", 2, 16, 16, 512, 512, 3, 1, true, true, true, false);
+        case_conv("conv 3x3 s1 32->32 1x32x32 (SW64)", 1, 32, 32, 32, 32, 3, 1, false, true, true, true);
+        case_conv("conv 3x3 s1 16->16 1x32x32 (SW32)", 1, 32, 32, 16, 16, 3, 1, false, true, true, true);
+        case_conv("conv 3x3 s2 64->128 2x32x32", 2, 32, 32, 64, 128, 3, 2, false, true, true, false);
+        case_conv("conv 1x1 s2 64->128 2x32x32", 2, 32, 32, 64, 128, 1, 2, false, false, true, false);
+        case_conv("conv 3x3 s1 64->64 3x8x8 (bn=2,partial)", 3, 8, 8, 64, 64, 3, 1, true, true, true, true);
+        case_conv("conv 3x3 s1 64->64 1x24x40 (partial)", 1, 24, 40, 64, 64, 3, 1, false, true, true, true);
+        case_conv("conv 3x3 s1 64->64 5x64x64 (multi-tile/CTA)", 5, 64, 64, 64, 64, 3, 1, true, true, true, true);
+        case_conv("conv 3x3 s1 256->512 9x16x16", 9, 16, 16, 256, 512, 3, 1, false, true, true, false);
+    }
+    if (want("stem")) {
+        case_stem("stem 7x7 s2 3->64 2x64x64", 2, 64, 64);
+        case_stem("stem 7x7 s2 3->64 1x96x160", 1, 96, 160);
+    }
+    if (want("dec1")) {
+        case_dec1("dec1 up64+skip64->32 2x16x16", 2, 16, 16, 64, 64, 32);
+        case_dec1("dec1 up128+skip64->64 1x16x16", 1, 16, 16, 128, 64, 64);
+        case_dec1("dec1 up512+skip256->256 1x8x8", 1, 8, 8, 512, 256, 256);
+        case_dec1("dec1 up32->16 (no skip) 2x16x32", 2, 16, 32, 32, 0, 16);
+    }
+    if (want("bench")) {
+        bench_conv("L1 3x3 64->64 @128^2 x32", 32, 128, 128, 64, 64, 3, 1, 20);
+        bench_conv("L2 3x3 128->128 @64^2 x32", 32, 64, 64, 128, 128, 3, 1, 20);
+        bench_conv("L3 3x3 256->256 @32^2 x32", 32, 32, 32, 256, 256, 3, 1, 20);
+        bench_conv("L4 3x3 512->512 @16^2 x32", 32, 16, 16, 512, 512, 3, 1, 20);
+        bench_conv("D3 3x3 32->32 @256^2 x32", 32, 256, 256, 32, 32, 3, 1, 10);
+        bench_conv("D4 3x3 16->16 @512^2 x32", 32, 512, 512, 16, 16, 3, 1, 10);
+    }
+    printf("SELFTEST %s: %d checks, %d failures\n", g_fail ? "FAILED" : "OK", g_run, g_fail);
+    return g_fail ? 1 : 0;
+}

@@ -1,0 +1,351 @@
+// Multi-source "tap table" implicit-GEMM convolution on tcgen05 (sm_100a).
+//
+//   D[pixel, co] = sum over taps t, channels c of  SRC_t[pixel*mul + (dw_t, dh_t), c0_t + c] * Wpk[co, k(t, c)]
+//
+// One kernel covers every conv of the U-Net hot path (SURVEY.md section 8a rows A1, A3-A6 and their dgrads):
+//   3x3 s1/s2, 1x1 s2, the 7x7 s2 stem (7 row-taps over an overlapped-window view), the decoder's fused
+//   nearest-2x-upsample + concat conv (two sources, parity decomposition) and stride-2 dgrad (strided output view).
+// Operands are NHWC bf16; A tiles are 128 output pixels (bw x bh x bn box) x chunk channels fetched by 4-D TMA
+// tile loads whose out-of-bounds zero fill implements the conv padding; B tiles are [ntile x chunk] slices of the
+// packed K-major weight matrix; the fp32 accumulator lives in TMEM (double buffered); the epilogue applies
+// scale/shift (folded BN), residual add and ReLU, or emits raw output + per-channel batch statistics partials,
+// and writes bf16 through a swizzled smem staging tile with TMA stores (which clip partial tiles).
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+constexpr int kMaxTaps = 16;
+constexpr int kIgemmThreads = 192;  // warp0: TMA producer, warp1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct IgemmTap {
+    int16_t dw, dh;    // coordinate offset in source pixels
+    int16_t c0;        // first source channel of this tap
+    int16_t nchunks;   // number of chunk_elems-wide K chunks
+    int32_t src;       // which A tensor map (0/1)
+};
+
+struct IgemmParams {
+    int tiles_w, tiles_h, tiles_n, n_tiles;  // M-tile grid (w,h,image) and number of Cout tiles
+    int bw, bh, bn;                          // pixels per tile along w, h, image: bw*bh*bn == 128
+    int ntile;                               // UMMA N: 16..256, multiple of 16
+    int chunk_elems;                         // K elements per pipeline stage: 16, 32 or 64 (32/64/128-byte swizzle)
+    int stages;
+    int num_taps, total_chunks;
+    IgemmTap taps[kMaxTaps];
+    int mulw[2], mulh[2];                    // source coordinate = tile origin * mul + tap offset
+    int Wo, Ho, Nimg, cout;                  // logical output extent (masking) and channel count
+    int out_cblk;                            // channels per staging/store block = min(64, ntile)
+    const float* scale;                      // [cout] or nullptr (identity)
+    const float* shift;                      // [cout] or nullptr
+    int relu;
+    const __nv_bfloat16* residual;           // NHWC-strided bf16 or nullptr
+    long long res_sw, res_sh, res_sn;        // element strides of the residual
+    float* stats;                            // [m_tiles][cout][2] (sum, sumsq of the bf16 output) or nullptr
+    int* err;                                // device error flag (set on pipeline timeout)
+};
+
+// dynamic shared memory carve-up (all offsets relative to a 1024-aligned base)
+struct IgemmSmem {
+    uint32_t a_bytes, b_bytes, stage_bytes, staging_off, staging_bytes, ss_off, part_off, bar_off, total;
+};
+__host__ __device__ inline IgemmSmem igemm_smem(int ntile, int chunk_elems, int stages, int out_cblk) {
+    IgemmSmem s;
+    const uint32_t cb = chunk_elems * 2;
+    s.a_bytes = 128 * cb;
+    s.b_bytes = (ntile * cb + 1023u) & ~1023u;
+    s.stage_bytes = s.a_bytes + s.b_bytes;  // a_bytes is a multiple of 1024 for every chunk size (>= 4 KB)
+    s.staging_off = s.stage_bytes * stages;
+    s.staging_bytes = 128 * out_cblk * 2;   // x2 buffers
+    s.ss_off = s.staging_off + 2 * s.staging_bytes;
+    s.part_off = s.ss_off + 2 * 512 * 4;    // scale/shift for up to 512 channels
+    s.bar_off = s.part_off + 8 * 64 * 2 * 4;  // stats partials [8 groups][64 ch][2]
+    s.total = s.bar_off + (2 * stages + 4) * 8 + 16;
+    return s;
+}
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+             const __grid_constant__ IgemmParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_addr);
+    const IgemmSmem L = igemm_smem(P.ntile, P.chunk_elems, P.stages, P.out_cblk);
+
+    const uint32_t bar0 = base + L.bar_off;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (P.stages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * P.stages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * P.stages + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bar_off + (2 * P.stages + 4) * 8);
+    volatile int* s_abort = reinterpret_cast<volatile int*>(sm + L.bar_off + (2 * P.stages + 4) * 8 + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < 2u * P.ntile) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmD);
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        *s_abort = 0;
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
+        tmem_relinquish();
+    }
+    // per-channel scale/shift -> smem (identity when absent)
+    {
+        float* ss = reinterpret_cast<float*>(sm + L.ss_off);
+        for (int c = threadIdx.x; c < 512; c += blockDim.x) {
+            ss[c] = (P.scale && c < P.cout) ? P.scale[c] : 1.f;
+            ss[512 + c] = (P.shift && c < P.cout) ? P.shift[c] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx = L.a_bytes + P.ntile * P.chunk_elems * 2;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % P.n_tiles;
+                int m = tile / P.n_tiles;
+                const int tw = m % P.tiles_w;
+                m /= P.tiles_w;
+                const int th = m % P.tiles_h;
+                const int tn = m / P.tiles_h;
+                int kidx = 0;
+                for (int t = 0; t < P.num_taps; ++t) {
+                    const IgemmTap tap = P.taps[t];
+                    const CUtensorMap* mp = tap.src ? &tmA1 : &tmA0;
+                    const int cw = tw * P.bw * P.mulw[tap.src] + tap.dw;
+                    const int ch = th * P.bh * P.mulh[tap.src] + tap.dh;
+                    for (int cc = 0; cc < tap.nchunks; ++cc, ++kidx) {
+                        if (!mbar_wait(empty_bar(stage), phase ^ 1)) {
+                            *s_abort = 1;
+                            atomicExch(P.err, 1);
+                            goto role_done;
+                        }
+                        const uint32_t sa = base + stage * L.stage_bytes;
+                        mbar_expect_tx(full_bar(stage), tx);
+                        tma_load_4d(sa, mp, full_bar(stage), tap.c0 + cc * P.chunk_elems, cw, ch, tn * P.bn);
+                        tma_load_2d(sa + L.a_bytes, &tmB, full_bar(stage), kidx * P.chunk_elems, nt * P.ntile);
+                        if (++stage == P.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (single thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const uint32_t idesc = umma_idesc_bf16(128, P.ntile, 0, 0);
+            const uint32_t sbo = 8u * P.chunk_elems * 2;
+            const uint32_t layout = (P.chunk_elems == 64) ? 2u : (P.chunk_elems == 32 ? 4u : 6u);
+            const int ksteps = P.chunk_elems / 16;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1)) {
+                    *s_abort = 1;
+                    atomicExch(P.err, 2);
+                    goto role_done;
+                }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * P.ntile;
+                uint32_t accum = 0;
+                for (int kc = 0; kc < P.total_chunks; ++kc) {
+                    if (!mbar_wait(full_bar(stage), phase)) {
+                        *s_abort = 1;
+                        atomicExch(P.err, 3);
+                        goto role_done;
+                    }
+                    tc_fence_after();
+                    const uint32_t sa = base + stage * L.stage_bytes;
+                    const uint32_t sb = sa + L.a_bytes;
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t ad = umma_desc(sa + k * 32, 16, sbo, layout);
+                        const uint64_t bd = umma_desc(sb + k * 32, 16, sbo, layout);
+                        umma_bf16(d_tmem, ad, bd, idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
+                    if (++stage == P.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ================================================================= epilogue (4 warps, one TMEM lane quadrant each)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;          // tile row == TMEM lane == pixel index inside the tile
+        const int et = threadIdx.x - 64;        // 0..127
+        const float* ss = reinterpret_cast<const float*>(sm + L.ss_off);
+        float* part = reinterpret_cast<float*>(sm + L.part_off);
+        const int cblk = P.out_cblk;
+        const int nblk = P.ntile / cblk;
+        const uint32_t row_bytes = cblk * 2;
+        const uint32_t swz_mask = (cblk >= 64) ? 7u : (cblk == 32 ? 3u : 1u);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t blk_counter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % P.n_tiles;
+            int m = tile / P.n_tiles;
+            const int m_tile = m;
+            const int tw = m % P.tiles_w;
+            m /= P.tiles_w;
+            const int th = m % P.tiles_h;
+            const int tn = m / P.tiles_h;
+            const int pw = tw * P.bw + row % P.bw;
+            const int ph = th * P.bh + (row / P.bw) % P.bh;
+            const int pn = tn * P.bn + row / (P.bw * P.bh);
+            const bool valid = (pw < P.Wo) && (ph < P.Ho) && (pn < P.Nimg);
+
+            if (!mbar_wait(tfull_bar(acc), acc_phase)) {
+                *s_abort = 1;
+                atomicExch(P.err, 4);
+                goto role_done;
+            }
+            tc_fence_after();
+            for (int cb = 0; cb < nblk; ++cb, ++blk_counter) {
+                const int cbase = nt * P.ntile + cb * cblk;  // first output channel of this block
+                uint8_t* sbuf = sm + L.staging_off + (blk_counter & 1) * L.staging_bytes;
+                if (et == 0) tma_wait_read<1>();  // the store issued two blocks ago has finished reading this buffer
+                named_bar_sync(1, 128);
+                for (int h0 = 0; h0 < cblk; h0 += 32) {
+                    const int ncol = (cblk - h0) < 32 ? (cblk - h0) : 32;  // 16 or 32
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * P.ntile + cb * cblk + h0;
+                    if (ncol == 32) {
+                        tmem_ld32(taddr, r);
+                    } else {
+                        uint32_t r16[16];
+                        tmem_ld16(taddr, r16);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r[i] = r16[i];
+#pragma unroll
+                        for (int i = 16; i < 32; ++i) r[i] = 0;
+                    }
+                    tmem_ld_wait();
+                    if (cb == nblk - 1 && h0 + 32 >= cblk) {
+                        // last TMEM read of this accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    const __nv_bfloat16* resp = nullptr;
+                    if (P.residual && valid)
+                        resp = P.residual + pn * P.res_sn + ph * P.res_sh + pw * P.res_sw + cbase + h0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // 4 x (8 channels = 16 B)
+                        if (j * 8 >= ncol) break;
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int c = cbase + h0 + j * 8 + i;
+                            v[i] = __uint_as_float(r[j * 8 + i]) * ss[c] + ss[512 + c];
+                        }
+                        if (resp) {
+                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + j * 8));
+                            v[0] += bf16_lo(rv.x); v[1] += bf16_hi(rv.x);
+                            v[2] += bf16_lo(rv.y); v[3] += bf16_hi(rv.y);
+                            v[4] += bf16_lo(rv.z); v[5] += bf16_hi(rv.z);
+                            v[6] += bf16_lo(rv.w); v[7] += bf16_hi(rv.w);
+                        }
+                        if (P.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (!valid) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                        }
+                        uint4 o;
+                        o.x = pack_bf16(v[0], v[1]);
+                        o.y = pack_bf16(v[2], v[3]);
+                        o.z = pack_bf16(v[4], v[5]);
+                        o.w = pack_bf16(v[6], v[7]);
+                        uint32_t off = row * row_bytes + (h0 * 2 + j * 16);
+                        off ^= ((off >> 7) & swz_mask) << 4;
+                        *reinterpret_cast<uint4*>(sbuf + off) = o;
+                    }
+                }
+                fence_async_smem();
+                named_bar_sync(2, 128);
+                if (et == 0) {
+                    tma_store_4d(&tmD, smem_u32(sbuf), cbase, tw * P.bw, th * P.bh, tn * P.bn);
+                    tma_commit();
+                }
+                if (P.stats) {
+                    // per-channel sum / sum of squares over the tile's 128 pixels, from the bf16 values just staged
+                    const int ngrp = 128 / cblk;
+                    const int c = et % cblk, g = et / cblk;
+                    float s1 = 0.f, s2 = 0.f;
+                    for (int rr = g; rr < 128; rr += ngrp) {
+                        uint32_t off = rr * row_bytes + c * 2;
+                        off ^= ((off >> 7) & swz_mask) << 4;
+                        const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sbuf + off));
+                        s1 += x;
+                        s2 += x * x;
+                    }
+                    part[(g * 64 + c) * 2 + 0] = s1;
+                    part[(g * 64 + c) * 2 + 1] = s2;
+                    named_bar_sync(3, 128);
+                    if (et < cblk) {
+                        float t1 = 0.f, t2 = 0.f;
+                        for (int gg = 0; gg < ngrp; ++gg) {
+                            t1 += part[(gg * 64 + et) * 2 + 0];
+                            t2 += part[(gg * 64 + et) * 2 + 1];
+                        }
+                        float* dst = P.stats + (static_cast<size_t>(m_tile) * P.cout + cbase + et) * 2;
+                        dst[0] = t1;
+                        dst[1] = t2;
+                    }
+                    // `part` is rewritten only after the next block's named_bar_sync(1), which orders it after these reads
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+        if (et == 0) tma_wait_all<0>();  // all output stores complete before the CTA exits
+    }
+role_done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace ub

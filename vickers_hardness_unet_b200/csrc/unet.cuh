@@ -1,0 +1,543 @@
+// U-Net(ResNet-34) network description + inference orchestration on top of the igemm / elementwise kernels.
+// Tensor table order == the state_dict order of smp.Unet("resnet34"), parameters and
+// buffers each in their own flat fp32 array owned by the caller (PyTorch).
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv_plan.cuh"
+#include "ops.cuh"
+
+namespace ub {
+
+struct TensorInfo {
+    std::string name;
+    int ndim;
+    int shape[4];
+    long long offset;  // element offset inside its flat array
+    int kind;          // 0 = parameter (fp32 flat params), 1 = fp32 buffer (flat buffers), 2 = int64 counter (index)
+    long long numel() const {
+        long long n = 1;
+        for (int i = 0; i < ndim; ++i) n *= shape[i];
+        return n;
+    }
+};
+
+struct BnRef {
+    int c = 0;
+    long long gamma = -1, beta = -1;  // offsets into flat params
+    long long mean = -1, var = -1;    // offsets into flat buffers
+    long long fold = -1;              // offset into the folded scale/shift arrays
+    int counter = -1;
+};
+struct ConvRef {
+    std::string name;
+    int cin = 0, cout = 0, k = 0, stride = 1;
+    long long w = -1;     // offset into flat params
+    long long bias = -1;  // head only
+    int bn = -1;          // index into bns
+    long long wpk = -1;   // offset (elements) into the packed bf16 weight arena
+    long long wpk_elems = 0;
+};
+
+struct NetSpec {
+    std::vector<TensorInfo> tensors;
+    std::vector<ConvRef> convs;
+    std::vector<BnRef> bns;
+    long long n_params = 0, n_buffers = 0;
+    int n_counters = 0;
+    long long fold_total = 0, wpk_total = 0;
+    // indices
+    int stem = -1, head = -1;
+    struct Block { int c1, c2, ds; };
+    std::vector<Block> enc_blocks[4];
+    struct Dec { int c1, c2; int cup, cskip, cout; };
+    std::vector<Dec> dec;
+
+    int add_bn(const std::string& prefix, int c) {
+        BnRef b;
+        b.c = c;
+        b.gamma = n_params;
+        tensors.push_back({prefix + ".weight", 1, {c, 0, 0, 0}, n_params, 0});
+        n_params += c;
+        b.beta = n_params;
+        tensors.push_back({prefix + ".bias", 1, {c, 0, 0, 0}, n_params, 0});
+        n_params += c;
+        b.mean = n_buffers;
+        tensors.push_back({prefix + ".running_mean", 1, {c, 0, 0, 0}, n_buffers, 1});
+        n_buffers += c;
+        b.var = n_buffers;
+        tensors.push_back({prefix + ".running_var", 1, {c, 0, 0, 0}, n_buffers, 1});
+        n_buffers += c;
+        b.counter = n_counters;
+        tensors.push_back({prefix + ".num_batches_tracked", 0, {0, 0, 0, 0}, n_counters, 2});
+        n_counters += 1;
+        b.fold = fold_total;
+        fold_total += c;
+        bns.push_back(b);
+        return int(bns.size()) - 1;
+    }
+    int add_conv(const std::string& wname, int cin, int cout, int k, int stride) {
+        ConvRef c;
+        c.name = wname;
+        c.cin = cin; c.cout = cout; c.k = k; c.stride = stride;
+        c.w = n_params;
+        tensors.push_back({wname, 4, {cout, cin, k, k}, n_params, 0});
+        n_params += (long long)cout * cin * k * k;
+        convs.push_back(c);
+        return int(convs.size()) - 1;
+    }
+
+    NetSpec() {
+        stem = add_conv("encoder.conv1.weight", 3, 64, 7, 2);
+        convs[stem].bn = add_bn("encoder.bn1", 64);
+        const int nblocks[4] = {3, 4, 6, 3};
+        const int planes[4] = {64, 128, 256, 512};
+        int inpl = 64;
+        for (int l = 0; l < 4; ++l) {
+            for (int b = 0; b < nblocks[l]; ++b) {
+                const std::string p = "encoder.layer" + std::to_string(l + 1) + "." + std::to_string(b);
+                const int stride = (b == 0 && l > 0) ? 2 : 1;
+                Block blk;
+                blk.c1 = add_conv(p + ".conv1.weight", inpl, planes[l], 3, stride);
+                convs[blk.c1].bn = add_bn(p + ".bn1", planes[l]);
+                blk.c2 = add_conv(p + ".conv2.weight", planes[l], planes[l], 3, 1);
+                convs[blk.c2].bn = add_bn(p + ".bn2", planes[l]);
+                blk.ds = -1;
+                if (stride != 1 || inpl != planes[l]) {
+                    blk.ds = add_conv(p + ".downsample.0.weight", inpl, planes[l], 1, stride);
+                    convs[blk.ds].bn = add_bn(p + ".downsample.1", planes[l]);
+                }
+                inpl = planes[l];
+                enc_blocks[l].push_back(blk);
+            }
+        }
+        const int cin[5] = {512, 256, 128, 64, 32}, cskip[5] = {256, 128, 64, 64, 0}, co[5] = {256, 128, 64, 32, 16};
+        for (int i = 0; i < 5; ++i) {
+            const std::string p = "decoder.blocks." + std::to_string(i);
+            Dec d;
+            d.cup = cin[i]; d.cskip = cskip[i]; d.cout = co[i];
+            d.c1 = add_conv(p + ".conv1.0.weight", cin[i] + cskip[i], co[i], 3, 1);
+            convs[d.c1].bn = add_bn(p + ".conv1.1", co[i]);
+            d.c2 = add_conv(p + ".conv2.0.weight", co[i], co[i], 3, 1);
+            convs[d.c2].bn = add_bn(p + ".conv2.1", co[i]);
+            dec.push_back(d);
+        }
+        head = add_conv("segmentation_head.0.weight", 16, 1, 3, 1);
+        convs[head].bias = n_params;
+        tensors.push_back({"segmentation_head.0.bias", 1, {1, 0, 0, 0}, n_params, 0});
+        n_params += 1;
+
+        // packed bf16 weight arena (forward operands)
+        for (size_t i = 0; i < convs.size(); ++i) {
+            ConvRef& c = convs[i];
+            if ((int)i == head) continue;
+            long long n;
+            if ((int)i == stem) n = 64 * 224;
+            else n = (long long)c.cout * c.cin * c.k * c.k;
+            bool is_dec1 = false;
+            for (auto& d : dec) if (d.c1 == (int)i) { n = 4ll * d.cout * (9 * d.cskip + 4 * d.cup); is_dec1 = true; }
+            (void)is_dec1;
+            c.wpk = wpk_total;
+            c.wpk_elems = n;
+            wpk_total += (n + 63) & ~63ll;  // keep every matrix 128 B aligned
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ runtime context
+struct Ctx {
+    NetSpec spec;
+    int device = 0, num_sms = 148;
+    int max_batch = 0, H = 0, W = 0;
+    std::string last_error;
+    int* d_err = nullptr;
+    // caches owned by the library
+    __nv_bfloat16* wpk = nullptr;    // packed forward weights
+    float* fold_scale = nullptr;     // [fold_total]
+    float* fold_shift = nullptr;
+    float* head_w = nullptr;         // fp32 copy [144] + bias [1]
+    bool weights_ready = false;
+    // activation arena
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+
+    struct InferPlan {
+        int N = 0;
+        __nv_bfloat16* xp = nullptr;
+        __nv_bfloat16* head_in = nullptr;
+        std::vector<std::function<cudaError_t(cudaStream_t)>> steps;  // everything between input pack and head
+        int launches = 0;
+    };
+    std::map<int, InferPlan> infer_plans;  // keyed by batch size
+    // staging for the host-buffer entry point (unetb200_infer_host)
+    float* io_x = nullptr;
+    float* io_f = nullptr;
+    uint8_t* io_m = nullptr;
+    cudaStream_t io_stream = nullptr;
+
+    ~Ctx() {
+        cudaFree(io_x);
+        cudaFree(io_f);
+        cudaFree(io_m);
+        if (io_stream) cudaStreamDestroy(io_stream);
+        cudaFree(d_err);
+        cudaFree(wpk);
+        cudaFree(fold_scale);
+        cudaFree(fold_shift);
+        cudaFree(head_w);
+        cudaFree(arena);
+    }
+};
+
+#define UB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                  \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+inline int ctx_fail(Ctx* ctx, const std::string& msg) {
+    ctx->last_error = msg;
+    return 1;
+}
+
+// Re-pack fp32 master weights (flat params / buffers in state-dict order) into the bf16 operand caches and fold BN.
+inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers, cudaStream_t st) {
+    const NetSpec& S = ctx->spec;
+    for (size_t i = 0; i < S.convs.size(); ++i) {
+        const ConvRef& c = S.convs[i];
+        if ((int)i == S.head) {
+            UB_CUDA(cudaMemcpyAsync(ctx->head_w, params + c.w, 144 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            UB_CUDA(cudaMemcpyAsync(ctx->head_w + 144, params + c.bias, sizeof(float), cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        __nv_bfloat16* dst = ctx->wpk + c.wpk;
+        if ((int)i == S.stem) {
+            pack_stem_w_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(params + c.w, dst);
+        } else {
+            const NetSpec::Dec* dd = nullptr;
+            for (auto& d : S.dec) if (d.c1 == (int)i) dd = &d;
+            if (dd) {
+                pack_dec1_w_kernel<<<ew_grid(c.wpk_elems, 256, ctx->num_sms), 256, 0, st>>>(params + c.w, dst, dd->cout,
+                                                                                          dd->cup, dd->cskip);
+            } else {
+                pack_conv_w_kernel<<<ew_grid(c.wpk_elems, 256, ctx->num_sms), 256, 0, st>>>(params + c.w, dst, c.cout,
+                                                                                          c.cin, c.k, c.k, 0);
+            }
+        }
+    }
+    for (const BnRef& b : S.bns) {
+        bn_fold_kernel<<<(b.c + 127) / 128, 128, 0, st>>>(params + b.gamma, params + b.beta, buffers + b.mean,
+                                                         buffers + b.var, 1e-5f, ctx->fold_scale + b.fold,
+                                                         ctx->fold_shift + b.fold, b.c);
+    }
+    UB_CUDA(cudaGetLastError());
+    ctx->weights_ready = true;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------- conv launch builders
+inline void taps_3x3(std::vector<IgemmTap>& taps, int src, int cin, int c0, int chunk, int off_h, int off_w) {
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s) {
+            IgemmTap t;
+            t.dw = int16_t(s - 1 + off_w);
+            t.dh = int16_t(r - 1 + off_h);
+            t.c0 = int16_t(c0);
+            t.nchunks = int16_t(cin / chunk);
+            t.src = src;
+            taps.push_back(t);
+        }
+}
+inline int chunk_for(int cin) { return cin >= 64 ? 64 : cin; }
+
+// plain k x k conv (k = 1 or 3), stride 1 or 2, NHWC in -> NHWC out
+inline std::string build_conv(Ctx* ctx, IgemmLaunch& L, const ConvRef& c, const __nv_bfloat16* wpk, const void* in,
+                              int N, int Hin, int Win, void* out, const EpilogueDesc& ep) {
+    const int chunk = chunk_for(c.cin);
+    if (c.cin % chunk) return "cin not divisible by chunk";
+    SrcDesc s;
+    s.v = nhwc_view(in, N, Hin, Win, c.cin);
+    s.es_w = s.es_h = c.stride;
+    std::vector<IgemmTap> taps;
+    if (c.k == 3) {
+        taps_3x3(taps, 0, c.cin, 0, chunk, 0, 0);
+    } else {
+        IgemmTap t;
+        t.dw = 0; t.dh = 0; t.c0 = 0; t.nchunks = int16_t(c.cin / chunk); t.src = 0;
+        taps.push_back(t);
+    }
+    const int Ho = Hin / c.stride, Wo = Win / c.stride;
+    View4 o = nhwc_view(out, N, Ho, Wo, c.cout);
+    return igemm_build(L, &s, 1, taps.data(), (int)taps.size(), chunk, wpk, c.cin * c.k * c.k, c.cout, o, ep,
+                       ctx->d_err, ctx->num_sms);
+}
+
+// 7x7 s2 stem over the packed input xp [N][H][W+8][4]: 7 row taps, each a 32-element (8 px x 4 ch) window.
+inline std::string build_stem(Ctx* ctx, IgemmLaunch& L, const __nv_bfloat16* wpk, const void* xp, int N, int H, int W,
+                              void* out, const EpilogueDesc& ep) {
+    SrcDesc s;
+    s.v.ptr = xp;
+    s.v.C = 32;
+    s.v.W = W / 2;           // one window per output column, 16 B apart (overlapping)
+    s.v.H = H;
+    s.v.N = N;
+    s.v.sW = 8;
+    s.v.sH = (long long)(W + 8) * 4;
+    s.v.sN = (long long)H * (W + 8) * 4;
+    s.es_w = 1;
+    s.es_h = 2;
+    std::vector<IgemmTap> taps;
+    for (int r = 0; r < 7; ++r) {
+        IgemmTap t;
+        t.dw = 0; t.dh = int16_t(r - 3); t.c0 = 0; t.nchunks = 1; t.src = 0;
+        taps.push_back(t);
+    }
+    View4 o = nhwc_view(out, N, H / 2, W / 2, 64);
+    return igemm_build(L, &s, 1, taps.data(), 7, 32, wpk, 224, 64, o, ep, ctx->d_err, ctx->num_sms);
+}
+
+// decoder conv1 for one output parity: sources = skip (full res, traversal stride 2) and low-res x (stride 1).
+inline std::string build_dec1(Ctx* ctx, IgemmLaunch& L, const NetSpec::Dec& d, const __nv_bfloat16* wpk_all, int par,
+                              const void* low, const void* skip, int N, int Hl, int Wl, void* out,
+                              const EpilogueDesc& ep) {
+    const int ph = par >> 1, pw = par & 1;
+    const int minc = (d.cskip && d.cskip < d.cup) ? d.cskip : d.cup;
+    const int chunk = chunk_for(minc);
+    const int kt = 9 * d.cskip + 4 * d.cup;
+    SrcDesc s[2];
+    std::vector<IgemmTap> taps;
+    int nsrc = 1;
+    // source 0: low-res x ; source 1: skip
+    s[0].v = nhwc_view(low, N, Hl, Wl, d.cup);
+    if (d.cskip) {
+        s[1].v = nhwc_view(skip, N, Hl * 2, Wl * 2, d.cskip);
+        s[1].es_w = s[1].es_h = 2;
+        nsrc = 2;
+        taps_3x3(taps, 1, d.cskip, 0, chunk, ph, pw);
+    }
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            IgemmTap t;
+            t.dh = int16_t(a - 1 + ph);
+            t.dw = int16_t(b - 1 + pw);
+            t.c0 = 0;
+            t.nchunks = int16_t(d.cup / chunk);
+            t.src = 0;
+            taps.push_back(t);
+        }
+    // strided output view: pixels (2i+ph, 2j+pw) of the [N, 2Hl, 2Wl, cout] tensor
+    View4 o;
+    o.ptr = reinterpret_cast<const __nv_bfloat16*>(out) + ((long long)ph * (Wl * 2) + pw) * d.cout;
+    o.C = d.cout; o.W = Wl; o.H = Hl; o.N = N;
+    o.sW = 2ll * d.cout;
+    o.sH = 2ll * (Wl * 2) * d.cout;
+    o.sN = (long long)(Hl * 2) * (Wl * 2) * d.cout;
+    return igemm_build(L, s, nsrc, taps.data(), (int)taps.size(), chunk, wpk_all + (long long)par * d.cout * kt, kt,
+                       d.cout, o, ep, ctx->d_err, ctx->num_sms);
+}
+
+// ------------------------------------------------------------------------------------------------ inference plan
+struct ArenaCarver {
+    uint8_t* base;
+    size_t off = 0, cap;
+    ArenaCarver(uint8_t* b, size_t c) : base(b), cap(c) {}
+    __nv_bfloat16* take(long long elems) {
+        size_t bytes = (size_t(elems) * 2 + 1023) & ~size_t(1023);
+        uint8_t* p = base ? base + off : nullptr;
+        off += bytes;
+        return reinterpret_cast<__nv_bfloat16*>(p);
+    }
+};
+
+// Builds (or sizes, when ctx->arena == nullptr) the launch list for batch N.  Returns "" on success.
+inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_t* arena_needed) {
+    const NetSpec& S = ctx->spec;
+    const int H = ctx->H, W = ctx->W;
+    ArenaCarver A(ctx->arena, ctx->arena_bytes);
+    const bool dry = (ctx->arena == nullptr);
+    plan.N = N;
+    plan.steps.clear();
+    auto fold = [&](int bn, int relu) {
+        EpilogueDesc ep;
+        ep.scale = ctx->fold_scale + S.bns[bn].fold;
+        ep.shift = ctx->fold_shift + S.bns[bn].fold;
+        ep.relu = relu;
+        return ep;
+    };
+    std::string err;
+    auto add_igemm = [&](const IgemmLaunch& L) {
+        plan.steps.push_back([L](cudaStream_t st) { return igemm_launch(L, st); });
+    };
+
+    plan.xp = A.take((long long)N * H * (W + 8) * 4);
+    __nv_bfloat16* f1 = A.take((long long)N * (H / 2) * (W / 2) * 64);
+    if (!dry) {
+        IgemmLaunch L;
+        err = build_stem(ctx, L, ctx->wpk + S.convs[S.stem].wpk, plan.xp, N, H, W, f1, fold(S.convs[S.stem].bn, 1));
+        if (!err.empty()) return "stem: " + err;
+        add_igemm(L);
+    }
+    int h = H / 4, w = W / 4;
+    __nv_bfloat16* cur = A.take((long long)N * h * w * 64);
+    if (!dry) {
+        const int num_sms = ctx->num_sms;
+        const int Hh = H / 2, Wh = W / 2;
+        plan.steps.push_back([=](cudaStream_t st) {
+            maxpool3x3s2_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, num_sms), 256, 0, st>>>(
+                f1, cur, N, Hh, Wh, 64);
+            return cudaGetLastError();
+        });
+    }
+    __nv_bfloat16* feats[5] = {f1, nullptr, nullptr, nullptr, nullptr};  // f1, layer1..4 outputs
+    for (int l = 0; l < 4; ++l) {
+        for (size_t b = 0; b < S.enc_blocks[l].size(); ++b) {
+            const NetSpec::Block& blk = S.enc_blocks[l][b];
+            const ConvRef& c1 = S.convs[blk.c1];
+            const ConvRef& c2 = S.convs[blk.c2];
+            const int ho = h / c1.stride, wo = w / c1.stride;
+            __nv_bfloat16* t = A.take((long long)N * ho * wo * c1.cout);
+            __nv_bfloat16* o = A.take((long long)N * ho * wo * c1.cout);
+            __nv_bfloat16* ident = cur;
+            if (blk.ds >= 0) ident = A.take((long long)N * ho * wo * c1.cout);
+            if (!dry) {
+                IgemmLaunch L;
+                err = build_conv(ctx, L, c1, ctx->wpk + c1.wpk, cur, N, h, w, t, fold(c1.bn, 1));
+                if (!err.empty()) return c1.name + ": " + err;
+                add_igemm(L);
+                if (blk.ds >= 0) {
+                    const ConvRef& cd = S.convs[blk.ds];
+                    err = build_conv(ctx, L, cd, ctx->wpk + cd.wpk, cur, N, h, w, ident, fold(cd.bn, 0));
+                    if (!err.empty()) return cd.name + ": " + err;
+                    add_igemm(L);
+                }
+                EpilogueDesc ep = fold(c2.bn, 1);
+                ep.residual = nhwc_view(ident, N, ho, wo, c1.cout);
+                err = build_conv(ctx, L, c2, ctx->wpk + c2.wpk, t, N, ho, wo, o, ep);
+                if (!err.empty()) return c2.name + ": " + err;
+                add_igemm(L);
+            }
+            cur = o;
+            h = ho;
+            w = wo;
+        }
+        feats[l + 1] = cur;
+    }
+    // decoder: skips = layer3, layer2, layer1, f1, none
+    __nv_bfloat16* skips[5] = {feats[3], feats[2], feats[1], feats[0], nullptr};
+    for (int i = 0; i < 5; ++i) {
+        const NetSpec::Dec& d = S.dec[i];
+        const ConvRef& c1 = S.convs[d.c1];
+        const ConvRef& c2 = S.convs[d.c2];
+        __nv_bfloat16* t = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
+        __nv_bfloat16* o = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
+        if (!dry) {
+            for (int par = 0; par < 4; ++par) {
+                IgemmLaunch L;
+                err = build_dec1(ctx, L, d, ctx->wpk + c1.wpk, par, cur, skips[i], N, h, w, t, fold(c1.bn, 1));
+                if (!err.empty()) return c1.name + ": " + err;
+                add_igemm(L);
+            }
+            IgemmLaunch L;
+            err = build_conv(ctx, L, c2, ctx->wpk + c2.wpk, t, N, 2 * h, 2 * w, o, fold(c2.bn, 1));
+            if (!err.empty()) return c2.name + ": " + err;
+            add_igemm(L);
+        }
+        cur = o;
+        h *= 2;
+        w *= 2;
+    }
+    plan.head_in = cur;
+    plan.launches = (int)plan.steps.size() + 2;  // + input pack + head
+    if (arena_needed) *arena_needed = A.off;
+    return "";
+}
+
+// logits / prob / mask: any may be null (at least one non-null). x: fp32 NCHW [N,3,H,W] device pointer.
+inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* prob, uint8_t* mask, float thresh, int N,
+                             cudaStream_t st) {
+    if (!ctx->weights_ready) return ctx_fail(ctx, "forward_infer: weights not loaded");
+    if (N < 1 || N > ctx->max_batch) return ctx_fail(ctx, "forward_infer: batch outside [1, max_batch]");
+    auto it = ctx->infer_plans.find(N);
+    if (it == ctx->infer_plans.end()) {
+        Ctx::InferPlan plan;
+        std::string e = build_infer_plan(ctx, N, plan, nullptr);
+        if (!e.empty()) return ctx_fail(ctx, "plan: " + e);
+        it = ctx->infer_plans.emplace(N, std::move(plan)).first;
+    }
+    Ctx::InferPlan& P = it->second;
+    const int H = ctx->H, W = ctx->W;
+    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P.xp, N, H, W);
+    UB_CUDA(cudaGetLastError());
+    for (auto& s : P.steps) UB_CUDA(s(st));
+    float tl = 0.f;
+    if (thresh <= 0.f) tl = -INFINITY;
+    else if (thresh >= 1.f) tl = INFINITY;
+    else tl = logf(thresh / (1.f - thresh));
+    dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
+    head_conv_kernel<<<grid, 256, 0, st>>>(P.head_in, ctx->head_w, ctx->head_w + 144, logits, prob, mask, tl, N, H, W);
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+inline int ctx_create(Ctx** out, int device, int max_batch, int H, int W, std::string* err) {
+    if (H % 32 || W % 32 || H < 32 || W < 32) {
+        *err = "H and W must be positive multiples of 32";
+        return 1;
+    }
+    if (max_batch < 1) {
+        *err = "max_batch must be >= 1";
+        return 1;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        *err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    if (prop.major != 10) {
+        *err = "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major) +
+               std::to_string(prop.minor);
+        return 1;
+    }
+    Ctx* ctx = new Ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_batch = max_batch;
+    ctx->H = H;
+    ctx->W = W;
+    const NetSpec& S = ctx->spec;
+    bool ok = cudaMalloc(&ctx->d_err, sizeof(int)) == cudaSuccess &&
+              cudaMemset(ctx->d_err, 0, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&ctx->wpk, S.wpk_total * 2) == cudaSuccess &&
+              cudaMalloc(&ctx->fold_scale, S.fold_total * 4) == cudaSuccess &&
+              cudaMalloc(&ctx->fold_shift, S.fold_total * 4) == cudaSuccess &&
+              cudaMalloc(&ctx->head_w, 145 * 4) == cudaSuccess;
+    if (ok) {
+        Ctx::InferPlan tmp;
+        size_t need = 0;
+        std::string pe = build_infer_plan(ctx, max_batch, tmp, &need);  // dry run: arena == nullptr
+        ok = pe.empty() && cudaMalloc(&ctx->arena, need) == cudaSuccess &&
+             cudaMemset(ctx->arena, 0, need) == cudaSuccess;
+        ctx->arena_bytes = need;
+    }
+    if (!ok) {
+        *err = std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+}  // namespace ub

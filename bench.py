@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the U-Net(ResNet-34) hot path (BASELINE.json: 512x512 images/sec, infer + train step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
+
+One JSON line on stdout (rank 0).  N=1 workload = BASELINE.json configs[1]: batch-32 bf16 inference at 512x512.
+A "step" is one forward pass of the whole network over one batch of synthetic inputs.
+  value     images/s with the fp32 NCHW input batch already resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the C-ABI host-buffer call (pinned host input -> H2D -> forward -> D2H of the uint8 mask)
+  roofline  the igemm conv stack (dominant kernel) against the measured dense bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the fp32 CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: smp is not installable
+offline) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_FWD_512 = 62.512  # algorithmic forward GFLOP / image @512x512 (scales with H*W)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--profile-out", default="", help="write the per-launch timing table here (rank 0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(size: int, batch: int, budget_s: float, threads: int):
+    """images/s of the fp32 oracle forward (eval, no_grad) on the host: bounded sample."""
+    import torch
+    from oracle import build_oracle
+    torch.set_num_threads(threads)
+    m = build_oracle(42).eval()
+    x = torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        m(x)
+        t0 = time.perf_counter()
+        m(x)
+        one = time.perf_counter() - t0
+        n = max(2, min(20, int(budget_s / max(one, 1e-3))))
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            m(x)
+            ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return batch / med, n, med
+
+
+def run_reference(a, rank):
+    """Reference arm: the reference's own CPU path for this metric (oracle port), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    sb = min(a.batch, 8)  # bounded sample of the batch-32 step
+    torch.set_num_threads(threads)
+    from oracle import build_oracle
+    m = build_oracle(42).eval()
+    x = torch.randn(sb, 3, a.size, a.size, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for _ in range(max(1, min(a.warmup, 3))):
+            m(x)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            m(x)
+        dt = time.perf_counter() - t0
+    val = sb * a.steps / dt
+    sample = f"{sb} of {a.batch} images per step, {a.steps} steps, fp32 oracle forward (eval, no_grad), {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "images_per_sec_infer_512", "value": val, "unit": "images/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Unet(resnet34) {a.size}x{a.size} batch-{a.batch} inference (configs[1])",
+                   "weights": "random-init seed 42"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        return run_reference(a, rank)
+
+    import torch
+    import torch.distributed as dist
+    import vickers_hardness_unet_b200 as vb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, S = a.batch, a.size
+    model = vb.Unet("resnet34", encoder_weights=None, in_channels=3, classes=1, activation=None)
+    torch.manual_seed(42)
+    model = model.to(dev).eval()
+    # two input batches, alternated (each step's working set, ~0.18 GB/image of activations, is far beyond L2)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    xs = [torch.randn(B, 3, S, S, device=dev, generator=g) for _ in range(2)]
+    logits = None
+
+    def step(i):
+        nonlocal logits
+        with torch.no_grad():
+            logits = model(xs[i & 1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(a.warmup):
+        step(i)
+    barrier()
+    ctx = model._ctx
+    launches = ctx.lib.unetb200_infer_launch_count(ctx.handle, B)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * a.steps / (ms * 1e-3)
+
+    # ---- end to end through the C-ABI host-buffer entry point (pinned host buffers, copies inside the timed region)
+    xh = [x.cpu().pin_memory() for x in xs]
+    mask_h = torch.empty(B, 1, S, S, dtype=torch.uint8).pin_memory()
+    import ctypes
+
+    def e2e_step(i):
+        ctx.check(ctx.lib.unetb200_infer_host(ctx.handle, xh[i & 1].data_ptr(), None, None, mask_h.data_ptr(),
+                                              ctypes.c_float(0.5), B), "infer_host")
+
+    for i in range(max(2, min(a.warmup, 3))):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_val = world * B * a.steps / e2e_s
+
+    # ---- per-launch timing of one step (CUDA events on the launch stream) -> conv-stack roofline
+    pk, pk_kind = peaks()
+    prof = None
+    if hasattr(ctx.lib, "unetb200_profile_infer"):
+        from vickers_hardness_unet_b200.profile import profile_infer
+        prof = profile_infer(model, xs[0], reps=3)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        thr = os.cpu_count() or 1
+        rate, n, med = cpu_oracle_rate(S, 1, 15.0, thr)
+        cpu = {"value": rate, "unit": "images/s", "cores": thr, "kind": "port",
+               "sample": f"fp32 oracle forward, batch 1 @ {S}x{S}, median of {n} runs ({med * 1e3:.0f} ms each), "
+                         f"{thr} torch threads on {os.cpu_count()} host cores"}
+    if rank == 0:
+        gflop = GFLOP_FWD_512 * (S * S) / (512 * 512)
+        whole_tf = gflop * B * a.steps / (ms * 1e-3) / 1e3  # whole step, per GPU
+        roof = {"bound": "tensor", "achieved": whole_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": whole_tf / pk["bf16_tflops_sustained"], "traffic": None, "peak_kind": pk_kind,
+                "kernel": "whole forward step (no per-launch breakdown available)"}
+        if prof is not None:
+            conv_ms = prof["igemm_ms"]
+            conv_tf = gflop * B / (conv_ms * 1e-3) / 1e3
+            roof.update({"achieved": conv_tf, "frac": conv_tf / pk["bf16_tflops_sustained"],
+                         "kernel": "ub::igemm_kernel (all conv launches of one step, algorithmic FLOPs)",
+                         "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / prof["total_ms"],
+                         "launches_per_step": prof["n_igemm"]})
+            if a.profile_out:
+                with open(a.profile_out, "w") as f:
+                    f.write(prof["table"])
+        out = {
+            "metric": "images_per_sec_infer_512", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"Unet(resnet34) {S}x{S} batch-{B}/GPU bf16 inference (BASELINE configs[1])",
+                       "weights": "random-init seed 42", "input": "fp32 NCHW randn, 2 batches alternated",
+                       "l2": "per-step working set >> 126 MB L2 (inputs larger than L2)",
+                       "parallelism": f"batch-sharded replicas x{world}, no collective"},
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
+                    "d2h_bytes_per_step": B * S * S, "call": "unetb200_infer_host (pinned fp32 in, uint8 mask out)"},
+            "gpu_launches": launches * a.steps, "roofline": roof, "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,12 @@ int unetb200_infer_host(unetb200_ctx* ctx, const float* x_host, float* logits_ho
 /* number of kernel launches one forward_infer call issues at batch N (after the plan for N exists) */
 int unetb200_infer_launch_count(unetb200_ctx* ctx, int N);
 
+/* One forward with a CUDA event recorded between consecutive launches on `stream`: ms_out[i] = device time of launch i
+ * (0 = input pack, last = seg head), is_igemm_out[i] = 1 for implicit-GEMM conv launches.  Synchronises the stream. */
+int unetb200_profile_infer(unetb200_ctx* ctx, const float* x_dev, float* logits_dev, int N, void* stream,
+                           float* ms_out, int* is_igemm_out, int cap, int* n_out);
+int unetb200_profile_name(unetb200_ctx* ctx, int N, int index, char* name_out, int name_cap);
+
 /* ---- per-kernel entry points for unit parity tests --------------------------------------------------------------- */
 /* conv + folded scale/shift (+residual) (+ReLU) on NHWC bf16: w_dev fp32 OIHW [cout,cin,k,k], k in {1,3},
  * stride in {1,2}, padding k/2.  scale/shift/residual may be NULL.  stats_dev (optional) fp32 [cout][2] receives

@@ -1,0 +1,9 @@
+"""B200-native U-Net(ResNet-34) hot path of ZooMEISTER/vickers-hardness-Unet.
+
+Public surface mirrors the two smp symbols the reference uses (`Unet`, `losses.DiceLoss`), see SURVEY.md section 8b.
+"""
+from ._lib import UnetB200Error, LIB_PATH  # noqa: F401
+from .unet import Unet  # noqa: F401
+from . import losses  # noqa: F401
+
+__all__ = ["Unet", "losses", "UnetB200Error"]

@@ -1,0 +1,113 @@
+"""ctypes binding of libunetb200.so (C ABI declared in include/unetb200.h).
+
+The product path has no fallback: if the shared library is missing this module raises at first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libunetb200.so"
+_lib = None
+
+
+class UnetB200Error(RuntimeError):
+    pass
+
+
+def _proto(lib):
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+    P = C.POINTER
+    sigs = {
+        "unetb200_create": (i32, [P(vp), i32, i32, i32, i32]),
+        "unetb200_destroy": (None, [vp]),
+        "unetb200_last_error": (C.c_char_p, [vp]),
+        "unetb200_check_device_error": (i32, [vp, P(i32)]),
+        "unetb200_num_tensors": (i32, []),
+        "unetb200_tensor_info": (i32, [i32, C.c_char_p, i32, P(i32), P(i32), P(i64), P(i32)]),
+        "unetb200_num_params": (i64, []),
+        "unetb200_num_buffers": (i64, []),
+        "unetb200_num_counters": (i32, []),
+        "unetb200_load_weights": (i32, [vp, vp, vp, vp]),
+        "unetb200_forward_infer": (i32, [vp, vp, vp, vp, vp, f32, i32, vp]),
+        "unetb200_infer_host": (i32, [vp, vp, vp, vp, vp, f32, i32]),
+        "unetb200_infer_launch_count": (i32, [vp, i32]),
+        "unetb200_profile_infer": (i32, [vp, vp, vp, i32, vp, P(f32), P(i32), i32, P(i32)]),
+        "unetb200_profile_name": (i32, [vp, i32, i32, C.c_char_p, i32]),
+        "unetb200_conv_nhwc": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return sigs
+
+
+def exported_symbols():
+    """Names include/unetb200.h declares (used by the CPU-side export test)."""
+    hdr = (_HERE.parent / "include" / "unetb200.h").read_text()
+    import re
+
+    return sorted(set(re.findall(r"\b(unetb200_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise UnetB200Error(
+                f"{LIB_PATH} is missing: build it with `make` (nvcc, sm_100a). There is no CPU / cuDNN fallback."
+            )
+        lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_GLOBAL", 0))
+        _proto(lib)
+        _lib = lib
+    return _lib
+
+
+def tensor_table():
+    """[(name, shape tuple, offset, kind)] in state_dict order; kind 0 param, 1 fp32 buffer, 2 int64 counter."""
+    lib = load()
+    out = []
+    name = C.create_string_buffer(256)
+    nd, kind, off = C.c_int(), C.c_int(), C.c_longlong()
+    shape = (C.c_int * 4)()
+    for i in range(lib.unetb200_num_tensors()):
+        rc = lib.unetb200_tensor_info(i, name, 256, C.byref(nd), shape, C.byref(off), C.byref(kind))
+        if rc:
+            raise UnetB200Error("tensor_info failed")
+        out.append((name.value.decode(), tuple(shape[j] for j in range(nd.value)), off.value, kind.value))
+    return out
+
+
+class Context:
+    """Owns one unetb200_ctx (device, max_batch, H, W)."""
+
+    def __init__(self, device: int, max_batch: int, H: int, W: int):
+        self.lib = load()
+        self.handle = C.c_void_p()
+        rc = self.lib.unetb200_create(C.byref(self.handle), device, max_batch, H, W)
+        if rc:
+            raise UnetB200Error("unetb200_create: " + self.lib.unetb200_last_error(None).decode())
+        self.device, self.max_batch, self.H, self.W = device, max_batch, H, W
+
+    def check(self, rc: int, what: str):
+        if rc:
+            raise UnetB200Error(f"{what}: " + self.lib.unetb200_last_error(self.handle).decode())
+
+    def device_error_flag(self) -> int:
+        f = C.c_int()
+        self.check(self.lib.unetb200_check_device_error(self.handle, C.byref(f)), "check_device_error")
+        return f.value
+
+    def close(self):
+        if self.handle:
+            self.lib.unetb200_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -102,6 +102,7 @@ int unetb200_infer_host(unetb200_ctx* h, const float* x_host, float* logits_host
         UB_CUDA(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
     }
     cudaStream_t st = ctx->io_stream;
+    if (ctx->weights_event) UB_CUDA(cudaStreamWaitEvent(st, ctx->weights_event, 0));
     UB_CUDA(cudaMemcpyAsync(ctx->io_x, x_host, px * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     float* dl = logits_host ? ctx->io_f : nullptr;
     float* dp = prob_host ? ctx->io_f + (size_t)ctx->max_batch * ctx->H * ctx->W : nullptr;
@@ -118,6 +119,37 @@ int unetb200_infer_host(unetb200_ctx* h, const float* x_host, float* logits_host
 int unetb200_infer_launch_count(unetb200_ctx* h, int N) {
     auto it = h->c->infer_plans.find(N);
     return it == h->c->infer_plans.end() ? -1 : it->second.launches;
+}
+
+int unetb200_profile_infer(unetb200_ctx* h, const float* x_dev, float* logits_dev, int N, void* stream, float* ms_out,
+                           int* is_igemm_out, int cap, int* n_out) {
+    Ctx* ctx = h->c;
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev;
+    if (ctx_forward_infer(ctx, x_dev, logits_dev, nullptr, nullptr, 0.5f, N, st, &ev)) return 1;
+    UB_CUDA(cudaStreamSynchronize(st));
+    const int n = (int)ev.size() - 1;
+    auto& plan = ctx->infer_plans[N];
+    for (int i = 0; i < n && i < cap; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        ms_out[i] = ms;
+        // launch 0 = input pack, last = head, others = plan steps
+        is_igemm_out[i] = (i >= 1 && i <= (int)plan.steps.size()) ? plan.steps[i - 1].is_igemm : 0;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    if (n_out) *n_out = n;
+    return 0;
+}
+
+int unetb200_profile_name(unetb200_ctx* h, int N, int i, char* out, int cap) {
+    auto it = h->c->infer_plans.find(N);
+    if (it == h->c->infer_plans.end() || cap < 1) return 1;
+    const int ns = (int)it->second.steps.size();
+    std::string nm = i == 0 ? "input_pack" : (i <= ns ? it->second.steps[i - 1].name : "segmentation_head");
+    strncpy(out, nm.c_str(), cap - 1);
+    out[cap - 1] = 0;
+    return 0;
 }
 
 int unetb200_conv_nhwc(unetb200_ctx* h, const void* in, const float* w, const float* scale, const float* shift,

@@ -168,7 +168,12 @@ struct Ctx {
         int N = 0;
         __nv_bfloat16* xp = nullptr;
         __nv_bfloat16* head_in = nullptr;
-        std::vector<std::function<cudaError_t(cudaStream_t)>> steps;  // everything between input pack and head
+        struct Step {
+            std::function<cudaError_t(cudaStream_t)> fn;
+            std::string name;
+            int is_igemm;
+        };
+        std::vector<Step> steps;  // everything between input pack and head
         int launches = 0;
     };
     std::map<int, InferPlan> infer_plans;  // keyed by batch size
@@ -177,8 +182,10 @@ struct Ctx {
     float* io_f = nullptr;
     uint8_t* io_m = nullptr;
     cudaStream_t io_stream = nullptr;
+    cudaEvent_t weights_event = nullptr;  // recorded after every weight re-pack (cross-stream ordering for io_stream)
 
     ~Ctx() {
+        if (weights_event) cudaEventDestroy(weights_event);
         cudaFree(io_x);
         cudaFree(io_f);
         cudaFree(io_m);
@@ -237,6 +244,8 @@ inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers,
                                                          ctx->fold_shift + b.fold, b.c);
     }
     UB_CUDA(cudaGetLastError());
+    if (!ctx->weights_event) UB_CUDA(cudaEventCreateWithFlags(&ctx->weights_event, cudaEventDisableTiming));
+    UB_CUDA(cudaEventRecord(ctx->weights_event, st));
     ctx->weights_ready = true;
     return 0;
 }
@@ -371,8 +380,8 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         return ep;
     };
     std::string err;
-    auto add_igemm = [&](const IgemmLaunch& L) {
-        plan.steps.push_back([L](cudaStream_t st) { return igemm_launch(L, st); });
+    auto add_igemm = [&](const IgemmLaunch& L, const std::string& name) {
+        plan.steps.push_back({[L](cudaStream_t st) { return igemm_launch(L, st); }, name, 1});
     };
 
     plan.xp = A.take((long long)N * H * (W + 8) * 4);
@@ -381,18 +390,18 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         IgemmLaunch L;
         err = build_stem(ctx, L, ctx->wpk + S.convs[S.stem].wpk, plan.xp, N, H, W, f1, fold(S.convs[S.stem].bn, 1));
         if (!err.empty()) return "stem: " + err;
-        add_igemm(L);
+        add_igemm(L, "encoder.conv1");
     }
     int h = H / 4, w = W / 4;
     __nv_bfloat16* cur = A.take((long long)N * h * w * 64);
     if (!dry) {
         const int num_sms = ctx->num_sms;
         const int Hh = H / 2, Wh = W / 2;
-        plan.steps.push_back([=](cudaStream_t st) {
+        plan.steps.push_back({[=](cudaStream_t st) {
             maxpool3x3s2_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, num_sms), 256, 0, st>>>(
                 f1, cur, N, Hh, Wh, 64);
             return cudaGetLastError();
-        });
+        }, "encoder.maxpool", 0});
     }
     __nv_bfloat16* feats[5] = {f1, nullptr, nullptr, nullptr, nullptr};  // f1, layer1..4 outputs
     for (int l = 0; l < 4; ++l) {
@@ -409,18 +418,18 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
                 IgemmLaunch L;
                 err = build_conv(ctx, L, c1, ctx->wpk + c1.wpk, cur, N, h, w, t, fold(c1.bn, 1));
                 if (!err.empty()) return c1.name + ": " + err;
-                add_igemm(L);
+                add_igemm(L, c1.name);
                 if (blk.ds >= 0) {
                     const ConvRef& cd = S.convs[blk.ds];
                     err = build_conv(ctx, L, cd, ctx->wpk + cd.wpk, cur, N, h, w, ident, fold(cd.bn, 0));
                     if (!err.empty()) return cd.name + ": " + err;
-                    add_igemm(L);
+                    add_igemm(L, cd.name);
                 }
                 EpilogueDesc ep = fold(c2.bn, 1);
                 ep.residual = nhwc_view(ident, N, ho, wo, c1.cout);
                 err = build_conv(ctx, L, c2, ctx->wpk + c2.wpk, t, N, ho, wo, o, ep);
                 if (!err.empty()) return c2.name + ": " + err;
-                add_igemm(L);
+                add_igemm(L, c2.name);
             }
             cur = o;
             h = ho;
@@ -441,12 +450,12 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
                 IgemmLaunch L;
                 err = build_dec1(ctx, L, d, ctx->wpk + c1.wpk, par, cur, skips[i], N, h, w, t, fold(c1.bn, 1));
                 if (!err.empty()) return c1.name + ": " + err;
-                add_igemm(L);
+                add_igemm(L, c1.name + "[parity " + std::to_string(par) + "]");
             }
             IgemmLaunch L;
             err = build_conv(ctx, L, c2, ctx->wpk + c2.wpk, t, N, 2 * h, 2 * w, o, fold(c2.bn, 1));
             if (!err.empty()) return c2.name + ": " + err;
-            add_igemm(L);
+            add_igemm(L, c2.name);
         }
         cur = o;
         h *= 2;
@@ -459,8 +468,16 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
 }
 
 // logits / prob / mask: any may be null (at least one non-null). x: fp32 NCHW [N,3,H,W] device pointer.
+// ev != nullptr: record an event before every launch and one at the end (per-launch timing for bench.py).
 inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* prob, uint8_t* mask, float thresh, int N,
-                             cudaStream_t st) {
+                             cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr) {
+    auto mark = [&]() {
+        if (!ev) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev->push_back(e);
+    };
     if (!ctx->weights_ready) return ctx_fail(ctx, "forward_infer: weights not loaded");
     if (N < 1 || N > ctx->max_batch) return ctx_fail(ctx, "forward_infer: batch outside [1, max_batch]");
     auto it = ctx->infer_plans.find(N);
@@ -472,9 +489,14 @@ inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* pro
     }
     Ctx::InferPlan& P = it->second;
     const int H = ctx->H, W = ctx->W;
+    mark();
     pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P.xp, N, H, W);
     UB_CUDA(cudaGetLastError());
-    for (auto& s : P.steps) UB_CUDA(s(st));
+    for (auto& s : P.steps) {
+        mark();
+        UB_CUDA(s.fn(st));
+    }
+    mark();
     float tl = 0.f;
     if (thresh <= 0.f) tl = -INFINITY;
     else if (thresh >= 1.f) tl = INFINITY;
@@ -482,6 +504,7 @@ inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* pro
     dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
     head_conv_kernel<<<grid, 256, 0, st>>>(P.head_in, ctx->head_w, ctx->head_w + 144, logits, prob, mask, tl, N, H, W);
     UB_CUDA(cudaGetLastError());
+    mark();
     return 0;
 }
 

@@ -1,0 +1,191 @@
+"""`Unet`: drop-in for `segmentation_models_pytorch.Unet("resnet34", in_channels=3, classes=1, activation=None)`.
+
+Same constructor call, same `nn.Module` surface and the same 278-entry state_dict key layout as the model the
+reference builds at /root/reference/train.py:372-378, infer_pth_gui.py:31-33, ui_infer_rectangle.py:496-499 and
+ui_infer_quadrilateral.py:638-641 — but `forward` runs the hand-written sm_100a kernels of libunetb200.so.
+Parameters are fp32 master copies living in ONE flat tensor (views per state_dict entry), which is what the fused
+optimizer and the bucketed gradient all-reduce operate on.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class _Node(nn.Module):
+    """Anonymous container so that parameters get smp's dotted key names."""
+
+
+def _init_tensor(name: str, t: torch.Tensor):
+    """Default init of smp / torchvision; only matters without a checkpoint."""
+    if name.endswith("running_var"):
+        t.fill_(1.0)
+    elif name.endswith("running_mean"):
+        t.zero_()
+    elif t.dim() == 4:
+        if name.startswith("encoder."):  # torchvision/models/resnet.py:208-210
+            nn.init.kaiming_normal_(t, mode="fan_out", nonlinearity="relu")
+        elif name.startswith("decoder."):
+            nn.init.kaiming_uniform_(t, mode="fan_in", nonlinearity="relu")
+        else:
+            nn.init.xavier_uniform_(t)
+    elif name.endswith(".weight"):
+        t.fill_(1.0)  # BatchNorm gamma
+    else:
+        t.zero_()  # BatchNorm beta / head bias
+
+
+class Unet(nn.Module):
+    def __init__(self, encoder_name: str = "resnet34", encoder_depth: int = 5, encoder_weights=None,
+                 decoder_use_batchnorm: bool = True, decoder_channels=(256, 128, 64, 32, 16),
+                 decoder_attention_type=None, in_channels: int = 3, classes: int = 1, activation=None,
+                 aux_params=None, **kwargs):
+        super().__init__()
+        if encoder_name != "resnet34":
+            raise ValueError(f"unet_b200 implements encoder_name='resnet34' only (got {encoder_name!r})")
+        if encoder_weights is not None:
+            raise ValueError(
+                "encoder_weights must be None: pretrained ImageNet weights need a network download; "
+                "load a state_dict instead (key layout is identical to smp)")
+        if (encoder_depth != 5 or tuple(decoder_channels) != (256, 128, 64, 32, 16) or not decoder_use_batchnorm
+                or decoder_attention_type is not None or in_channels != 3 or classes != 1
+                or activation is not None or aux_params is not None):
+            raise ValueError("unet_b200 implements exactly smp.Unet('resnet34', in_channels=3, classes=1, "
+                             "activation=None) with default decoder settings")
+        table = _lib.tensor_table()
+        lib = _lib.load()
+        self._table = table
+        n_p, n_b, n_c = lib.unetb200_num_params(), lib.unetb200_num_buffers(), lib.unetb200_num_counters()
+        flat_p = torch.zeros(n_p, dtype=torch.float32)
+        flat_b = torch.zeros(n_b, dtype=torch.float32)
+        flat_c = torch.zeros(n_c, dtype=torch.int64)
+        self._flat = {"p": flat_p, "b": flat_b, "c": flat_c}
+        self._entries = []  # (owner module, attr, kind, offset, shape)
+        for name, shape, off, kind in table:
+            parts = name.split(".")
+            mod = self
+            for p in parts[:-1]:
+                if p not in mod._modules:
+                    mod.add_module(p, _Node())
+                mod = mod._modules[p]
+            numel = int(math.prod(shape)) if shape else 1
+            if kind == 0:
+                view = flat_p[off:off + numel].view(shape)
+                with torch.no_grad():
+                    _init_tensor(name, view)
+                mod.register_parameter(parts[-1], nn.Parameter(view))
+            elif kind == 1:
+                view = flat_b[off:off + numel].view(shape)
+                _init_tensor(name, view)
+                mod.register_buffer(parts[-1], view)
+            else:
+                mod.register_buffer(parts[-1], flat_c[off:off + 1].view(()))
+            self._entries.append((mod, parts[-1], kind, off, shape, numel))
+        self._ctx = None
+        self._packed_version = None
+        self.name = "u-resnet34"
+
+    # ------------------------------------------------------------------ flat storage upkeep
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        self._reflatten()
+        return self
+
+    def _reflatten(self):
+        """nn.Module._apply re-creates every tensor separately; gather them back into the flat arrays."""
+        first = next(p for p in self.parameters())
+        dev = first.device
+        flat = {"p": torch.empty(self._flat["p"].numel(), dtype=torch.float32, device=dev),
+                "b": torch.empty(self._flat["b"].numel(), dtype=torch.float32, device=dev),
+                "c": torch.empty(self._flat["c"].numel(), dtype=torch.int64, device=dev)}
+        with torch.no_grad():
+            for mod, attr, kind, off, shape, numel in self._entries:
+                if kind == 0:
+                    p = mod._parameters[attr]
+                    view = flat["p"][off:off + numel].view(shape)
+                    view.copy_(p.data.to(torch.float32))
+                    p.data = view
+                elif kind == 1:
+                    view = flat["b"][off:off + numel].view(shape)
+                    view.copy_(mod._buffers[attr].to(torch.float32))
+                    mod._buffers[attr] = view
+                else:
+                    view = flat["c"][off:off + 1].view(())
+                    view.copy_(mod._buffers[attr])
+                    mod._buffers[attr] = view
+        self._flat = flat
+        self._packed_version = None
+        if self._ctx is not None and self._ctx.device != (dev.index if dev.type == "cuda" else -1):
+            self._ctx = None
+
+    @property
+    def flat_params(self) -> torch.Tensor:
+        return self._flat["p"]
+
+    @property
+    def flat_buffers(self) -> torch.Tensor:
+        return self._flat["b"]
+
+    # ------------------------------------------------------------------ native context
+    def _context(self, x: torch.Tensor) -> "_lib.Context":
+        if not x.is_cuda:
+            raise _lib.UnetB200Error(
+                "unet_b200.Unet runs on CUDA sm_100a only — there is no CPU fallback. "
+                "Move the model and the input to a B200 (`.to('cuda')`).")
+        if self._flat["p"].device != x.device:
+            raise _lib.UnetB200Error(f"model is on {self._flat['p'].device}, input on {x.device}")
+        N, Cin, H, W = x.shape
+        if Cin != 3:
+            raise ValueError(f"expected [N,3,H,W] input, got {tuple(x.shape)}")
+        if H % 32 or W % 32:
+            raise ValueError(f"H and W must be divisible by 32 (got {H}x{W})")  # same rule as smp>=0.5
+        c = self._ctx
+        if c is None or c.H != H or c.W != W or c.max_batch < N or c.device != x.device.index:
+            if c is not None:
+                torch.cuda.synchronize(x.device)
+                c.close()
+            mb = N if c is None or c.H != H or c.W != W else max(N, c.max_batch)
+            self._ctx = c = _lib.Context(x.device.index, mb, H, W)
+            self._packed_version = None
+        return c
+
+    def _sync_weights(self, ctx, stream):
+        ver = (self._flat["p"]._version, self._flat["b"]._version, id(ctx))
+        if ver != self._packed_version:
+            ctx.check(ctx.lib.unetb200_load_weights(ctx.handle, self._flat["p"].data_ptr(), self._flat["b"].data_ptr(),
+                                                    stream), "load_weights")
+            self._packed_version = ver
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        ctx = self._context(x)
+        x = x.detach().to(torch.float32).contiguous()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        self._sync_weights(ctx, stream)
+        if self.training and torch.is_grad_enabled():
+            from .train import unet_train_forward
+            return unet_train_forward(self, ctx, x, stream)
+        N, _, H, W = x.shape
+        logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+        ctx.check(ctx.lib.unetb200_forward_infer(ctx.handle, x.data_ptr(), logits.data_ptr(), None, None, 0.5, N,
+                                                 stream), "forward_infer")
+        return logits
+
+    @torch.no_grad()
+    def predict_mask(self, x: torch.Tensor, threshold: float = 0.5, return_prob: bool = False):
+        """Fused `sigmoid(model(x)) >= threshold` (infer_pth_gui.py:50-52): uint8 {0,255} mask [N,1,H,W]."""
+        ctx = self._context(x)
+        x = x.detach().to(torch.float32).contiguous()
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        self._sync_weights(ctx, stream)
+        N, _, H, W = x.shape
+        mask = torch.empty((N, 1, H, W), dtype=torch.uint8, device=x.device)
+        prob = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device) if return_prob else None
+        ctx.check(ctx.lib.unetb200_forward_infer(ctx.handle, x.data_ptr(), None,
+                                                 prob.data_ptr() if return_prob else None, mask.data_ptr(),
+                                                 float(threshold), N, stream), "forward_infer")
+        return (mask, prob) if return_prob else mask

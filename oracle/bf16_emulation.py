@@ -1,0 +1,87 @@
+"""fp32 emulation of the bf16 storage points of the CUDA path (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+The product keeps activations and conv weights in bf16 (fp32 accumulate).  Measured on this model (random init,
+calibrated BatchNorm statistics, noise input) rounding ONLY the conv weights and the input image to bf16 already moves
+the logits by ~0.03-0.09 mean-abs / 0.2-0.7 max-abs against the fp32 oracle (|logit| mean ~0.8, max ~5-7), i.e. the
+BASELINE north_star figure "2e-2 max-abs / 1e-3 mean-abs" is below what bf16 operands can deliver on this network
+(fp16 operands: ~5e-3..2e-2 mean, 3e-2..0.15 max).  The parity tests therefore check the CUDA path against THIS
+emulation (same rounding points, fp32 math in between) and report the distance to the fp32 oracle beside it.
+
+Rounding points emulated (eval mode):
+  input image -> bf16; every conv weight except the seg head -> bf16; the decoder conv1 weights that act on the
+  up-sampled channels are first summed per output parity (3x3 -> 2x2 on the low-res tensor) and then rounded, exactly
+  as the packed operand of the CUDA kernel; every unit output (after BN(+residual)+ReLU, and after the downsample BN)
+  -> bf16.  BatchNorm is applied in fp32 on the fp32 accumulator, the seg head runs in fp32 on bf16 inputs.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn.functional as F
+
+
+def _r(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def _dec_conv1_parity(x_low, skip, w, cup):
+    """cat(nearest2x(x_low), skip) (*) w, computed as the CUDA path does: 4 output parities, summed 2x2 weights."""
+    N, _, Hl, Wl = x_low.shape
+    cout = w.shape[0]
+    out = x_low.new_zeros(N, cout, 2 * Hl, 2 * Wl)
+    w_up, w_sk = w[:, :cup], w[:, cup:]
+    rsets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # parity -> row sets of a=0, a=1
+    for ph in (0, 1):
+        for pw in (0, 1):
+            weff = x_low.new_zeros(cout, cup, 2, 2)
+            for a in (0, 1):
+                for b in (0, 1):
+                    weff[:, :, a, b] = sum(w_up[:, :, r, s] for r in rsets[ph][a] for s in rsets[pw][b])
+            weff = _r(weff)
+            # low-res taps at offsets (a-1+ph, b-1+pw): pad so that a 2x2 VALID conv lines up
+            xp = F.pad(x_low, (1 - pw, pw, 1 - ph, ph))
+            acc = F.conv2d(xp, weff)
+            if skip is not None:
+                full = F.conv2d(skip, _r(w_sk), padding=1)
+                acc = acc + full[:, :, ph::2, pw::2]
+            out[:, :, ph::2, pw::2] = acc
+    return out
+
+
+class Bf16EmulatedUnet(torch.nn.Module):
+    """Eval-mode forward of the oracle with the CUDA path's bf16 rounding points."""
+
+    def __init__(self, oracle):
+        super().__init__()
+        self.o = copy.deepcopy(oracle).eval()
+
+    @staticmethod
+    def _bn(x, bn):
+        return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+
+    @torch.no_grad()
+    def forward(self, x):
+        o = self.o
+        e = o.encoder
+        x = _r(x)
+        f1 = _r(F.relu(self._bn(F.conv2d(x, _r(e.conv1.weight), None, 2, 3), e.bn1)))
+        t = _r(F.max_pool2d(f1, 3, 2, 1))
+        feats = [f1]
+        for layer in (e.layer1, e.layer2, e.layer3, e.layer4):
+            for blk in layer:
+                idn = t
+                u = _r(F.relu(self._bn(F.conv2d(t, _r(blk.conv1.weight), None, blk.stride, 1), blk.bn1)))
+                if blk.downsample is not None:
+                    idn = _r(self._bn(F.conv2d(t, _r(blk.downsample[0].weight), None, blk.stride, 0),
+                                      blk.downsample[1]))
+                t = _r(F.relu(self._bn(F.conv2d(u, _r(blk.conv2.weight), None, 1, 1), blk.bn2) + idn))
+            feats.append(t)
+        skips = [feats[3], feats[2], feats[1], feats[0], None]
+        cups = [512, 256, 128, 64, 32]
+        for i, blk in enumerate(o.decoder.blocks):
+            z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i])
+            u = _r(F.relu(self._bn(z, blk.conv1[1])))
+            t = _r(F.relu(self._bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
+        head = o.segmentation_head[0]
+        return F.conv2d(t, head.weight, head.bias, 1, 1)

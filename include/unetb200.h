@@ -79,6 +79,52 @@ int unetb200_conv_nhwc(unetb200_ctx* ctx, const void* in_bf16_dev, const float* 
                        const float* shift_dev, const void* residual_bf16_dev, int relu, void* out_bf16_dev,
                        float* stats_dev, int N, int H, int W, int cin, int cout, int k, int stride, void* stream);
 
+/* ---- training step (/root/reference/train.py:428-449) --------------------------------------------------------------- */
+/* model.train(); logits = model(x)  (train.py:413,436).  BatchNorm uses batch statistics; running_mean / running_var
+ * (buffers_dev, fp32 flat) and num_batches_tracked (counters_dev, int64[46]) are updated in place like nn.BatchNorm2d
+ * (momentum 0.1, unbiased running variance).  Activations needed by the backward stay in the library's arena until the
+ * next train_forward.  grads_dev is the flat fp32 gradient array (same layout as params_dev) train_backward fills.
+ * unetb200_load_weights must have been called since the parameters last changed. */
+int unetb200_train_forward(unetb200_ctx* ctx, const float* x_dev, float* logits_dev, const float* params_dev,
+                           float* buffers_dev, long long* counters_dev, float* grads_dev, int N, void* stream);
+/* loss.backward() through the network (train.py:443,448) given dL/dlogits fp32 [N,1,H,W].  The backward is cut into
+ * 4 stages whose parameter gradients are complete when the stage ends (0 = head + decoder, 1 = encoder.layer4,
+ * 2 = layer3, 3 = layer2 + layer1 + stem) so that a data-parallel caller can all-reduce bucket k while stage k+1 runs.
+ * Runs stages stage_first..stage_last; stage 0 first OVERWRITES the whole gradient array (no accumulation). */
+int unetb200_train_backward(unetb200_ctx* ctx, const float* dlogits_dev, int N, int stage_first, int stage_last,
+                            void* stream);
+/* element range [begin, end) of the flat parameter / gradient array that backward stage `stage` completes */
+int unetb200_grad_bucket_range(int stage, long long* begin_out, long long* end_out);
+/* kernel launches of one train_forward / one full train_backward at batch N (after the plan exists) */
+int unetb200_train_launch_count(unetb200_ctx* ctx, int N, int* fwd_out, int* bwd_out);
+
+/* Test hooks: the library's internal training tensors of the last step at batch N (saved activations z / a, their
+ * gradients dz / dA, batch mean / invstd, ...), by index; NHWC, bf16 (is_bf16 = 1) or fp32.  Used by the layer-local
+ * parity tests, which re-derive every backward kernel's output from ITS OWN inputs with PyTorch. */
+int unetb200_train_debug_count(unetb200_ctx* ctx, int N);
+int unetb200_train_debug_info(unetb200_ctx* ctx, int N, int index, char* name_out, int name_cap, int shape_out[4],
+                              int* is_bf16_out);
+int unetb200_train_debug_copy(unetb200_ctx* ctx, int N, int index, void* dst_dev, long long cap_bytes, void* stream);
+
+/* nn.BCEWithLogitsLoss()(logits, y) + smp.losses.DiceLoss("binary")(logits, y)  (train.py:438,600-601), one pass:
+ * result_dev[0..2] = bce, dice, bce + dice; result_dev[3..5] = sum(p*y), sum(p), sum(y) (kept for the backward);
+ * result_dev must hold 8 floats.  n = N*H*W elements; eps = DiceLoss eps (1e-7).  scratch_dev: caller-owned device
+ * scratch of unetb200_loss_scratch_floats() floats.  No ctx: errors are reported through unetb200_last_error(NULL). */
+int unetb200_loss_scratch_floats(void);
+int unetb200_loss_bce_dice_forward(const float* logits_dev, const float* target_dev, long long n, float eps,
+                                   float* scratch_dev, float* result_dev, void* stream);
+/* dlogits = gscale * (g_bce * dBCE/dlogits + g_dice * dDice/dlogits); g_*_dev are device scalars (NULL = 0). */
+int unetb200_loss_bce_dice_backward(const float* logits_dev, const float* target_dev, const float* result_dev,
+                                    const float* g_bce_dev, const float* g_dice_dev, float gscale, float eps,
+                                    float* dlogits_dev, long long n, void* stream);
+
+/* torch.optim.AdamW(...).step() (train.py:606,444,449) fused over the flat arrays: decoupled weight decay on every
+ * element, bias-corrected moments (step >= 1).  grad_scale multiplies the gradient first (1/world_size, 1/loss_scale);
+ * zero_grad != 0 clears grads_dev afterwards (optimizer.zero_grad, train.py:428). */
+int unetb200_adamw_step(unetb200_ctx* ctx, float* params_dev, float* grads_dev, float* exp_avg_dev,
+                        float* exp_avg_sq_dev, long long n, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, long long step, float grad_scale, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

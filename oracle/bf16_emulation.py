@@ -21,32 +21,82 @@ import torch
 import torch.nn.functional as F
 
 
+class _RoundSTE(torch.autograd.Function):
+    """bf16 rounding with a straight-through (identity) gradient: the backward of the emulated network is then the
+    exact gradient of the rounded-forward computation, which is what the CUDA backward approximates."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 def _r(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).to(torch.float32)
+    return _RoundSTE.apply(t)
 
 
 def _dec_conv1_parity(x_low, skip, w, cup):
     """cat(nearest2x(x_low), skip) (*) w, computed as the CUDA path does: 4 output parities, summed 2x2 weights."""
     N, _, Hl, Wl = x_low.shape
     cout = w.shape[0]
-    out = x_low.new_zeros(N, cout, 2 * Hl, 2 * Wl)
     w_up, w_sk = w[:, :cup], w[:, cup:]
     rsets = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # parity -> row sets of a=0, a=1
+    full = F.conv2d(skip, _r(w_sk), padding=1) if skip is not None else None
+    rows = []
     for ph in (0, 1):
+        cols = []
         for pw in (0, 1):
-            weff = x_low.new_zeros(cout, cup, 2, 2)
-            for a in (0, 1):
-                for b in (0, 1):
-                    weff[:, :, a, b] = sum(w_up[:, :, r, s] for r in rsets[ph][a] for s in rsets[pw][b])
+            weff = torch.stack([torch.stack([sum(w_up[:, :, r, s] for r in rsets[ph][a] for s in rsets[pw][b])
+                                             for b in (0, 1)], -1) for a in (0, 1)], -2)  # [cout, cup, 2(a), 2(b)]
             weff = _r(weff)
             # low-res taps at offsets (a-1+ph, b-1+pw): pad so that a 2x2 VALID conv lines up
             xp = F.pad(x_low, (1 - pw, pw, 1 - ph, ph))
             acc = F.conv2d(xp, weff)
-            if skip is not None:
-                full = F.conv2d(skip, _r(w_sk), padding=1)
+            if full is not None:
                 acc = acc + full[:, :, ph::2, pw::2]
-            out[:, :, ph::2, pw::2] = acc
-    return out
+            cols.append(acc)
+        rows.append(torch.stack(cols, -1).reshape(N, cout, Hl, 2 * Wl))       # interleave the two column parities
+    return torch.stack(rows, -2).reshape(N, cout, 2 * Hl, 2 * Wl)              # interleave the two row parities
+
+
+def emulated_forward(o, x, train: bool):
+    """Forward of oracle `o` with the CUDA path's bf16 rounding points.
+
+    eval : BatchNorm folded into the conv epilogue: a = bf16(relu(acc*scale + shift (+ identity)))
+    train: raw conv output stored first, z = bf16(acc); batch statistics are taken from the ROUNDED z; then
+           a = bf16(relu(bn(z) (+ identity)))  -- running statistics of `o` are updated like nn.BatchNorm2d.
+    """
+    def bn(t, m):
+        if train:
+            if m.num_batches_tracked is not None:
+                m.num_batches_tracked += 1
+            return F.batch_norm(_r(t), m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
+        return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, m.eps)
+
+    e = o.encoder
+    x = _r(x)
+    f1 = _r(F.relu(bn(F.conv2d(x, _r(e.conv1.weight), None, 2, 3), e.bn1)))
+    t = F.max_pool2d(f1, 3, 2, 1)
+    feats = [f1]
+    for layer in (e.layer1, e.layer2, e.layer3, e.layer4):
+        for blk in layer:
+            idn = t
+            u = _r(F.relu(bn(F.conv2d(t, _r(blk.conv1.weight), None, blk.stride, 1), blk.bn1)))
+            if blk.downsample is not None:
+                idn = _r(bn(F.conv2d(t, _r(blk.downsample[0].weight), None, blk.stride, 0), blk.downsample[1]))
+            t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2.weight), None, 1, 1), blk.bn2) + idn))
+        feats.append(t)
+    skips = [feats[3], feats[2], feats[1], feats[0], None]
+    cups = [512, 256, 128, 64, 32]
+    for i, blk in enumerate(o.decoder.blocks):
+        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i])
+        u = _r(F.relu(bn(z, blk.conv1[1])))
+        t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
+    head = o.segmentation_head[0]
+    return F.conv2d(t, head.weight, head.bias, 1, 1)
 
 
 class Bf16EmulatedUnet(torch.nn.Module):
@@ -56,32 +106,18 @@ class Bf16EmulatedUnet(torch.nn.Module):
         super().__init__()
         self.o = copy.deepcopy(oracle).eval()
 
-    @staticmethod
-    def _bn(x, bn):
-        return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
-
     @torch.no_grad()
     def forward(self, x):
-        o = self.o
-        e = o.encoder
-        x = _r(x)
-        f1 = _r(F.relu(self._bn(F.conv2d(x, _r(e.conv1.weight), None, 2, 3), e.bn1)))
-        t = _r(F.max_pool2d(f1, 3, 2, 1))
-        feats = [f1]
-        for layer in (e.layer1, e.layer2, e.layer3, e.layer4):
-            for blk in layer:
-                idn = t
-                u = _r(F.relu(self._bn(F.conv2d(t, _r(blk.conv1.weight), None, blk.stride, 1), blk.bn1)))
-                if blk.downsample is not None:
-                    idn = _r(self._bn(F.conv2d(t, _r(blk.downsample[0].weight), None, blk.stride, 0),
-                                      blk.downsample[1]))
-                t = _r(F.relu(self._bn(F.conv2d(u, _r(blk.conv2.weight), None, 1, 1), blk.bn2) + idn))
-            feats.append(t)
-        skips = [feats[3], feats[2], feats[1], feats[0], None]
-        cups = [512, 256, 128, 64, 32]
-        for i, blk in enumerate(o.decoder.blocks):
-            z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i])
-            u = _r(F.relu(self._bn(z, blk.conv1[1])))
-            t = _r(F.relu(self._bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
-        head = o.segmentation_head[0]
-        return F.conv2d(t, head.weight, head.bias, 1, 1)
+        return emulated_forward(self.o, x, False)
+
+
+class Bf16EmulatedTrainUnet(torch.nn.Module):
+    """Train-mode forward (batch statistics) with the CUDA path's rounding points and straight-through gradients.
+    Owns a deep copy of the oracle: `.o.named_parameters()` receive the gradients of the rounded-forward network."""
+
+    def __init__(self, oracle):
+        super().__init__()
+        self.o = copy.deepcopy(oracle).train()
+
+    def forward(self, x):
+        return emulated_forward(self.o, x, True)

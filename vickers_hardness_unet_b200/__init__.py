@@ -5,5 +5,7 @@ Public surface mirrors the two smp symbols the reference uses (`Unet`, `losses.D
 from ._lib import UnetB200Error, LIB_PATH  # noqa: F401
 from .unet import Unet  # noqa: F401
 from . import losses  # noqa: F401
+from . import distributed  # noqa: F401
+from .optim import FusedAdamW  # noqa: F401
 
-__all__ = ["Unet", "losses", "UnetB200Error"]
+__all__ = ["Unet", "losses", "distributed", "FusedAdamW", "UnetB200Error"]

@@ -37,6 +37,17 @@ def _proto(lib):
         "unetb200_profile_infer": (i32, [vp, vp, vp, i32, vp, P(f32), P(i32), i32, P(i32)]),
         "unetb200_profile_name": (i32, [vp, i32, i32, C.c_char_p, i32]),
         "unetb200_conv_nhwc": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "unetb200_train_forward": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "unetb200_train_backward": (i32, [vp, vp, i32, i32, i32, vp]),
+        "unetb200_grad_bucket_range": (i32, [i32, P(i64), P(i64)]),
+        "unetb200_train_launch_count": (i32, [vp, i32, P(i32), P(i32)]),
+        "unetb200_train_debug_count": (i32, [vp, i32]),
+        "unetb200_train_debug_info": (i32, [vp, i32, i32, C.c_char_p, i32, P(i32), P(i32)]),
+        "unetb200_train_debug_copy": (i32, [vp, i32, i32, vp, i64, vp]),
+        "unetb200_loss_scratch_floats": (i32, []),
+        "unetb200_loss_bce_dice_forward": (i32, [vp, vp, i64, f32, vp, vp, vp]),
+        "unetb200_loss_bce_dice_backward": (i32, [vp, vp, vp, vp, vp, f32, f32, vp, i64, vp]),
+        "unetb200_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -64,6 +75,24 @@ def load():
         _proto(lib)
         _lib = lib
     return _lib
+
+
+def grad_bucket_ranges():
+    """[(begin, end)] element ranges of the flat gradient array, in backward-completion order (stage 0..3)."""
+    lib = load()
+    out = []
+    for stage in range(4):
+        b, e = C.c_longlong(), C.c_longlong()
+        if lib.unetb200_grad_bucket_range(stage, C.byref(b), C.byref(e)):
+            raise UnetB200Error("grad_bucket_range failed")
+        out.append((b.value, e.value))
+    return out
+
+
+def check_global(rc: int, what: str):
+    """Error check for the ctx-free entry points (loss): message is the thread's last global error."""
+    if rc:
+        raise UnetB200Error(f"{what}: " + load().unetb200_last_error(None).decode())
 
 
 def tensor_table():

@@ -2,7 +2,7 @@
 #include <string.h>
 
 #include "../../include/unetb200.h"
-#include "unet.cuh"
+#include "train.cuh"
 
 using namespace ub;
 
@@ -171,9 +171,8 @@ int unetb200_conv_nhwc(unetb200_ctx* h, const void* in, const float* w, const fl
     const int Ho = H / stride, Wo = W / stride;
     if (residual) ep.residual = nhwc_view(residual, N, Ho, Wo, cout);
     float* part = nullptr;
-    const int mt = igemm_m_tiles(nhwc_view(out, N, Ho, Wo, cout));
     if (stats) {
-        UB_CUDA(cudaMallocAsync(&part, (size_t)mt * cout * 2 * sizeof(float), st));
+        UB_CUDA(cudaMallocAsync(&part, (size_t)ctx->num_sms * cout * 2 * sizeof(float), st));
         ep.stats = part;
     }
     IgemmLaunch L;
@@ -181,11 +180,127 @@ int unetb200_conv_nhwc(unetb200_ctx* h, const void* in, const float* w, const fl
     if (!e.empty()) return ctx_fail(ctx, "conv_nhwc: " + e);
     UB_CUDA(igemm_launch(L, st));
     if (stats) {
-        reduce_partials_kernel<<<(cout * 2 + 127) / 128, 128, 0, st>>>(part, stats, mt, cout * 2);
+        reduce_partials_kernel<<<(cout * 2 + 127) / 128, 128, 0, st>>>(part, stats, L.grid, cout * 2);
         UB_CUDA(cudaGetLastError());
         UB_CUDA(cudaFreeAsync(part, st));
     }
     UB_CUDA(cudaFreeAsync(wpk, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ training step
+int unetb200_train_forward(unetb200_ctx* h, const float* x_dev, float* logits_dev, const float* params_dev,
+                           float* buffers_dev, long long* counters_dev, float* grads_dev, int N, void* stream) {
+    Ctx* ctx = h->c;
+    if (!x_dev || !logits_dev || !params_dev || !buffers_dev || !counters_dev || !grads_dev)
+        return ctx_fail(ctx, "train_forward: null pointer");
+    if (N < 1 || N > ctx->max_batch) return ctx_fail(ctx, "train_forward: batch outside [1, max_batch]");
+    UB_CUDA(cudaSetDevice(ctx->device));
+    return ctx_train_forward(ctx, x_dev, logits_dev, params_dev, buffers_dev, counters_dev, grads_dev, N,
+                             (cudaStream_t)stream);
+}
+
+int unetb200_train_backward(unetb200_ctx* h, const float* dlogits_dev, int N, int stage_first, int stage_last,
+                            void* stream) {
+    Ctx* ctx = h->c;
+    UB_CUDA(cudaSetDevice(ctx->device));
+    return ctx_train_backward(ctx, dlogits_dev, N, stage_first, stage_last, (cudaStream_t)stream);
+}
+
+int unetb200_grad_bucket_range(int stage, long long* begin_out, long long* end_out) {
+    if (stage < 0 || stage > 3 || !begin_out || !end_out) return 1;
+    grad_bucket_range(spec(), stage, begin_out, end_out);
+    return 0;
+}
+
+int unetb200_train_launch_count(unetb200_ctx* h, int N, int* fwd_out, int* bwd_out) {
+    TrainState* T = static_cast<TrainState*>(h->c->train);
+    if (!T) return 1;
+    auto it = T->plans.find(N);
+    if (it == T->plans.end()) return 1;
+    if (fwd_out) *fwd_out = it->second->n_fwd;
+    if (bwd_out) *bwd_out = it->second->n_bwd;
+    return 0;
+}
+
+int unetb200_train_debug_count(unetb200_ctx* h, int N) {
+    TrainState* T = static_cast<TrainState*>(h->c->train);
+    if (!T) return -1;
+    auto it = T->plans.find(N);
+    return it == T->plans.end() ? -1 : (int)it->second->dbg.size();
+}
+int unetb200_train_debug_info(unetb200_ctx* h, int N, int index, char* name_out, int name_cap, int shape_out[4],
+                              int* is_bf16_out) {
+    TrainState* T = static_cast<TrainState*>(h->c->train);
+    if (!T) return 1;
+    auto it = T->plans.find(N);
+    if (it == T->plans.end() || index < 0 || index >= (int)it->second->dbg.size()) return 1;
+    const TrainPlan::Dbg& d = it->second->dbg[index];
+    if (name_out && name_cap > 0) {
+        strncpy(name_out, d.name.c_str(), name_cap - 1);
+        name_out[name_cap - 1] = 0;
+    }
+    if (shape_out) { shape_out[0] = d.n; shape_out[1] = d.h; shape_out[2] = d.w; shape_out[3] = d.c; }
+    if (is_bf16_out) *is_bf16_out = d.bf16;
+    return 0;
+}
+int unetb200_train_debug_copy(unetb200_ctx* h, int N, int index, void* dst_dev, long long cap_bytes, void* stream) {
+    Ctx* ctx = h->c;
+    TrainState* T = static_cast<TrainState*>(ctx->train);
+    if (!T) return ctx_fail(ctx, "train_debug_copy: no training state");
+    auto it = T->plans.find(N);
+    if (it == T->plans.end() || index < 0 || index >= (int)it->second->dbg.size())
+        return ctx_fail(ctx, "train_debug_copy: bad index");
+    const TrainPlan::Dbg& d = it->second->dbg[index];
+    const long long bytes = (long long)d.n * d.h * d.w * d.c * (d.bf16 ? 2 : 4);
+    if (bytes > cap_bytes) return ctx_fail(ctx, "train_debug_copy: destination too small");
+    UB_CUDA(cudaMemcpyAsync(dst_dev, d.ptr, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+static int loss_fail(const char* msg) {
+    g_create_error = msg;
+    return 1;
+}
+int unetb200_loss_scratch_floats(void) { return 4 * 1024; }
+
+int unetb200_loss_bce_dice_forward(const float* logits_dev, const float* target_dev, long long n, float eps,
+                                   float* scratch_dev, float* result_dev, void* stream) {
+    if (!logits_dev || !target_dev || !result_dev || !scratch_dev || n < 1) return loss_fail("loss_forward: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long nb = (n + 1023) / 1024;
+    if (nb > 1024) nb = 1024;
+    loss_partial_kernel<<<(int)nb, 256, 0, st>>>(logits_dev, target_dev, scratch_dev, n);
+    loss_finalize_kernel<<<1, 32, 0, st>>>(scratch_dev, (int)nb, (double)n, eps, result_dev);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
+}
+
+int unetb200_loss_bce_dice_backward(const float* logits_dev, const float* target_dev, const float* result_dev,
+                                    const float* g_bce_dev, const float* g_dice_dev, float gscale, float eps,
+                                    float* dlogits_dev, long long n, void* stream) {
+    if (!logits_dev || !target_dev || !result_dev || !dlogits_dev || n < 1) return loss_fail("loss_backward: bad argument");
+    long long nb = (n + 1023) / 1024;
+    if (nb > 148 * 16) nb = 148 * 16;
+    loss_bwd_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(logits_dev, target_dev, result_dev, g_bce_dev, g_dice_dev,
+                                                               gscale, eps, dlogits_dev, n);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
+}
+
+int unetb200_adamw_step(unetb200_ctx* h, float* params_dev, float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                        long long n, float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
+                        float grad_scale, int zero_grad, void* stream) {
+    Ctx* ctx = h->c;
+    if (!params_dev || !grads_dev || !exp_avg_dev || !exp_avg_sq_dev || n < 1 || step < 1)
+        return ctx_fail(ctx, "adamw_step: bad argument");
+    UB_CUDA(cudaSetDevice(ctx->device));
+    const float bc1 = 1.f - (float)pow((double)beta1, (double)step);
+    const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    adamw_kernel<<<ew_grid(n / 4 + 4, 256, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        params_dev, grads_dev, exp_avg_dev, exp_avg_sq_dev, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale,
+        zero_grad);
+    UB_CUDA(cudaGetLastError());
     return 0;
 }
 

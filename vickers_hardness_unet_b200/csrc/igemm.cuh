@@ -41,13 +41,13 @@ struct IgemmParams {
     int relu;
     const __nv_bfloat16* residual;           // NHWC-strided bf16 or nullptr
     long long res_sw, res_sh, res_sn;        // element strides of the residual
-    float* stats;                            // [m_tiles][cout][2] (sum, sumsq of the bf16 output) or nullptr
+    float* stats;                            // [gridDim.x][cout][2] per-CTA (sum, sumsq of the bf16 output) or nullptr
     int* err;                                // device error flag (set on pipeline timeout)
 };
 
 // dynamic shared memory carve-up (all offsets relative to a 1024-aligned base)
 struct IgemmSmem {
-    uint32_t a_bytes, b_bytes, stage_bytes, staging_off, staging_bytes, ss_off, part_off, bar_off, total;
+    uint32_t a_bytes, b_bytes, stage_bytes, staging_off, staging_bytes, ss_off, part_off, cstat_off, bar_off, total;
 };
 __host__ __device__ inline IgemmSmem igemm_smem(int ntile, int chunk_elems, int stages, int out_cblk) {
     IgemmSmem s;
@@ -59,7 +59,8 @@ __host__ __device__ inline IgemmSmem igemm_smem(int ntile, int chunk_elems, int 
     s.staging_bytes = 128 * out_cblk * 2;   // x2 buffers
     s.ss_off = s.staging_off + 2 * s.staging_bytes;
     s.part_off = s.ss_off + 2 * 512 * 4;    // scale/shift for up to 512 channels
-    s.bar_off = s.part_off + 8 * 64 * 2 * 4;  // stats partials [8 groups][64 ch][2]
+    s.cstat_off = s.part_off + 8 * 64 * 2 * 4;  // stats partials [8 groups][64 ch][2]
+    s.bar_off = s.cstat_off + 512 * 2 * 4;      // per-CTA running statistics [512 ch][2]
     s.total = s.bar_off + (2 * stages + 4) * 8 + 16;
     return s;
 }
@@ -111,9 +112,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     // per-channel scale/shift -> smem (identity when absent)
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);
+        float* cst = reinterpret_cast<float*>(sm + L.cstat_off);
         for (int c = threadIdx.x; c < 512; c += blockDim.x) {
             ss[c] = (P.scale && c < P.cout) ? P.scale[c] : 1.f;
             ss[512 + c] = (P.shift && c < P.cout) ? P.shift[c] : 0.f;
+            cst[2 * c] = 0.f;
+            cst[2 * c + 1] = 0.f;
         }
     }
     tc_fence_before();
@@ -211,6 +215,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         const int et = threadIdx.x - 64;        // 0..127
         const float* ss = reinterpret_cast<const float*>(sm + L.ss_off);
         float* part = reinterpret_cast<float*>(sm + L.part_off);
+        float* cst = reinterpret_cast<float*>(sm + L.cstat_off);
         const int cblk = P.out_cblk;
         const int nblk = P.ntile / cblk;
         const uint32_t row_bytes = cblk * 2;
@@ -221,7 +226,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % P.n_tiles;
             int m = tile / P.n_tiles;
-            const int m_tile = m;
             const int tw = m % P.tiles_w;
             m /= P.tiles_w;
             const int th = m % P.tiles_h;
@@ -327,15 +331,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                             t1 += part[(gg * 64 + et) * 2 + 0];
                             t2 += part[(gg * 64 + et) * 2 + 1];
                         }
-                        float* dst = P.stats + (static_cast<size_t>(m_tile) * P.cout + cbase + et) * 2;
-                        dst[0] = t1;
-                        dst[1] = t2;
+                        // channel cbase+et is always owned by this thread (et == channel % cblk): no race
+                        cst[2 * (cbase + et)] += t1;
+                        cst[2 * (cbase + et) + 1] += t2;
                     }
                     // `part` is rewritten only after the next block's named_bar_sync(1), which orders it after these reads
                 }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
+        if (P.stats) {
+            named_bar_sync(3, 128);
+            float* dst = P.stats + static_cast<size_t>(blockIdx.x) * P.cout * 2;
+            for (int j = et; j < 2 * P.cout; j += 128) dst[j] = cst[j];
         }
         if (et == 0) tma_wait_all<0>();  // all output stores complete before the CTA exits
     }

@@ -1,0 +1,875 @@
+// Training-step orchestration: forward with batch-statistics BatchNorm, backward (dgrad / wgrad / BN / pool / head),
+// on top of igemm_kernel, wgrad_kernel and the elementwise kernels.  Mirrors /root/reference/train.py:428-449
+// (zero_grad -> forward -> loss -> backward -> optimizer.step) with the autograd graph written out by hand.
+#pragma once
+#include <memory>
+
+#include "train_ops.cuh"
+#include "unet.cuh"
+#include "wgrad.cuh"
+
+namespace ub {
+
+typedef std::function<cudaError_t(cudaStream_t)> LaunchFn;
+
+struct WgLaunch {
+    CUtensorMap z, x;
+    WgParams p;
+    int grid = 0, max_ncin = 0;
+    uint32_t smem = 0;
+};
+inline cudaError_t wg_launch(const WgLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    wgrad_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.z, L.x, L.p, L.max_ncin);
+    return cudaGetLastError();
+}
+
+// One BN-normalised conv unit of the network and everything its backward needs.
+struct Unit {
+    int conv = -1;                 // index into spec.convs
+    int N = 0, Hin = 0, Win = 0, Ho = 0, Wo = 0;
+    __nv_bfloat16* z = nullptr;    // raw conv output
+    __nv_bfloat16* a = nullptr;    // activation after BN (+residual) (+ReLU)
+    __nv_bfloat16* dz = nullptr;   // gradient w.r.t. z
+    float* mean = nullptr;         // [C] batch mean / invstd / scale / shift / backward coefficients
+    float* invstd = nullptr;
+    float* scale = nullptr;
+    float* shift = nullptr;
+    float* coef = nullptr;
+};
+
+struct TrainPlan {
+    int N = 0;
+    __nv_bfloat16* xp = nullptr;
+    __nv_bfloat16* head_in = nullptr;   // activation feeding the seg head
+    __nv_bfloat16* d_head_in = nullptr; // its gradient
+    std::vector<Unit> units;
+    std::vector<LaunchFn> fwd;          // after input pack, before head
+    std::vector<LaunchFn> bwd[4];       // stage 0: decoder, 1: layer4, 2: layer3, 3: layer2 + layer1 + stem
+    int n_fwd = 0, n_bwd = 0;
+    // scratch
+    float* stat_part = nullptr;         // conv-epilogue statistic partials [4][num_sms][512][2]
+    float* red_part = nullptr;          // reduction partials (BN backward / head / loss)
+    WgItem* items = nullptr;            // device work-item arena for all wgrad launches
+    size_t items_cap = 0, items_used = 0;
+    std::vector<WgItem> host_items;
+    // named internal tensors for layer-local parity tests (unetb200_train_debug_copy)
+    struct Dbg { std::string name; const void* ptr; int n, h, w, c; int bf16; };
+    std::vector<Dbg> dbg;
+    // identity of the caller-owned tensors the launch closures captured
+    const float* params = nullptr;
+    float* buffers = nullptr;
+    long long* counters = nullptr;
+    float* grads = nullptr;
+    TrainPlan() = default;
+    TrainPlan(const TrainPlan&) = delete;
+    TrainPlan& operator=(const TrainPlan&) = delete;
+    ~TrainPlan() { cudaFree(items); }
+};
+
+struct TrainState {
+    std::map<int, std::unique_ptr<TrainPlan>> plans;
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    int arena_batch = 0;
+    __nv_bfloat16* wdg = nullptr;   // packed dgrad operands
+    long long wdg_total = 0;
+    std::vector<long long> wdg_off;       // per conv: offset of its dgrad operand(s)
+    std::vector<long long> wdg_off2;      // decoder conv1: dLow operand
+    ~TrainState() {
+        plans.clear();
+        cudaFree(arena);
+        cudaFree(wdg);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ dgrad operand layout
+// stride-2 3x3 conv: 4 parity matrices, taps per parity 1/2/2/4 (+1 downsample tap on parity 0)
+inline void s2_parity_taps(int par, TapList& tl, int dh[4], int dw[4]) {
+    const int ph = par >> 1, pw = par & 1;
+    int rr[2], rdh[2], nr = 0, ss[2], sdw[2], ns = 0;
+    if (ph == 0) { rr[0] = 1; rdh[0] = 0; nr = 1; } else { rr[0] = 0; rdh[0] = 1; rr[1] = 2; rdh[1] = 0; nr = 2; }
+    if (pw == 0) { ss[0] = 1; sdw[0] = 0; ns = 1; } else { ss[0] = 0; sdw[0] = 1; ss[1] = 2; sdw[1] = 0; ns = 2; }
+    tl.n = 0;
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < ns; ++j) {
+            tl.r[tl.n] = rr[i];
+            tl.s[tl.n] = ss[j];
+            dh[tl.n] = rdh[i];
+            dw[tl.n] = sdw[j];
+            tl.n++;
+        }
+}
+
+inline void train_layout_dgrad(Ctx* ctx, TrainState& T) {
+    const NetSpec& S = ctx->spec;
+    T.wdg_off.assign(S.convs.size(), -1);
+    T.wdg_off2.assign(S.convs.size(), -1);
+    long long off = 0;
+    auto take = [&](long long n) {
+        long long o = off;
+        off += (n + 63) & ~63ll;
+        return o;
+    };
+    for (size_t i = 0; i < S.convs.size(); ++i) {
+        const ConvRef& c = S.convs[i];
+        if ((int)i == S.stem || (int)i == S.head) continue;
+        bool is_ds = false;
+        for (int l = 0; l < 4; ++l)
+            for (auto& b : S.enc_blocks[l]) if (b.ds == (int)i) is_ds = true;
+        if (is_ds) continue;  // folded into the owning block's conv1 parity-0 operand
+        const NetSpec::Dec* dd = nullptr;
+        for (auto& d : S.dec) if (d.c1 == (int)i) dd = &d;
+        if (dd) {
+            if (dd->cskip) T.wdg_off[i] = take((long long)dd->cskip * 9 * dd->cout);
+            T.wdg_off2[i] = take((long long)dd->cup * 16 * dd->cout);
+        } else if (c.stride == 2) {
+            // 4 parity matrices [cin][(ntaps (+1 ds)) * cout]; ds exists for every stride-2 conv1 of this network
+            T.wdg_off[i] = take((long long)c.cin * (9 + 1) * c.cout);
+        } else {
+            T.wdg_off[i] = take((long long)c.cin * 9 * c.cout);
+        }
+    }
+    T.wdg_total = off;
+}
+
+inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaStream_t st) {
+    const NetSpec& S = ctx->spec;
+    auto grid = [&](long long n) { return ew_grid(n, 256, ctx->num_sms); };
+    for (size_t i = 0; i < S.convs.size(); ++i) {
+        if (T.wdg_off[i] < 0 && T.wdg_off2[i] < 0) continue;
+        const ConvRef& c = S.convs[i];
+        const NetSpec::Dec* dd = nullptr;
+        for (auto& d : S.dec) if (d.c1 == (int)i) dd = &d;
+        if (dd) {
+            const int cin_total = dd->cup + dd->cskip;
+            if (dd->cskip) {
+                TapList tl;
+                tl.n = 9;
+                for (int t = 0; t < 9; ++t) { tl.r[t] = 2 - t / 3; tl.s[t] = 2 - t % 3; }
+                pack_dgrad_w_kernel<<<grid((long long)dd->cskip * 9 * dd->cout), 256, 0, st>>>(
+                    params + c.w, T.wdg + T.wdg_off[i], dd->cout, cin_total, dd->cup, dd->cskip, 3, 3, 9 * dd->cout, 0, tl);
+            }
+            pack_dec1_dlow_w_kernel<<<grid((long long)dd->cup * 16 * dd->cout), 256, 0, st>>>(
+                params + c.w, T.wdg + T.wdg_off2[i], dd->cout, dd->cup, cin_total);
+        } else if (c.stride == 2) {
+            // find the block's downsample conv
+            int ds = -1;
+            for (int l = 0; l < 4; ++l)
+                for (auto& b : S.enc_blocks[l]) if (b.c1 == (int)i) ds = b.ds;
+            long long o = T.wdg_off[i];
+            for (int par = 0; par < 4; ++par) {
+                TapList tl;
+                int dh[4], dw[4];
+                s2_parity_taps(par, tl, dh, dw);
+                const int ncols = (tl.n + (par == 0 ? 1 : 0)) * c.cout;
+                pack_dgrad_w_kernel<<<grid((long long)c.cin * tl.n * c.cout), 256, 0, st>>>(
+                    params + c.w, T.wdg + o, c.cout, c.cin, 0, c.cin, 3, 3, ncols, 0, tl);
+                if (par == 0) {
+                    TapList t1;
+                    t1.n = 1; t1.r[0] = 0; t1.s[0] = 0;
+                    pack_dgrad_w_kernel<<<grid((long long)c.cin * c.cout), 256, 0, st>>>(
+                        params + S.convs[ds].w, T.wdg + o, c.cout, c.cin, 0, c.cin, 1, 1, ncols, tl.n * c.cout, t1);
+                }
+                o += (long long)c.cin * ncols;
+            }
+        } else {
+            pack_conv_w_kernel<<<grid((long long)c.cin * 9 * c.cout), 256, 0, st>>>(params + c.w, T.wdg + T.wdg_off[i],
+                                                                                   c.cout, c.cin, 3, 3, 1);
+        }
+    }
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad launch builder
+struct WgSpec {
+    View4 z;              // dZ view (M side), extents define the pixel-tile grid
+    View4 x;              // source view (N side)
+    int es_w = 1, es_h = 1;
+    int cout = 0;
+    int nsrc_c = 0;       // number of source channels to cover starting at x_c0
+    int x_c0 = 0;
+    int dci0 = 0;         // destination channel offset
+    struct Tap { int dw, dh, ndst, dst[4]; };
+    std::vector<Tap> taps;
+    float* grad = nullptr;
+    long long s_co = 0, s_ci = 0;
+    int stem_mode = 0;
+};
+
+inline std::string wg_build(Ctx* ctx, TrainPlan& plan, WgLaunch& L, const WgSpec& s) {
+    memset(&L, 0, sizeof(L));
+    WgParams& P = L.p;
+    igemm_tile_shape(s.z, P.bw, P.bh, P.bn);
+    P.tiles_w = (s.z.W + P.bw - 1) / P.bw;
+    P.tiles_h = (s.z.H + P.bh - 1) / P.bh;
+    P.tiles_n = (s.z.N + P.bn - 1) / P.bn;
+    P.mulw = s.es_w; P.mulh = s.es_h;
+    P.cout = s.cout;
+    P.zc_box = s.cout < 64 ? s.cout : 64;
+    P.xc_box = s.nsrc_c < 64 ? s.nsrc_c : 64;
+    P.grad = s.grad; P.s_co = s.s_co; P.s_ci = s.s_ci; P.stem_mode = s.stem_mode;
+    P.err = ctx->d_err;
+    const int ncin_tile = s.nsrc_c < 256 ? s.nsrc_c : 256;
+    L.max_ncin = ncin_tile;
+    const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    const int co_tiles = (s.cout + 127) / 128, ci_tiles = (s.nsrc_c + ncin_tile - 1) / ncin_tile;
+    const int base_items = co_tiles * ci_tiles * (int)s.taps.size();
+    int splits = (3 * ctx->num_sms + base_items - 1) / base_items;
+    if (splits > total_tiles) splits = total_tiles;
+    if (splits < 1) splits = 1;
+    // keep at least 4 pixel tiles per item where possible
+    while (splits > 1 && total_tiles / splits < 4) --splits;
+    const size_t first = plan.host_items.size();
+    for (int sp = 0; sp < splits; ++sp) {
+        const int tb = (int)((long long)total_tiles * sp / splits), te = (int)((long long)total_tiles * (sp + 1) / splits);
+        if (te <= tb) continue;
+        for (size_t t = 0; t < s.taps.size(); ++t)
+            for (int ct = 0; ct < co_tiles; ++ct)
+                for (int it = 0; it < ci_tiles; ++it) {
+                    WgItem w;
+                    memset(&w, 0, sizeof(w));
+                    w.co0 = ct * 128;
+                    w.ci0 = s.x_c0 + it * ncin_tile;
+                    w.dci0 = s.dci0 + it * ncin_tile;
+                    w.ncin = (s.nsrc_c - it * ncin_tile) < ncin_tile ? (s.nsrc_c - it * ncin_tile) : ncin_tile;
+                    w.dw = s.taps[t].dw; w.dh = s.taps[t].dh;
+                    w.tile_begin = tb; w.tile_end = te;
+                    w.ndst = s.taps[t].ndst;
+                    for (int d = 0; d < 4; ++d) w.dst_off[d] = s.taps[t].dst[d];
+                    plan.host_items.push_back(w);
+                }
+    }
+    P.num_items = (int)(plan.host_items.size() - first);
+    P.items = reinterpret_cast<const WgItem*>(first);  // patched to a device pointer once the arena is uploaded
+    int stages = 4;
+    for (; stages >= 2; --stages)
+        if (wg_smem(P.zc_box, P.xc_box, ncin_tile, stages).total + 1024 <= 232448u) break;
+    if (stages < 2) return "wgrad tile does not fit in shared memory";
+    P.stages = stages;
+    L.smem = wg_smem(P.zc_box, P.xc_box, ncin_tile, stages).total + 1024;
+    L.grid = P.num_items < ctx->num_sms ? P.num_items : ctx->num_sms;
+    {
+        uint64_t dims[4] = {(uint64_t)s.z.C, (uint64_t)s.z.W, (uint64_t)s.z.H, (uint64_t)s.z.N};
+        uint64_t str[3] = {(uint64_t)s.z.sW * 2, (uint64_t)s.z.sH * 2, (uint64_t)s.z.sN * 2};
+        uint32_t box[4] = {(uint32_t)P.zc_box, (uint32_t)P.bw, (uint32_t)P.bh, (uint32_t)P.bn};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.z, s.z.ptr, 4, dims, str, box, es, swizzle_for_bytes(P.zc_box * 2));
+        if (!e.empty()) return "Z map: " + e;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)s.x.C, (uint64_t)s.x.W, (uint64_t)s.x.H, (uint64_t)s.x.N};
+        uint64_t str[3] = {(uint64_t)s.x.sW * 2, (uint64_t)s.x.sH * 2, (uint64_t)s.x.sN * 2};
+        uint32_t box[4] = {(uint32_t)P.xc_box, (uint32_t)(P.bw * s.es_w), (uint32_t)(P.bh * s.es_h), (uint32_t)P.bn};
+        uint32_t es[4] = {1, (uint32_t)s.es_w, (uint32_t)s.es_h, 1};
+        std::string e = make_tmap_bf16(&L.x, s.x.ptr, 4, dims, str, box, es, swizzle_for_bytes(P.xc_box * 2));
+        if (!e.empty()) return "X map: " + e;
+    }
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------ plan builder
+struct FloatCarver {
+    float* base;
+    size_t off = 0;
+    explicit FloatCarver(float* b) : base(b) {}
+    float* take(size_t n) {
+        float* p = base ? base + off : nullptr;
+        off += (n + 63) & ~size_t(63);
+        return p;
+    }
+};
+
+inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& plan, bool dry, size_t* arena_needed,
+                                    float* grads /* flat fp32 gradient buffer */, const float* params, float* buffers,
+                                    long long* counters) {
+    const NetSpec& S = ctx->spec;
+    const int H = ctx->H, W = ctx->W, SM = ctx->num_sms;
+    ArenaCarver A(dry ? nullptr : T.arena, T.arena_bytes);
+    plan.N = N;
+    plan.params = params; plan.buffers = buffers; plan.counters = counters; plan.grads = grads;
+    plan.units.clear();
+    plan.dbg.clear();
+    plan.fwd.clear();
+    for (auto& b : plan.bwd) b.clear();
+    plan.host_items.clear();
+    std::string err;
+
+    // fp32 scratch carved from the same arena
+    auto take_f = [&](size_t n) { return reinterpret_cast<float*>(A.take((long long)n * 2)); };
+    plan.stat_part = take_f((size_t)4 * SM * 512 * 2);
+    plan.red_part = take_f((size_t)2048 * 512 * 2);
+
+    auto new_unit = [&](int conv, int Hin, int Win) -> int {
+        const ConvRef& c = S.convs[conv];
+        Unit u;
+        u.conv = conv; u.N = N; u.Hin = Hin; u.Win = Win;
+        u.Ho = Hin / c.stride; u.Wo = Win / c.stride;
+        const long long n = (long long)N * u.Ho * u.Wo * c.cout;
+        u.z = A.take(n); u.a = A.take(n); u.dz = A.take(n);
+        u.mean = take_f(c.cout); u.invstd = take_f(c.cout); u.scale = take_f(c.cout); u.shift = take_f(c.cout);
+        u.coef = take_f(3 * c.cout);
+        plan.units.push_back(u);
+        return (int)plan.units.size() - 1;
+    };
+    auto add_f = [&](LaunchFn f) { plan.fwd.push_back(std::move(f)); };
+    // BN finalize + apply after a conv whose statistics partial rows are described by segs
+    auto add_bn_fwd = [&](int ui, StatSegs segs, const __nv_bfloat16* residual, int relu) {
+        const Unit u = plan.units[ui];
+        const ConvRef& c = S.convs[u.conv];
+        const BnRef& b = S.bns[c.bn];
+        const double count = (double)N * u.Ho * u.Wo;
+        const long long npix = (long long)N * u.Ho * u.Wo;
+        float* rm = buffers + b.mean;
+        float* rv = buffers + b.var;
+        long long* cnt = counters + b.counter;
+        const float* gm = params + b.gamma;
+        const float* bt = params + b.beta;
+        const int C = c.cout;
+        add_f([=](cudaStream_t st) {
+            bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(segs, C, count, gm, bt, rm, rv, cnt, 0.1f, 1e-5f,
+                                                               u.scale, u.shift, u.mean, u.invstd);
+            return cudaGetLastError();
+        });
+        add_f([=](cudaStream_t st) {
+            bn_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(u.z, u.scale, u.shift, residual, relu, u.a,
+                                                                             npix, C);
+            return cudaGetLastError();
+        });
+    };
+
+    // ---------------------------------------------------------------- forward graph
+    plan.xp = A.take((long long)N * H * (W + 8) * 4);
+    struct BlockRec { int u1, u2, ud; __nv_bfloat16* x_in; __nv_bfloat16* g; int layer; };
+    std::vector<BlockRec> blocks;
+    struct DecRec { int u1, u2; __nv_bfloat16* low; __nv_bfloat16* skip; __nv_bfloat16* d_skip; int Hl, Wl; };
+    std::vector<DecRec> decs;
+
+    auto fwd_unit = [&](int ui, const void* in, const __nv_bfloat16* residual, int relu) -> std::string {
+        const Unit u = plan.units[ui];
+        const ConvRef& c = S.convs[u.conv];
+        if (dry) return "";
+        EpilogueDesc ep;
+        ep.stats = plan.stat_part;
+        IgemmLaunch L;
+        std::string e = (u.conv == S.stem)
+                            ? build_stem(ctx, L, ctx->wpk + c.wpk, in, N, H, W, u.z, ep)
+                            : build_conv(ctx, L, c, ctx->wpk + c.wpk, in, N, u.Hin, u.Win, u.z, ep);
+        if (!e.empty()) return c.name + ": " + e;
+        add_f([L](cudaStream_t st) { return igemm_launch(L, st); });
+        StatSegs segs;
+        memset(&segs, 0, sizeof(segs));
+        segs.n = 1; segs.ptr[0] = plan.stat_part; segs.rows[0] = L.grid;
+        add_bn_fwd(ui, segs, residual, relu);
+        return "";
+    };
+
+    const int u_stem = new_unit(S.stem, H, W);
+    if (!(err = fwd_unit(u_stem, plan.xp, nullptr, 1)).empty()) return err;
+    __nv_bfloat16* f1 = plan.units[u_stem].a;
+    int h = H / 4, w = W / 4;
+    __nv_bfloat16* p1 = A.take((long long)N * h * w * 64);
+    __nv_bfloat16* d_p1 = A.take((long long)N * h * w * 64);
+    if (!dry) {
+        const int Hh = H / 2, Wh = W / 2;
+        add_f([=](cudaStream_t st) {
+            maxpool3x3s2_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, SM), 256, 0, st>>>(f1, p1, N, Hh,
+                                                                                                        Wh, 64);
+            return cudaGetLastError();
+        });
+    }
+    __nv_bfloat16* cur = p1;
+    __nv_bfloat16* feats[5] = {f1, nullptr, nullptr, nullptr, nullptr};
+    for (int l = 0; l < 4; ++l) {
+        for (size_t b = 0; b < S.enc_blocks[l].size(); ++b) {
+            const NetSpec::Block& blk = S.enc_blocks[l][b];
+            BlockRec r;
+            r.layer = l;
+            r.x_in = cur;
+            r.u1 = new_unit(blk.c1, h, w);
+            const int ho = plan.units[r.u1].Ho, wo = plan.units[r.u1].Wo;
+            r.u2 = new_unit(blk.c2, ho, wo);
+            r.ud = blk.ds >= 0 ? new_unit(blk.ds, h, w) : -1;
+            r.g = A.take((long long)N * ho * wo * S.convs[blk.c2].cout);
+            if (!(err = fwd_unit(r.u1, cur, nullptr, 1)).empty()) return err;
+            const __nv_bfloat16* ident = cur;
+            if (r.ud >= 0) {
+                if (!(err = fwd_unit(r.ud, cur, nullptr, 0)).empty()) return err;
+                ident = plan.units[r.ud].a;
+            }
+            if (!(err = fwd_unit(r.u2, plan.units[r.u1].a, ident, 1)).empty()) return err;
+            cur = plan.units[r.u2].a;
+            h = ho; w = wo;
+            blocks.push_back(r);
+        }
+        feats[l + 1] = cur;
+    }
+    __nv_bfloat16* skips[5] = {feats[3], feats[2], feats[1], feats[0], nullptr};
+    const int skip_c[5] = {256, 128, 64, 64, 0};
+    __nv_bfloat16* d_skips[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 5; ++i) {
+        const NetSpec::Dec& d = S.dec[i];
+        DecRec r;
+        r.low = cur; r.skip = skips[i]; r.Hl = h; r.Wl = w;
+        r.d_skip = skip_c[i] ? A.take((long long)N * (2 * h) * (2 * w) * skip_c[i]) : nullptr;
+        d_skips[i] = r.d_skip;
+        // unit 1: output at 2h x 2w; Hin/Win recorded as the OUTPUT resolution (stride-1 bookkeeping)
+        r.u1 = new_unit(d.c1, 2 * h, 2 * w);
+        r.u2 = new_unit(d.c2, 2 * h, 2 * w);
+        if (!dry) {
+            const Unit u1 = plan.units[r.u1];
+            StatSegs segs;
+            memset(&segs, 0, sizeof(segs));
+            segs.n = 4;
+            for (int par = 0; par < 4; ++par) {
+                EpilogueDesc ep;
+                ep.stats = plan.stat_part + (size_t)par * SM * 512 * 2;
+                IgemmLaunch L;
+                err = build_dec1(ctx, L, d, ctx->wpk + S.convs[d.c1].wpk, par, cur, skips[i], N, h, w, u1.z, ep);
+                if (!err.empty()) return S.convs[d.c1].name + ": " + err;
+                add_f([L](cudaStream_t st) { return igemm_launch(L, st); });
+                segs.ptr[par] = ep.stats;
+                segs.rows[par] = L.grid;
+            }
+            add_bn_fwd(r.u1, segs, nullptr, 1);
+        }
+        if (!(err = fwd_unit(r.u2, plan.units[r.u1].a, nullptr, 1)).empty()) return err;
+        cur = plan.units[r.u2].a;
+        h *= 2; w *= 2;
+        decs.push_back(r);
+    }
+    plan.head_in = cur;
+    plan.d_head_in = A.take((long long)N * H * W * 16);
+    // gradient buffers w.r.t. unit outputs `a` (dA): one per unit
+    std::vector<__nv_bfloat16*> dA(plan.units.size(), nullptr);
+    for (size_t i = 0; i < plan.units.size(); ++i) {
+        const Unit& u = plan.units[i];
+        dA[i] = A.take((long long)N * u.Ho * u.Wo * S.convs[u.conv].cout);
+    }
+    if (arena_needed) *arena_needed = A.off;
+    if (dry) return "";
+    {
+        auto reg = [&](const std::string& nm, const void* p, int n, int hh, int ww, int c, int bf) {
+            plan.dbg.push_back({nm, p, n, hh, ww, c, bf});
+        };
+        for (size_t i = 0; i < plan.units.size(); ++i) {
+            const Unit& u = plan.units[i];
+            const ConvRef& c = S.convs[u.conv];
+            reg(c.name + "/z", u.z, N, u.Ho, u.Wo, c.cout, 1);
+            reg(c.name + "/a", u.a, N, u.Ho, u.Wo, c.cout, 1);
+            reg(c.name + "/dz", u.dz, N, u.Ho, u.Wo, c.cout, 1);
+            reg(c.name + "/dA", dA[i], N, u.Ho, u.Wo, c.cout, 1);
+            reg(c.name + "/mean", u.mean, 1, 1, 1, c.cout, 0);
+            reg(c.name + "/invstd", u.invstd, 1, 1, 1, c.cout, 0);
+        }
+        reg("pool/out", p1, N, H / 4, W / 4, 64, 1);
+        reg("pool/dout", d_p1, N, H / 4, W / 4, 64, 1);
+        for (auto& r : blocks) {
+            const Unit& u2 = plan.units[r.u2];
+            reg(S.convs[u2.conv].name + "/g", r.g, N, u2.Ho, u2.Wo, S.convs[u2.conv].cout, 1);
+        }
+        for (int i = 0; i < 4; ++i)
+            reg("decoder.blocks." + std::to_string(i) + "/d_skip", decs[i].d_skip, N, 2 * decs[i].Hl, 2 * decs[i].Wl,
+                skip_c[i], 1);
+        reg("head/in", plan.head_in, N, H, W, 16, 1);
+        reg("head/din", plan.d_head_in, N, H, W, 16, 1);
+    }
+
+    // ---------------------------------------------------------------- backward graph
+    std::vector<WgLaunch> wgs;  // collected to patch item pointers after upload
+    std::vector<std::pair<int, int>> wg_pos;
+    auto add_b = [&](int stage, LaunchFn f) { plan.bwd[stage].push_back(std::move(f)); };
+    // BN backward of unit ui given dA_in (gradient w.r.t. `a`): dz (+ optional masked gradient g_out)
+    auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out) {
+        const Unit u = plan.units[ui];
+        const ConvRef& c = S.convs[u.conv];
+        const BnRef& b = S.bns[c.bn];
+        const long long npix = (long long)N * u.Ho * u.Wo;
+        const int C = c.cout;
+        const int ppb = 256 / (C / 8);
+        long long nb = (npix + ppb - 1) / ppb;
+        if (nb > 2 * SM) nb = 2 * SM;
+        const int nblocks = (int)nb;
+        float* part = plan.red_part;
+        const __nv_bfloat16* mask = relu_mask ? u.a : nullptr;
+        const float* gm = params + b.gamma;
+        float* dgm = grads + b.gamma;
+        float* dbt = grads + b.beta;
+        add_b(stage, [=](cudaStream_t st) {
+            bn_bwd_reduce_kernel<<<nblocks, 256, 0, st>>>(dA_in, mask, u.z, u.mean, u.invstd, part, npix, C);
+            return cudaGetLastError();
+        });
+        add_b(stage, [=](cudaStream_t st) {
+            bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nblocks, C, (double)npix, gm, u.invstd, dgm,
+                                                                   dbt, u.coef);
+            return cudaGetLastError();
+        });
+        add_b(stage, [=](cudaStream_t st) {
+            bn_bwd_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(dA_in, mask, u.z, u.mean, u.invstd,
+                                                                                 u.coef, u.dz, g_out, npix, C);
+            return cudaGetLastError();
+        });
+    };
+    auto add_wg = [&](int stage, const WgSpec& s) -> std::string {
+        WgLaunch L;
+        std::string e = wg_build(ctx, plan, L, s);
+        if (!e.empty()) return e;
+        wgs.push_back(L);
+        wg_pos.push_back({stage, (int)plan.bwd[stage].size()});
+        add_b(stage, LaunchFn());  // placeholder, filled after the item arena is uploaded
+        return "";
+    };
+    auto wg_conv3 = [&](int stage, int ui, const void* x_in, int x_C, int x_H, int x_W) -> std::string {
+        // regular k x k conv weight gradient
+        const Unit u = plan.units[ui];
+        const ConvRef& c = S.convs[u.conv];
+        WgSpec s;
+        s.z = nhwc_view(u.dz, N, u.Ho, u.Wo, c.cout);
+        s.x = nhwc_view(x_in, N, x_H, x_W, x_C);
+        s.es_w = s.es_h = c.stride;
+        s.cout = c.cout; s.nsrc_c = c.cin; s.x_c0 = 0; s.dci0 = 0;
+        s.grad = grads + c.w;
+        s.s_co = (long long)c.cin * c.k * c.k; s.s_ci = c.k * c.k;
+        for (int r = 0; r < c.k; ++r)
+            for (int q = 0; q < c.k; ++q) {
+                WgSpec::Tap t;
+                t.dh = r - c.k / 2; t.dw = q - c.k / 2; t.ndst = 1;
+                t.dst[0] = r * c.k + q; t.dst[1] = t.dst[2] = t.dst[3] = 0;
+                s.taps.push_back(t);
+            }
+        return add_wg(stage, s);
+    };
+    auto dgrad3 = [&](int stage, int ui, __nv_bfloat16* out, const __nv_bfloat16* residual) -> std::string {
+        // stride-1 3x3 conv: dX = conv(dZ, W^T flipped) (+ residual)
+        const Unit u = plan.units[ui];
+        const ConvRef& c = S.convs[u.conv];
+        ConvRef t;
+        t.cin = c.cout; t.cout = c.cin; t.k = 3; t.stride = 1;
+        EpilogueDesc ep;
+        if (residual) ep.residual = nhwc_view(residual, N, u.Hin, u.Win, c.cin);
+        IgemmLaunch L;
+        std::string e = build_conv(ctx, L, t, T.wdg + T.wdg_off[u.conv], u.dz, N, u.Ho, u.Wo, out, ep);
+        if (!e.empty()) return c.name + " dgrad: " + e;
+        add_b(stage, [L](cudaStream_t st) { return igemm_launch(L, st); });
+        return "";
+    };
+
+    // ---- decoder, last block first (stage 0)
+    const __nv_bfloat16* d_cur = plan.d_head_in;  // gradient w.r.t. the current block output
+    for (int i = 4; i >= 0; --i) {
+        const NetSpec::Dec& d = S.dec[i];
+        const DecRec& r = decs[i];
+        const Unit u1 = plan.units[r.u1], u2 = plan.units[r.u2];
+        const ConvRef& c1 = S.convs[d.c1];
+        bn_bwd(0, r.u2, d_cur, true, nullptr);
+        if (!(err = wg_conv3(0, r.u2, u1.a, d.cout, u1.Ho, u1.Wo)).empty()) return err;
+        if (!(err = dgrad3(0, r.u2, dA[r.u1], nullptr)).empty()) return err;
+        bn_bwd(0, r.u1, dA[r.u1], true, nullptr);
+        const int cin_total = d.cup + d.cskip;
+        // weight gradient, skip channels: regular 3x3 over the skip tensor
+        if (d.cskip) {
+            WgSpec s;
+            s.z = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, d.cout);
+            s.x = nhwc_view(r.skip, N, u1.Ho, u1.Wo, d.cskip);
+            s.cout = d.cout; s.nsrc_c = d.cskip; s.dci0 = d.cup;
+            s.grad = grads + c1.w; s.s_co = (long long)cin_total * 9; s.s_ci = 9;
+            for (int k = 0; k < 9; ++k) {
+                WgSpec::Tap t;
+                t.dh = k / 3 - 1; t.dw = k % 3 - 1; t.ndst = 1; t.dst[0] = k; t.dst[1] = t.dst[2] = t.dst[3] = 0;
+                s.taps.push_back(t);
+            }
+            if (!(err = add_wg(0, s)).empty()) return err;
+        }
+        // weight gradient, up-sampled channels: per output parity a 2x2 low-res neighbourhood, fanned out to 3x3
+        for (int par = 0; par < 4; ++par) {
+            const int ph = par >> 1, pw = par & 1;
+            WgSpec s;
+            s.z.ptr = u1.dz + ((long long)ph * u1.Wo + pw) * d.cout;
+            s.z.C = d.cout; s.z.W = r.Wl; s.z.H = r.Hl; s.z.N = N;
+            s.z.sW = 2ll * d.cout; s.z.sH = 2ll * u1.Wo * d.cout; s.z.sN = (long long)u1.Ho * u1.Wo * d.cout;
+            s.x = nhwc_view(r.low, N, r.Hl, r.Wl, d.cup);
+            s.cout = d.cout; s.nsrc_c = d.cup; s.dci0 = 0;
+            s.grad = grads + c1.w; s.s_co = (long long)cin_total * 9; s.s_ci = 9;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 2; ++b) {
+                    WgSpec::Tap t;
+                    t.dh = a - 1 + ph; t.dw = b - 1 + pw;
+                    const int r0 = ph == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+                    const int r1 = ph == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+                    const int s0 = pw == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+                    const int s1 = pw == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+                    t.ndst = 0;
+                    t.dst[0] = t.dst[1] = t.dst[2] = t.dst[3] = 0;
+                    for (int rr = r0; rr <= r1; ++rr)
+                        for (int ss = s0; ss <= s1; ++ss) t.dst[t.ndst++] = rr * 3 + ss;
+                    s.taps.push_back(t);
+                }
+            if (!(err = add_wg(0, s)).empty()) return err;
+        }
+        // data gradient: skip part (full-res 3x3) and low-res part (16 taps, traversal stride 2 over dZ)
+        if (d.cskip) {
+            ConvRef t;
+            t.cin = d.cout; t.cout = d.cskip; t.k = 3; t.stride = 1;
+            IgemmLaunch L;
+            EpilogueDesc ep;
+            err = build_conv(ctx, L, t, T.wdg + T.wdg_off[d.c1], u1.dz, N, u1.Ho, u1.Wo, r.d_skip, ep);
+            if (!err.empty()) return c1.name + " dskip: " + err;
+            add_b(0, [L](cudaStream_t st) { return igemm_launch(L, st); });
+        }
+        {
+            // gradient w.r.t. the low-res input -> becomes d_cur of the previous decoder block / layer4 output
+            __nv_bfloat16* d_low = (i > 0) ? dA[decs[i - 1].u2] : dA[blocks.back().u2];
+            SrcDesc s;
+            s.v = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, d.cout);
+            s.es_w = s.es_h = 2;
+            const int chunk = chunk_for(d.cout);
+            std::vector<IgemmTap> taps;
+            for (int t = 0; t < 16; ++t) {
+                const int b = t & 1, pw = (t >> 1) & 1, a = (t >> 2) & 1, ph = (t >> 3) & 1;
+                IgemmTap tp;
+                tp.dh = int16_t(2 - 2 * a - ph);
+                tp.dw = int16_t(2 - 2 * b - pw);
+                tp.c0 = 0; tp.nchunks = int16_t(d.cout / chunk); tp.src = 0;
+                taps.push_back(tp);
+            }
+            View4 o = nhwc_view(d_low, N, r.Hl, r.Wl, d.cup);
+            EpilogueDesc ep;
+            IgemmLaunch L;
+            err = igemm_build(L, &s, 1, taps.data(), 16, chunk, T.wdg + T.wdg_off2[d.c1], 16 * d.cout, d.cup, o, ep,
+                              ctx->d_err, SM);
+            if (!err.empty()) return c1.name + " dlow: " + err;
+            add_b(0, [L](cudaStream_t st) { return igemm_launch(L, st); });
+            d_cur = d_low;
+        }
+    }
+    // ---- encoder blocks, last first.  d_cur = gradient w.r.t. the block output (already complete)
+    for (int bi = (int)blocks.size() - 1; bi >= 0; --bi) {
+        const BlockRec& r = blocks[bi];
+        const int stage = r.layer == 3 ? 1 : (r.layer == 2 ? 2 : 3);
+        const Unit u1 = plan.units[r.u1], u2 = plan.units[r.u2];
+        const ConvRef& c1 = S.convs[u1.conv];
+        // gradient w.r.t. the block input goes to dA of the previous block's u2, or to d_p1 for the first block
+        __nv_bfloat16* d_in = bi > 0 ? dA[blocks[bi - 1].u2] : d_p1;
+        // is the block input an encoder feature that also feeds the decoder (skip)?  -> add that gradient
+        const __nv_bfloat16* d_skip_in = nullptr;
+        if (bi > 0 && blocks[bi - 1].layer != r.layer) {
+            const int lprev = blocks[bi - 1].layer;  // feats[lprev+1] : layer1 -> skips[2], layer2 -> [1], layer3 -> [0]
+            d_skip_in = d_skips[2 - lprev];
+        }
+        bn_bwd(stage, r.u2, dA[r.u2], true, r.g);
+        if (!(err = wg_conv3(stage, r.u2, u1.a, c1.cout, u1.Ho, u1.Wo)).empty()) return err;
+        if (!(err = dgrad3(stage, r.u2, dA[r.u1], nullptr)).empty()) return err;
+        bn_bwd(stage, r.u1, dA[r.u1], true, nullptr);
+        if (!(err = wg_conv3(stage, r.u1, r.x_in, c1.cin, u1.Hin, u1.Win)).empty()) return err;
+        if (r.ud < 0) {
+            // identity shortcut: dX = dgrad(conv1) + g
+            if (!(err = dgrad3(stage, r.u1, d_in, r.g)).empty()) return err;
+        } else {
+            const Unit ud = plan.units[r.ud];
+            bn_bwd(stage, r.ud, r.g, false, nullptr);
+            if (!(err = wg_conv3(stage, r.ud, r.x_in, c1.cin, u1.Hin, u1.Win)).empty()) return err;
+            // stride-2 dgrad by output parity (+ the 1x1 downsample tap on parity 0) (+ decoder skip gradient)
+            long long o = T.wdg_off[u1.conv];
+            for (int par = 0; par < 4; ++par) {
+                TapList tl;
+                int dh[4], dw[4];
+                s2_parity_taps(par, tl, dh, dw);
+                const int ntap = tl.n + (par == 0 ? 1 : 0);
+                const int chunk = chunk_for(c1.cout);
+                SrcDesc s[2];
+                s[0].v = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, c1.cout);
+                s[1].v = nhwc_view(ud.dz, N, u1.Ho, u1.Wo, c1.cout);
+                std::vector<IgemmTap> taps;
+                for (int t = 0; t < tl.n; ++t) {
+                    IgemmTap tp;
+                    tp.dh = int16_t(dh[t]); tp.dw = int16_t(dw[t]); tp.c0 = 0;
+                    tp.nchunks = int16_t(c1.cout / chunk); tp.src = 0;
+                    taps.push_back(tp);
+                }
+                if (par == 0) {
+                    IgemmTap tp;
+                    tp.dh = 0; tp.dw = 0; tp.c0 = 0; tp.nchunks = int16_t(c1.cout / chunk); tp.src = 1;
+                    taps.push_back(tp);
+                }
+                const int ph = par >> 1, pw = par & 1;
+                View4 ov;
+                ov.ptr = d_in + ((long long)ph * u1.Win + pw) * c1.cin;
+                ov.C = c1.cin; ov.W = u1.Wo; ov.H = u1.Ho; ov.N = N;
+                ov.sW = 2ll * c1.cin; ov.sH = 2ll * u1.Win * c1.cin; ov.sN = (long long)u1.Hin * u1.Win * c1.cin;
+                EpilogueDesc ep;
+                if (d_skip_in) {
+                    ep.residual = ov;
+                    ep.residual.ptr = d_skip_in + ((long long)ph * u1.Win + pw) * c1.cin;
+                }
+                IgemmLaunch L;
+                err = igemm_build(L, s, 2, taps.data(), (int)taps.size(), chunk, T.wdg + o, ntap * c1.cout, c1.cin, ov,
+                                  ep, ctx->d_err, SM);
+                if (!err.empty()) return c1.name + " dgrad s2: " + err;
+                add_b(stage, [L](cudaStream_t st) { return igemm_launch(L, st); });
+                o += (long long)c1.cin * ntap * c1.cout;
+            }
+        }
+    }
+    // ---- stem: dF1 = maxpool_bwd(d_p1) + dSkip(f1) ; BN backward ; weight gradient
+    {
+        const Unit us = plan.units[u_stem];
+        const int Hh = H / 2, Wh = W / 2;
+        const __nv_bfloat16* dsk = d_skips[3];
+        __nv_bfloat16* dF1 = dA[u_stem];
+        add_b(3, [=](cudaStream_t st) {
+            maxpool_bwd_kernel<<<ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st>>>(d_p1, f1, dsk, dF1, N, Hh, Wh,
+                                                                                            64);
+            return cudaGetLastError();
+        });
+        bn_bwd(3, u_stem, dF1, true, nullptr);
+        WgSpec s;
+        s.z = nhwc_view(us.dz, N, Hh, Wh, 64);
+        s.x.ptr = plan.xp; s.x.C = 32; s.x.W = W / 2; s.x.H = H; s.x.N = N;
+        s.x.sW = 8; s.x.sH = (long long)(W + 8) * 4; s.x.sN = (long long)H * (W + 8) * 4;
+        s.es_w = 1; s.es_h = 2;
+        s.cout = 64; s.nsrc_c = 32; s.grad = grads + S.convs[S.stem].w; s.s_co = 147; s.s_ci = 0; s.stem_mode = 1;
+        for (int r7 = 0; r7 < 7; ++r7) {
+            WgSpec::Tap t;
+            t.dh = r7 - 3; t.dw = 0; t.ndst = 1; t.dst[0] = r7 * 7; t.dst[1] = t.dst[2] = t.dst[3] = 0;
+            s.taps.push_back(t);
+        }
+        if (!(err = add_wg(3, s)).empty()) return err;
+    }
+    // ---- upload wgrad work items and patch the launches
+    plan.items_used = plan.host_items.size();
+    if (plan.items_used > plan.items_cap) {
+        cudaFree(plan.items);
+        plan.items_cap = plan.items_used;
+        if (cudaMalloc(&plan.items, plan.items_cap * sizeof(WgItem)) != cudaSuccess) return "wgrad item arena alloc";
+    }
+    if (cudaMemcpy(plan.items, plan.host_items.data(), plan.items_used * sizeof(WgItem), cudaMemcpyHostToDevice) !=
+        cudaSuccess)
+        return "wgrad item upload";
+    for (size_t k = 0; k < wgs.size(); ++k) {
+        WgLaunch L = wgs[k];
+        L.p.items = plan.items + reinterpret_cast<size_t>(L.p.items);
+        plan.bwd[wg_pos[k].first][wg_pos[k].second] = [L](cudaStream_t st) { return wg_launch(L, st); };
+    }
+    plan.n_fwd = (int)plan.fwd.size() + 2;
+    plan.n_bwd = 3;
+    for (auto& b : plan.bwd) plan.n_bwd += (int)b.size();
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------ runtime
+inline TrainState* train_state(Ctx* ctx) {
+    if (!ctx->train) {
+        ctx->train = new TrainState();
+        ctx->train_free = [](void* p) { delete static_cast<TrainState*>(p); };
+    }
+    return static_cast<TrainState*>(ctx->train);
+}
+
+// Gradient buckets in backward-completion order: stage 0 = decoder + head, 1 = encoder.layer4,
+// 2 = encoder.layer3, 3 = stem + layer1 + layer2.  Ranges are element offsets into the flat parameter / gradient array.
+inline void grad_bucket_range(const NetSpec& S, int stage, long long* begin, long long* end) {
+    const long long l3 = S.convs[S.enc_blocks[2][0].c1].w, l4 = S.convs[S.enc_blocks[3][0].c1].w;
+    const long long dec = S.convs[S.dec[0].c1].w;
+    switch (stage) {
+        case 0: *begin = dec; *end = S.n_params; break;
+        case 1: *begin = l4; *end = dec; break;
+        case 2: *begin = l3; *end = l4; break;
+        default: *begin = 0; *end = l3; break;
+    }
+}
+
+inline int ctx_train_prepare(Ctx* ctx, int N, const float* params, float* buffers, long long* counters, float* grads,
+                             TrainPlan** out) {
+    TrainState& T = *train_state(ctx);
+    if (N < 1) return ctx_fail(ctx, "train: batch must be >= 1");
+    auto it = T.plans.find(N);
+    if (it != T.plans.end()) {
+        TrainPlan& p = *it->second;
+        if (p.params == params && p.buffers == buffers && p.counters == counters && p.grads == grads) {
+            *out = &p;
+            return 0;
+        }
+        UB_CUDA(cudaDeviceSynchronize());
+        T.plans.erase(it);
+    }
+    if (!T.wdg) {
+        train_layout_dgrad(ctx, T);
+        UB_CUDA(cudaMalloc(&T.wdg, T.wdg_total * 2));
+    }
+    size_t need = 0;
+    {
+        TrainPlan probe;
+        std::string e = build_train_plan(ctx, T, N, probe, true, &need, grads, params, buffers, counters);
+        if (!e.empty()) return ctx_fail(ctx, "train plan (sizing): " + e);
+    }
+    if (need > T.arena_bytes) {
+        UB_CUDA(cudaDeviceSynchronize());
+        T.plans.clear();  // their launch closures point into the old arena
+        cudaFree(T.arena);
+        T.arena = nullptr;
+        T.arena_bytes = 0;
+        UB_CUDA(cudaMalloc(&T.arena, need));
+        UB_CUDA(cudaMemset(T.arena, 0, need));
+        T.arena_bytes = need;
+    }
+    std::unique_ptr<TrainPlan> plan(new TrainPlan());
+    std::string e = build_train_plan(ctx, T, N, *plan, false, nullptr, grads, params, buffers, counters);
+    if (!e.empty()) return ctx_fail(ctx, "train plan: " + e);
+    *out = plan.get();
+    T.plans[N] = std::move(plan);
+    return 0;
+}
+
+// model.train(); logits = model(x)   (/root/reference/train.py:413,436): batch-statistics BatchNorm, running statistics
+// and num_batches_tracked updated in the caller's buffers, activations kept in the library's arena for the backward.
+inline int ctx_train_forward(Ctx* ctx, const float* x, float* logits, const float* params, float* buffers,
+                             long long* counters, float* grads, int N, cudaStream_t st) {
+    if (!ctx->weights_ready) return ctx_fail(ctx, "train_forward: weights not loaded");
+    TrainPlan* P = nullptr;
+    if (ctx_train_prepare(ctx, N, params, buffers, counters, grads, &P)) return 1;
+    const int H = ctx->H, W = ctx->W;
+    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P->xp, N, H, W);
+    UB_CUDA(cudaGetLastError());
+    for (auto& f : P->fwd) UB_CUDA(f(st));
+    dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
+    head_conv_kernel<<<grid, 256, 0, st>>>(P->head_in, ctx->head_w, ctx->head_w + 144, logits, nullptr, nullptr, 0.f, N, H,
+                                           W);
+    UB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// loss.backward() through the network (/root/reference/train.py:443,448) for the stages [stage_first, stage_last].
+// Stage 0 also clears the gradient buffer, re-packs the dgrad operands and runs the seg-head backward.
+inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_first, int stage_last, cudaStream_t st) {
+    TrainState& T = *train_state(ctx);
+    auto it = T.plans.find(N);
+    if (it == T.plans.end()) return ctx_fail(ctx, "train_backward: no forward was run for this batch size");
+    TrainPlan& P = *it->second;
+    const NetSpec& S = ctx->spec;
+    const int H = ctx->H, W = ctx->W, SM = ctx->num_sms;
+    if (stage_first < 0 || stage_last > 3 || stage_first > stage_last) return ctx_fail(ctx, "train_backward: bad stage range");
+    for (int stage = stage_first; stage <= stage_last; ++stage) {
+        if (stage == 0) {
+            if (!dlogits) return ctx_fail(ctx, "train_backward: dlogits is null");
+            UB_CUDA(cudaMemsetAsync(P.grads, 0, (size_t)S.n_params * sizeof(float), st));
+            if (train_pack_dgrad(ctx, T, P.params, st)) return 1;
+            const ConvRef& hc = S.convs[S.head];
+            const long long npx = (long long)N * H * W;
+            head_bwd_data_kernel<<<ew_grid(npx, 256, SM), 256, 0, st>>>(dlogits, ctx->head_w, P.d_head_in, N, H, W);
+            const int nb = 2 * SM;
+            head_bwd_weight_kernel<<<nb, 256, 0, st>>>(P.head_in, dlogits, P.red_part, N, H, W);
+            sum_rows_kernel<<<2, 128, 0, st>>>(P.red_part, nb, 145, P.grads + hc.w);
+            UB_CUDA(cudaGetLastError());
+        }
+        for (auto& f : P.bwd[stage]) UB_CUDA(f(st));
+    }
+    return 0;
+}
+
+}  // namespace ub

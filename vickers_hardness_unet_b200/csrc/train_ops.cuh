@@ -1,0 +1,504 @@
+// Bandwidth-bound kernels of the training step: BatchNorm (batch statistics) forward/backward, max-pool backward,
+// seg-head backward, fused BCE+Dice loss, fused AdamW, dgrad weight packs.  NHWC bf16 activations, fp32 statistics.
+#pragma once
+#include "ptx.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 o;
+    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------ BN forward (train)
+// Second stage of the batch statistics: the conv epilogues left per-CTA partial (sum, sumsq) rows; up to 4 segments
+// (the 4 parity launches of a decoder conv1).  Produces scale/shift for the apply pass, saves mean/invstd for the
+// backward and updates the running statistics like nn.BatchNorm2d (momentum 0.1, unbiased running variance,
+// num_batches_tracked += 1)  [torch semantics used at /root/reference/train.py:413,436].
+struct StatSegs {
+    const float* ptr[4];
+    int rows[4];
+    int n;
+};
+__global__ void bn_finalize_kernel(StatSegs segs, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, long long* __restrict__ counter, float momentum,
+                                   float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && counter) *counter += 1;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int s = 0; s < segs.n; ++s)
+        for (int r = 0; r < segs.rows[s]; ++r) {
+            s1 += segs.ptr[s][((size_t)r * C + c) * 2];
+            s2 += segs.ptr[s][((size_t)r * C + c) * 2 + 1];
+        }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = invstd;
+    if (running_mean) {
+        const double unbiased = count > 1 ? var * count / (count - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// a = [relu]( z*scale + shift [+ residual] ), 8 channels per thread
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
+                                __nv_bfloat16* __restrict__ out, long long npix, int C) {
+    const int C8 = C / 8;
+    const long long total = npix * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = int(i % C8) * 8;
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), v);
+        float r[8];
+        if (residual) unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float y = v[k] * __ldg(scale + c0 + k) + __ldg(shift + c0 + k);
+            if (residual) y += r[k];
+            if (relu) y = fmaxf(y, 0.f);
+            v[k] = y;
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward
+// g = dA * [a > 0] ; partial sums per block of (sum g, sum g*zhat), zhat = (z - mean) * invstd.
+// blockDim = 256; thread t owns channel group t % C8 for the pixels t / C8 + k * (256 / C8).
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
+                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, float* __restrict__ partial, long long npix, int C) {
+    __shared__ float red[256 * 16];
+    const int C8 = C / 8;
+    const int cg = threadIdx.x % C8;
+    const int lane_p = threadIdx.x / C8;
+    const int ppb = 256 / C8;  // pixels per block iteration
+    float s1[8], s2[8], mu[8], is[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s1[k] = s2[k] = 0.f;
+        mu[k] = mean[cg * 8 + k];
+        is[k] = invstd[cg * 8 + k];
+    }
+    if (lane_p < ppb) {
+        for (long long p = (long long)blockIdx.x * ppb + lane_p; p < npix; p += (long long)gridDim.x * ppb) {
+            const long long idx = p * C8 + cg;
+            float g[8], zz[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dA) + idx), g);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(z) + idx), zz);
+            if (a_mask) {
+                float m[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(a_mask) + idx), m);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s1[k] += g[k];
+                s2[k] += g[k] * (zz[k] - mu[k]) * is[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        red[threadIdx.x * 16 + k] = s1[k];
+        red[threadIdx.x * 16 + 8 + k] = s2[k];
+    }
+    __syncthreads();
+    // thread t < C*2 sums its (channel, which) over the ppb pixel lanes
+    for (int j = threadIdx.x; j < C * 2; j += 256) {
+        const int c = j >> 1, which = j & 1;
+        const int g8 = c / 8, k = c % 8;
+        float acc = 0.f;
+        for (int l = 0; l < ppb; ++l) acc += red[(l * C8 + g8) * 16 + which * 8 + k];
+        partial[((size_t)blockIdx.x * C + c) * 2 + which] = acc;
+    }
+}
+
+// sums the per-block partials; writes dgamma / dbeta and the apply coefficients k1 = gamma*invstd, k2 = s1/n, k3 = s2/n
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0, s2 = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        s1 += partial[((size_t)b * C + c) * 2];
+        s2 += partial[((size_t)b * C + c) * 2 + 1];
+    }
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+    coef[c * 3 + 0] = gamma[c] * invstd[c];
+    coef[c * 3 + 1] = (float)(s1 / count);
+    coef[c * 3 + 2] = (float)(s2 / count);
+}
+
+// dz = k1 * (g - k2 - zhat*k3);  optionally also writes g (the masked gradient, for the residual identity path)
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
+                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ coef,
+                                    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long npix,
+                                    int C) {
+    const int C8 = C / 8;
+    const long long total = npix * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = int(i % C8) * 8;
+        float g[8], zz[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dA) + i), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
+        if (a_mask) {
+            float m[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(a_mask) + i), m);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            const float zh = (zz[k] - __ldg(mean + c)) * __ldg(invstd + c);
+            o[k] = __ldg(coef + c * 3) * (g[k] - __ldg(coef + c * 3 + 1) - zh * __ldg(coef + c * 3 + 2));
+        }
+        reinterpret_cast<uint4*>(dz)[i] = pack8(o);
+        if (g_out) reinterpret_cast<uint4*>(g_out)[i] = pack8(g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool backward
+// dF[n,h,w,c] = sum over the (<=4) 3x3/s2 windows containing (h,w) whose FIRST maximum (scan order r, s — the
+// element PyTorch's max_pool2d backward picks) is this element, of dP[window]  (+ dSkip, the decoder's gradient
+// into the same feature map).
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const __nv_bfloat16* __restrict__ F,
+                                   const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
+                                   int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    const long long total = (long long)N * H * W * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = int(i % C8);
+        long long t = i / C8;
+        const int w = int(t % W);
+        t /= W;
+        const int h = int(t % H);
+        const int n = int(t / H);
+        float me[8], acc[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(F) + i), me);
+        if (dSkip) unpack8(__ldg(reinterpret_cast<const uint4*>(dSkip) + i), acc);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        }
+        // windows (ho,wo) with 2*ho-1 <= h <= 2*ho+1
+        for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {
+            if (ho < 0 || ho >= Ho) continue;
+            for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
+                if (wo < 0 || wo >= Wo) continue;
+                float d[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(dP + (((long long)n * Ho + ho) * Wo + wo) * C) + c8), d);
+                // is (h,w) the first maximum of this window?
+                bool first[8];
+                float best[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    best[k] = -INFINITY;
+                    first[k] = false;
+                }
+                for (int r = 0; r < 3; ++r) {
+                    const int hh = 2 * ho - 1 + r;
+                    if (hh < 0 || hh >= H) continue;
+                    for (int s = 0; s < 3; ++s) {
+                        const int ww = 2 * wo - 1 + s;
+                        if (ww < 0 || ww >= W) continue;
+                        float v[8];
+                        unpack8(__ldg(reinterpret_cast<const uint4*>(F + (((long long)n * H + hh) * W + ww) * C) + c8),
+                                v);
+                        const bool is_me = (hh == h && ww == w);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (v[k] > best[k]) {
+                                best[k] = v[k];
+                                first[k] = is_me;
+                            }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (first[k]) acc[k] += d[k];
+            }
+        }
+        (void)me;
+        reinterpret_cast<uint4*>(dF)[i] = pack8(acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ seg head backward
+// dA[n,h,w,c] = sum_{r,s} dL[n, h+1-r, w+1-s] * w[c][r][s]   (bf16 out, 16 channels per pixel)
+__global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
+                                     __nv_bfloat16* __restrict__ dA, int N, int H, int W) {
+    __shared__ float sw[144];
+    if (threadIdx.x < 144) sw[threadIdx.x] = w[threadIdx.x];  // [c][r][s]
+    __syncthreads();
+    const long long total = (long long)N * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = int(i % W);
+        const int y = int((i / W) % H);
+        const long long nb = (i / ((long long)W * H)) * H * W;
+        float d[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int yy = y + 1 - r, xx = x + 1 - s;
+                d[r * 3 + s] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dL + nb + (long long)yy * W + xx) : 0.f;
+            }
+        float o[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) a += d[k] * sw[c * 9 + k];
+            o[c] = a;
+        }
+        float lo[8], hi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            lo[k] = o[k];
+            hi[k] = o[8 + k];
+        }
+        reinterpret_cast<uint4*>(dA)[i * 2] = pack8(lo);
+        reinterpret_cast<uint4*>(dA)[i * 2 + 1] = pack8(hi);
+    }
+}
+
+// per-block partials of dW[c][r][s] = sum a[n,h+r-1,w+s-1,c] * dL[n,h,w] and dbias = sum dL   -> partial[block][145]
+__global__ void __launch_bounds__(256)
+head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ dL, float* __restrict__ partial,
+                       int N, int H, int W) {
+    float acc[145];
+#pragma unroll
+    for (int k = 0; k < 145; ++k) acc[k] = 0.f;
+    const long long total = (long long)N * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = int(i % W);
+        const int y = int((i / W) % H);
+        const long long nb = (i / ((long long)W * H)) * H * W;
+        const float d = __ldg(dL + i);
+        acc[144] += d;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int yy = y + r - 1, xx = x + s - 1;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                const uint4* ap = reinterpret_cast<const uint4*>(A + (nb + (long long)yy * W + xx) * 16);
+                float v[8];
+                unpack8(__ldg(ap), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k * 9 + r * 3 + s] += v[k] * d;
+                unpack8(__ldg(ap + 1), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[(8 + k) * 9 + r * 3 + s] += v[k] * d;
+            }
+    }
+    __shared__ float red[8][145];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 145; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 145; k += 256) {
+        float s = 0.f;
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][k];
+        partial[(size_t)blockIdx.x * 145 + k] = s;
+    }
+}
+// out[j] (+)= sum_b partial[b][j]
+__global__ void sum_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= width) return;
+    double s = 0;
+    for (int b = 0; b < nrows; ++b) s += partial[(size_t)b * width + j];
+    out[j] = (float)s;
+}
+
+// ------------------------------------------------------------------------------------------------ BCE + Dice loss
+// nn.BCEWithLogitsLoss() (mean) + smp DiceLoss(mode="binary") over the whole batch (/root/reference/train.py:438,600-601)
+// pass 1: per-block partials of [sum bce_i, sum p*t, sum p, sum t]
+__global__ void __launch_bounds__(256)
+loss_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ partial,
+                    long long n) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float xv = __ldg(x + i), t = __ldg(y + i);
+        const float e = __expf(-fabsf(xv));
+        const float l1p = log1pf(e);
+        s[0] += fmaxf(xv, 0.f) - xv * t + l1p;      // BCE with logits, stable form
+        const float p = __expf(fminf(xv, 0.f) - l1p);  // exp(logsigmoid(x))
+        s[1] += p * t;
+        s[2] += p;
+        s[3] += t;
+    }
+    __shared__ float red[8][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float v = warp_sum(s[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
+        partial[blockIdx.x * 4 + threadIdx.x] = v;
+    }
+}
+// result[0..2] = bce, dice, bce+dice ; result[3..5] = I, P, T (saved for backward); single thread
+__global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n, float eps,
+                                     float* __restrict__ result) {
+    if (threadIdx.x || blockIdx.x) return;
+    double s[4] = {0, 0, 0, 0};
+    for (int b = 0; b < nblocks; ++b)
+        for (int k = 0; k < 4; ++k) s[k] += partial[b * 4 + k];
+    const double card = s[2] + s[3];
+    double dice = 1.0 - 2.0 * s[1] / (card > eps ? card : (double)eps);
+    if (!(s[3] > 0)) dice = 0.0;
+    result[0] = (float)(s[0] / n);
+    result[1] = (float)dice;
+    result[2] = (float)(s[0] / n + dice);
+    result[3] = (float)s[1];
+    result[4] = (float)s[2];
+    result[5] = (float)s[3];
+}
+// dx_i = g_bce * (sigma_i - y_i)/n  +  g_dice * ( -(2 t_i C - 2 I) / C^2 ) * sigma_i (1 - sigma_i)   (0 if T == 0)
+// g points to device scalars (upstream gradients), so no host sync is needed.
+__global__ void loss_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                const float* __restrict__ result, const float* __restrict__ g_bce,
+                                const float* __restrict__ g_dice, float gscale, float eps, float* __restrict__ dx,
+                                long long n) {
+    const float I = result[3], P = result[4], T = result[5];
+    const float gb = (g_bce ? *g_bce : 0.f) * gscale / (float)n;
+    float gd = (g_dice ? *g_dice : 0.f) * gscale;
+    const float Cc = P + T;
+    const bool clamped = !(Cc > eps);
+    if (!(T > 0.f)) gd = 0.f;
+    const float invC = clamped ? 1.f / eps : 1.f / Cc;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float xv = __ldg(x + i), t = __ldg(y + i);
+        const float sg = 1.f / (1.f + __expf(-xv));
+        // d(2I/C)/dp = 2t/C - 2I/C^2 (C not clamped) or 2t/eps (clamped)
+        const float dscore = clamped ? 2.f * t * invC : (2.f * t * invC - 2.f * I * invC * invC);
+        dx[i] = gb * (sg - t) - gd * dscore * sg * (1.f - sg);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused AdamW
+// torch.optim.AdamW semantics (/root/reference/train.py:606): decoupled decay on every tensor, bias-corrected moments.
+// Optionally scales the gradient (1/world_size, 1/loss_scale) and zeroes it afterwards.
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                             float gscale, int zero_grad) {
+    const long long n4 = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4 + (n & 3);
+         i += (long long)gridDim.x * blockDim.x) {
+        if (i < n4) {
+            float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+            float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+            float* P4 = &pp.x; float* G4 = &gg.x; float* M4 = &mm.x; float* V4 = &vv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gr = G4[k] * gscale;
+                P4[k] *= (1.f - lr * wd);
+                M4[k] = b1 * M4[k] + (1.f - b1) * gr;
+                V4[k] = b2 * V4[k] + (1.f - b2) * gr * gr;
+                const float denom = sqrtf(V4[k]) / bc2_sqrt + eps;
+                P4[k] -= (lr / bc1) * (M4[k] / denom);
+            }
+            reinterpret_cast<float4*>(p)[i] = pp;
+            reinterpret_cast<float4*>(m)[i] = mm;
+            reinterpret_cast<float4*>(v)[i] = vv;
+            if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const long long j = n4 * 4 + (i - n4);
+            const float gr = g[j] * gscale;
+            float pv = p[j] * (1.f - lr * wd);
+            const float mv = b1 * m[j] + (1.f - b1) * gr;
+            const float vv2 = b2 * v[j] + (1.f - b2) * gr * gr;
+            pv -= (lr / bc1) * (mv / (sqrtf(vv2) / bc2_sqrt + eps));
+            p[j] = pv; m[j] = mv; v[j] = vv2;
+            if (zero_grad) g[j] = 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ dgrad weight packs
+// Generic tap-list pack of a K-major dgrad operand:  out[ci][col0 + t*cout + co] = w[co][ci0+ci][r_t][s_t]
+// (w: OIHW fp32 [cout][cin_total][R][S]); `ld` = row length of out.
+struct TapList {
+    int n;
+    int r[16], s[16];
+};
+__global__ void pack_dgrad_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
+                                    int cin_total, int ci0, int cin, int R, int S, int ld, int col0, TapList taps) {
+    const long long total = (long long)cin * taps.n * cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = int(i % cout);
+        const int t = int((i / cout) % taps.n);
+        const int ci = int(i / ((long long)cout * taps.n));
+        out[(long long)ci * ld + col0 + t * cout + co] =
+            __float2bfloat16(w[(((long long)co * cin_total + ci0 + ci) * R + taps.r[t]) * S + taps.s[t]]);
+    }
+}
+// decoder conv1 dLow operand: 16 taps (ph,a,pw,b) -> out[c][t*cout + co] = sum_{r in R(ph,a), s in S(pw,b)} w[co][c][r][s]
+// tap index t = ((ph*2 + a)*2 + pw)*2 + b
+__global__ void pack_dec1_dlow_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cup,
+                                        int cin_total) {
+    const long long total = (long long)cup * 16 * cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = int(i % cout);
+        const int t = int((i / cout) % 16);
+        const int c = int(i / ((long long)cout * 16));
+        const int b = t & 1, pw = (t >> 1) & 1, a = (t >> 2) & 1, ph = (t >> 3) & 1;
+        const int r0 = ph == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+        const int r1 = ph == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int s0 = pw == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+        const int s1 = pw == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        float v = 0.f;
+        for (int r = r0; r <= r1; ++r)
+            for (int s = s0; s <= s1; ++s) v += w[((long long)co * cin_total + c) * 9 + r * 3 + s];
+        out[i] = __float2bfloat16(v);
+    }
+}
+
+}  // namespace ub

@@ -183,8 +183,12 @@ struct Ctx {
     uint8_t* io_m = nullptr;
     cudaStream_t io_stream = nullptr;
     cudaEvent_t weights_event = nullptr;  // recorded after every weight re-pack (cross-stream ordering for io_stream)
+    // training state (train.cuh), type-erased so that inference-only translation units need not see it
+    void* train = nullptr;
+    void (*train_free)(void*) = nullptr;
 
     ~Ctx() {
+        if (train && train_free) train_free(train);
         if (weights_event) cudaEventDestroy(weights_event);
         cudaFree(io_x);
         cudaFree(io_f);

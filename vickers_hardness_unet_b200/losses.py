@@ -18,3 +18,16 @@ class DiceLoss(nn.Module):
     def forward(self, y_pred, y_true):
         from .train import dice_loss
         return dice_loss(y_pred, y_true, self.eps)
+
+
+class BCEDiceLoss(nn.Module):
+    """`nn.BCEWithLogitsLoss()(x, y) + DiceLoss("binary")(x, y)` (/root/reference/train.py:438) as ONE fused pass."""
+
+    def __init__(self, eps: float = 1e-7):
+        super().__init__()
+        self.eps = float(eps)
+
+    def forward(self, y_pred, y_true):
+        from .train import bce_dice
+        bce, dice = bce_dice(y_pred, y_true, self.eps)
+        return bce + dice

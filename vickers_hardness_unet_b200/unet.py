@@ -87,6 +87,10 @@ class Unet(nn.Module):
             self._entries.append((mod, parts[-1], kind, off, shape, numel))
         self._ctx = None
         self._packed_version = None
+        self._params_epoch = 0   # bumped when the library itself writes parameters (FusedAdamW)
+        self._buffers_epoch = 0  # bumped when the library updates the BatchNorm running statistics (train forward)
+        self._grad_views = None
+        self._dp = None          # distributed.GradBucketReducer when data parallelism is enabled
         self.name = "u-resnet34"
 
     # ------------------------------------------------------------------ flat storage upkeep
@@ -119,6 +123,9 @@ class Unet(nn.Module):
                     mod._buffers[attr] = view
         self._flat = flat
         self._packed_version = None
+        self._grad_views = None
+        for p in self.parameters():
+            p.grad = None
         if self._ctx is not None and self._ctx.device != (dev.index if dev.type == "cuda" else -1):
             self._ctx = None
 
@@ -129,6 +136,23 @@ class Unet(nn.Module):
     @property
     def flat_buffers(self) -> torch.Tensor:
         return self._flat["b"]
+
+    @property
+    def flat_grads(self) -> torch.Tensor:
+        return self._grad_buffer()
+
+    def _grad_buffer(self) -> torch.Tensor:
+        """Flat fp32 gradient array (same layout as flat_params); `.grad` of every parameter is a view of it."""
+        g = self._flat.get("g")
+        p = self._flat["p"]
+        if g is None or g.device != p.device:
+            g = torch.zeros_like(p)
+            self._flat["g"] = g
+            self._grad_views = None
+        if self._grad_views is None:
+            self._grad_views = [g[off:off + numel].view(shape) for (_, _, kind, off, shape, numel) in self._entries
+                                if kind == 0]
+        return g
 
     # ------------------------------------------------------------------ native context
     def _context(self, x: torch.Tensor) -> "_lib.Context":
@@ -154,7 +178,8 @@ class Unet(nn.Module):
         return c
 
     def _sync_weights(self, ctx, stream):
-        ver = (self._flat["p"]._version, self._flat["b"]._version, id(ctx))
+        ver = (self._flat["p"]._version, self._flat["b"]._version, id(ctx), self._params_epoch,
+               self._buffers_epoch if not self.training else -1)
         if ver != self._packed_version:
             ctx.check(ctx.lib.unetb200_load_weights(ctx.handle, self._flat["p"].data_ptr(), self._flat["b"].data_ptr(),
                                                     stream), "load_weights")
@@ -166,7 +191,8 @@ class Unet(nn.Module):
         x = x.detach().to(torch.float32).contiguous()
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._sync_weights(ctx, stream)
-        if self.training and torch.is_grad_enabled():
+        if self.training:
+            # batch-statistics BatchNorm + running-stat update, activations kept for loss.backward()
             from .train import unet_train_forward
             return unet_train_forward(self, ctx, x, stream)
         N, _, H, W = x.shape

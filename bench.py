@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--profile-out", default="", help="write the per-launch timing table here (rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per train step (BASELINE configs[2])")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement")
     return ap.parse_args()
 
 
@@ -111,6 +113,100 @@ def cpu_oracle_rate(size: int, batch: int, budget_s: float, threads: int):
             ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     return batch / med, n, med
+
+
+def bench_train(a, dev, rank, world, barrier):
+    """Train step of BASELINE configs[2]: batch 16/GPU @512x512, BCE+Dice, fused AdamW, bucketed NCCL all-reduce of the
+    gradients overlapped with the backward when world > 1.  Returns the `train` sub-object of the JSON line."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+    import vickers_hardness_unet_b200 as vb
+
+    B, S = a.train_batch, a.size
+    torch.manual_seed(42)
+    model = vb.Unet("resnet34", encoder_weights=None, in_channels=3, classes=1, activation=None).to(dev).train()
+    if world > 1:
+        vb.distributed.enable_data_parallel(model)
+    opt = vb.FusedAdamW(model, lr=5e-5, weight_decay=1e-4)  # /root/reference/train.py:606, RECOMMENDED_CFG lr
+    crit = vb.losses.BCEDiceLoss()
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    xs = [torch.randn(B, 3, S, S, device=dev, generator=g) for _ in range(2)]
+    ys = [(torch.rand(B, 1, S, S, device=dev, generator=g) < 0.05).float() for _ in range(2)]
+    last = {}
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        last["loss"] = loss
+    steps, warm = max(3, a.steps // 2), max(3, min(a.warmup, 5))
+    for i in range(warm):
+        step(xs[i & 1], ys[i & 1])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(xs[i & 1], ys[i & 1])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # phase split of one step (CUDA events on the launch stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    opt.zero_grad(set_to_none=True)
+    logits = model(xs[0])
+    ev[1].record()
+    loss = crit(logits, ys[0])
+    ev[2].record()
+    loss.backward()
+    ev[3].record()
+    opt.step()
+    ev[4].record()
+    torch.cuda.synchronize(dev)
+    phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["forward_ms", "loss_ms", "backward_ms", "adamw_ms"])}
+    # end to end: pinned host batch -> H2D -> step -> loss.item() (the D2H sync of train.py:452)
+    xh = [x.cpu().pin_memory() for x in xs]
+    yh = [y.cpu().pin_memory() for y in ys]
+    xd, yd = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+
+    def e2e_step(i):
+        xd.copy_(xh[i & 1], non_blocking=True)
+        yd.copy_(yh[i & 1], non_blocking=True)
+        step(xd, yd)
+        return last["loss"].item()
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        lv = e2e_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    ctx = model._ctx
+    nf, nb = ctypes.c_int(), ctypes.c_int()
+    ctx.lib.unetb200_train_launch_count(ctx.handle, B, ctypes.byref(nf), ctypes.byref(nb))
+    pk, pk_kind = peaks()
+    gflop = 186.3 * (S * S) / (512 * 512)  # algorithmic train-step GFLOP / image (SURVEY.md section 8d)
+    val = world * B * steps / (ms * 1e-3)
+    tf = gflop * B * steps / (ms * 1e-3) / 1e3
+    return {"metric": "images_per_sec_train_512", "value": val, "unit": "images/s", "ms_per_step": ms / steps,
+            "steps": steps, "batch_per_gpu": B, "loss": lv,
+            "workload": f"Unet(resnet34) {S}x{S} train step BCE+Dice + fused AdamW, batch {B}/GPU (BASELINE configs[2])",
+            "parallelism": f"dp{world}: bucketed NCCL all-reduce (4 buckets) overlapped with backward" if world > 1
+            else "single GPU, no collective",
+            "e2e": {"value": world * B * steps / e2e_s, "unit": "images/s",
+                    "h2d_bytes_per_step": B * 4 * S * S * 4, "d2h_bytes_per_step": 4},
+            "phases": phases, "gpu_launches_per_step": nf.value + nb.value + 4,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / pk["bf16_tflops_sustained"], "peak_kind": pk_kind,
+                         "kernel": "whole train step (fwd + dgrad + wgrad algorithmic FLOPs)"}}
 
 
 def run_reference(a, rank):
@@ -241,6 +337,11 @@ def main():
         cpu = {"value": rate, "unit": "images/s", "cores": thr, "kind": "port",
                "sample": f"fp32 oracle forward, batch 1 @ {S}x{S}, median of {n} runs ({med * 1e3:.0f} ms each), "
                          f"{thr} torch threads on {os.cpu_count()} host cores"}
+    train = None
+    if not a.no_train:
+        del xs, xh
+        torch.cuda.empty_cache()
+        train = bench_train(a, dev, rank, world, barrier)
     if rank == 0:
         gflop = GFLOP_FWD_512 * (S * S) / (512 * 512)
         whole_tf = gflop * B * a.steps / (ms * 1e-3) / 1e3  # whole step, per GPU
@@ -271,6 +372,9 @@ def main():
         }
         if cpu:
             out["cpu_baseline"] = cpu
+        if train:
+            out["train"] = train
+            out["gpu_launches"] += train["gpu_launches_per_step"] * train["steps"]
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per train step (BASELINE configs[2])")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement")
+    ap.add_argument("--train-profile-out", default="", help="write the per-launch timing table of one train step here")
     return ap.parse_args()
 
 
@@ -167,6 +168,12 @@ def bench_train(a, dev, rank, world, barrier):
     ev[4].record()
     torch.cuda.synchronize(dev)
     phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["forward_ms", "loss_ms", "backward_ms", "adamw_ms"])}
+    if a.train_profile_out and rank == 0:
+        ctx = model._ctx
+        ctx.lib.unetb200_profile_enable(ctx.handle, 1)
+        step(xs[1], ys[1])
+        ctx.check(ctx.lib.unetb200_profile_dump(ctx.handle, a.train_profile_out.encode()), "profile_dump")
+        ctx.lib.unetb200_profile_enable(ctx.handle, 0)
     # end to end: pinned host batch -> H2D -> step -> loss.item() (the D2H sync of train.py:452)
     xh = [x.cpu().pin_memory() for x in xs]
     yh = [y.cpu().pin_memory() for y in ys]

@@ -106,6 +106,11 @@ int unetb200_train_debug_info(unetb200_ctx* ctx, int N, int index, char* name_ou
                               int* is_bf16_out);
 int unetb200_train_debug_copy(unetb200_ctx* ctx, int N, int index, void* dst_dev, long long cap_bytes, void* stream);
 
+/* Per-launch timing of train_forward / train_backward: while enabled a CUDA event is recorded on the launch stream
+ * before every kernel launch; profile_dump synchronises and writes "launch,kind,layer,ms" rows (CSV) to `path`. */
+int unetb200_profile_enable(unetb200_ctx* ctx, int on);
+int unetb200_profile_dump(unetb200_ctx* ctx, const char* path);
+
 /* nn.BCEWithLogitsLoss()(logits, y) + smp.losses.DiceLoss("binary")(logits, y)  (train.py:438,600-601), one pass:
  * result_dev[0..2] = bce, dice, bce + dice; result_dev[3..5] = sum(p*y), sum(p), sum(y) (kept for the backward);
  * result_dev must hold 8 floats.  n = N*H*W elements; eps = DiceLoss eps (1e-7).  scratch_dev: caller-owned device

@@ -44,6 +44,8 @@ def _proto(lib):
         "unetb200_train_debug_count": (i32, [vp, i32]),
         "unetb200_train_debug_info": (i32, [vp, i32, i32, C.c_char_p, i32, P(i32), P(i32)]),
         "unetb200_train_debug_copy": (i32, [vp, i32, i32, vp, i64, vp]),
+        "unetb200_profile_enable": (i32, [vp, i32]),
+        "unetb200_profile_dump": (i32, [vp, C.c_char_p]),
         "unetb200_loss_scratch_floats": (i32, []),
         "unetb200_loss_bce_dice_forward": (i32, [vp, vp, i64, f32, vp, vp, vp]),
         "unetb200_loss_bce_dice_backward": (i32, [vp, vp, vp, vp, vp, f32, f32, vp, i64, vp]),

@@ -258,6 +258,31 @@ int unetb200_train_debug_copy(unetb200_ctx* h, int N, int index, void* dst_dev, 
     return 0;
 }
 
+int unetb200_profile_enable(unetb200_ctx* h, int on) {
+    Ctx* ctx = h->c;
+    for (auto& pe : ctx->prof_ev) cudaEventDestroy(pe.second);
+    ctx->prof_ev.clear();
+    ctx->prof_on = on != 0;
+    return 0;
+}
+int unetb200_profile_dump(unetb200_ctx* h, const char* path) {
+    Ctx* ctx = h->c;
+    UB_CUDA(cudaDeviceSynchronize());
+    FILE* f = fopen(path, "w");
+    if (!f) return ctx_fail(ctx, "profile_dump: cannot open file");
+    fprintf(f, "launch,kind,layer,ms\n");
+    for (size_t i = 0; i + 1 < ctx->prof_ev.size(); ++i) {
+        const std::string& nm = ctx->prof_ev[i].first;
+        if (nm.rfind("end:", 0) == 0) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->prof_ev[i].second, ctx->prof_ev[i + 1].second);
+        const size_t c = nm.find(':');
+        fprintf(f, "%zu,%s,%s,%.5f\n", i, nm.substr(0, c).c_str(), nm.substr(c + 1).c_str(), ms);
+    }
+    fclose(f);
+    return 0;
+}
+
 static int loss_fail(const char* msg) {
     g_create_error = msg;
     return 1;

@@ -51,6 +51,7 @@ struct TrainPlan {
     std::vector<Unit> units;
     std::vector<LaunchFn> fwd;          // after input pack, before head
     std::vector<LaunchFn> bwd[4];       // stage 0: decoder, 1: layer4, 2: layer3, 3: layer2 + layer1 + stem
+    std::vector<std::string> fwd_names, bwd_names[4];  // "<kind>:<layer>" per launch (profiling)
     int n_fwd = 0, n_bwd = 0;
     // scratch
     float* stat_part = nullptr;         // conv-epilogue statistic partials [4][num_sms][512][2]
@@ -201,6 +202,7 @@ struct WgSpec {
     float* grad = nullptr;
     long long s_co = 0, s_ci = 0;
     int stem_mode = 0;
+    std::string name;
 };
 
 inline std::string wg_build(Ctx* ctx, TrainPlan& plan, WgLaunch& L, const WgSpec& s) {
@@ -297,7 +299,9 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     plan.units.clear();
     plan.dbg.clear();
     plan.fwd.clear();
+    plan.fwd_names.clear();
     for (auto& b : plan.bwd) b.clear();
+    for (auto& b : plan.bwd_names) b.clear();
     plan.host_items.clear();
     std::string err;
 
@@ -318,7 +322,10 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         plan.units.push_back(u);
         return (int)plan.units.size() - 1;
     };
-    auto add_f = [&](LaunchFn f) { plan.fwd.push_back(std::move(f)); };
+    auto add_f = [&](const std::string& nm, LaunchFn f) {
+        plan.fwd.push_back(std::move(f));
+        plan.fwd_names.push_back(nm);
+    };
     // BN finalize + apply after a conv whose statistics partial rows are described by segs
     auto add_bn_fwd = [&](int ui, StatSegs segs, const __nv_bfloat16* residual, int relu) {
         const Unit u = plan.units[ui];
@@ -332,12 +339,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const float* gm = params + b.gamma;
         const float* bt = params + b.beta;
         const int C = c.cout;
-        add_f([=](cudaStream_t st) {
+        add_f("bn_finalize:" + c.name, [=](cudaStream_t st) {
             bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(segs, C, count, gm, bt, rm, rv, cnt, 0.1f, 1e-5f,
                                                                u.scale, u.shift, u.mean, u.invstd);
             return cudaGetLastError();
         });
-        add_f([=](cudaStream_t st) {
+        add_f("bn_apply:" + c.name, [=](cudaStream_t st) {
             bn_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(u.z, u.scale, u.shift, residual, relu, u.a,
                                                                              npix, C);
             return cudaGetLastError();
@@ -362,7 +369,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                             ? build_stem(ctx, L, ctx->wpk + c.wpk, in, N, H, W, u.z, ep)
                             : build_conv(ctx, L, c, ctx->wpk + c.wpk, in, N, u.Hin, u.Win, u.z, ep);
         if (!e.empty()) return c.name + ": " + e;
-        add_f([L](cudaStream_t st) { return igemm_launch(L, st); });
+        add_f("conv_fwd:" + c.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
         StatSegs segs;
         memset(&segs, 0, sizeof(segs));
         segs.n = 1; segs.ptr[0] = plan.stat_part; segs.rows[0] = L.grid;
@@ -378,7 +385,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     __nv_bfloat16* d_p1 = A.take((long long)N * h * w * 64);
     if (!dry) {
         const int Hh = H / 2, Wh = W / 2;
-        add_f([=](cudaStream_t st) {
+        add_f("maxpool:encoder.maxpool", [=](cudaStream_t st) {
             maxpool3x3s2_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, SM), 256, 0, st>>>(f1, p1, N, Hh,
                                                                                                         Wh, 64);
             return cudaGetLastError();
@@ -433,7 +440,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                 IgemmLaunch L;
                 err = build_dec1(ctx, L, d, ctx->wpk + S.convs[d.c1].wpk, par, cur, skips[i], N, h, w, u1.z, ep);
                 if (!err.empty()) return S.convs[d.c1].name + ": " + err;
-                add_f([L](cudaStream_t st) { return igemm_launch(L, st); });
+                add_f("conv_fwd:" + S.convs[d.c1].name + "[parity]", [L](cudaStream_t st) { return igemm_launch(L, st); });
                 segs.ptr[par] = ep.stats;
                 segs.rows[par] = L.grid;
             }
@@ -484,7 +491,10 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     // ---------------------------------------------------------------- backward graph
     std::vector<WgLaunch> wgs;  // collected to patch item pointers after upload
     std::vector<std::pair<int, int>> wg_pos;
-    auto add_b = [&](int stage, LaunchFn f) { plan.bwd[stage].push_back(std::move(f)); };
+    auto add_b = [&](int stage, const std::string& nm, LaunchFn f) {
+        plan.bwd[stage].push_back(std::move(f));
+        plan.bwd_names[stage].push_back(nm);
+    };
     // BN backward of unit ui given dA_in (gradient w.r.t. `a`): dz (+ optional masked gradient g_out)
     auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out) {
         const Unit u = plan.units[ui];
@@ -501,16 +511,16 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const float* gm = params + b.gamma;
         float* dgm = grads + b.gamma;
         float* dbt = grads + b.beta;
-        add_b(stage, [=](cudaStream_t st) {
+        add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
             bn_bwd_reduce_kernel<<<nblocks, 256, 0, st>>>(dA_in, mask, u.z, u.mean, u.invstd, part, npix, C);
             return cudaGetLastError();
         });
-        add_b(stage, [=](cudaStream_t st) {
+        add_b(stage, "bn_bwd_finalize:" + c.name, [=](cudaStream_t st) {
             bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nblocks, C, (double)npix, gm, u.invstd, dgm,
                                                                    dbt, u.coef);
             return cudaGetLastError();
         });
-        add_b(stage, [=](cudaStream_t st) {
+        add_b(stage, "bn_bwd_apply:" + c.name, [=](cudaStream_t st) {
             bn_bwd_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(dA_in, mask, u.z, u.mean, u.invstd,
                                                                                  u.coef, u.dz, g_out, npix, C);
             return cudaGetLastError();
@@ -522,7 +532,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         if (!e.empty()) return e;
         wgs.push_back(L);
         wg_pos.push_back({stage, (int)plan.bwd[stage].size()});
-        add_b(stage, LaunchFn());  // placeholder, filled after the item arena is uploaded
+        add_b(stage, "wgrad:" + s.name, LaunchFn());  // placeholder, filled after the item arena is uploaded
         return "";
     };
     auto wg_conv3 = [&](int stage, int ui, const void* x_in, int x_C, int x_H, int x_W) -> std::string {
@@ -530,6 +540,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
         WgSpec s;
+        s.name = c.name;
         s.z = nhwc_view(u.dz, N, u.Ho, u.Wo, c.cout);
         s.x = nhwc_view(x_in, N, x_H, x_W, x_C);
         s.es_w = s.es_h = c.stride;
@@ -556,7 +567,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         IgemmLaunch L;
         std::string e = build_conv(ctx, L, t, T.wdg + T.wdg_off[u.conv], u.dz, N, u.Ho, u.Wo, out, ep);
         if (!e.empty()) return c.name + " dgrad: " + e;
-        add_b(stage, [L](cudaStream_t st) { return igemm_launch(L, st); });
+        add_b(stage, "dgrad:" + c.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
         return "";
     };
 
@@ -575,6 +586,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         // weight gradient, skip channels: regular 3x3 over the skip tensor
         if (d.cskip) {
             WgSpec s;
+            s.name = c1.name + "[skip]";
             s.z = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, d.cout);
             s.x = nhwc_view(r.skip, N, u1.Ho, u1.Wo, d.cskip);
             s.cout = d.cout; s.nsrc_c = d.cskip; s.dci0 = d.cup;
@@ -590,6 +602,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         for (int par = 0; par < 4; ++par) {
             const int ph = par >> 1, pw = par & 1;
             WgSpec s;
+            s.name = c1.name + "[up parity]";
             s.z.ptr = u1.dz + ((long long)ph * u1.Wo + pw) * d.cout;
             s.z.C = d.cout; s.z.W = r.Wl; s.z.H = r.Hl; s.z.N = N;
             s.z.sW = 2ll * d.cout; s.z.sH = 2ll * u1.Wo * d.cout; s.z.sN = (long long)u1.Ho * u1.Wo * d.cout;
@@ -620,7 +633,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             EpilogueDesc ep;
             err = build_conv(ctx, L, t, T.wdg + T.wdg_off[d.c1], u1.dz, N, u1.Ho, u1.Wo, r.d_skip, ep);
             if (!err.empty()) return c1.name + " dskip: " + err;
-            add_b(0, [L](cudaStream_t st) { return igemm_launch(L, st); });
+            add_b(0, "dgrad_skip:" + c1.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
         }
         {
             // gradient w.r.t. the low-res input -> becomes d_cur of the previous decoder block / layer4 output
@@ -644,7 +657,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             err = igemm_build(L, &s, 1, taps.data(), 16, chunk, T.wdg + T.wdg_off2[d.c1], 16 * d.cout, d.cup, o, ep,
                               ctx->d_err, SM);
             if (!err.empty()) return c1.name + " dlow: " + err;
-            add_b(0, [L](cudaStream_t st) { return igemm_launch(L, st); });
+            add_b(0, "dgrad_low:" + c1.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
             d_cur = d_low;
         }
     }
@@ -711,7 +724,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                 err = igemm_build(L, s, 2, taps.data(), (int)taps.size(), chunk, T.wdg + o, ntap * c1.cout, c1.cin, ov,
                                   ep, ctx->d_err, SM);
                 if (!err.empty()) return c1.name + " dgrad s2: " + err;
-                add_b(stage, [L](cudaStream_t st) { return igemm_launch(L, st); });
+                add_b(stage, "dgrad_s2:" + c1.name + "[parity]", [L](cudaStream_t st) { return igemm_launch(L, st); });
                 o += (long long)c1.cin * ntap * c1.cout;
             }
         }
@@ -722,13 +735,14 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const int Hh = H / 2, Wh = W / 2;
         const __nv_bfloat16* dsk = d_skips[3];
         __nv_bfloat16* dF1 = dA[u_stem];
-        add_b(3, [=](cudaStream_t st) {
+        add_b(3, "maxpool_bwd:encoder.maxpool", [=](cudaStream_t st) {
             maxpool_bwd_kernel<<<ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st>>>(d_p1, f1, dsk, dF1, N, Hh, Wh,
                                                                                             64);
             return cudaGetLastError();
         });
         bn_bwd(3, u_stem, dF1, true, nullptr);
         WgSpec s;
+        s.name = "encoder.conv1.weight";
         s.z = nhwc_view(us.dz, N, Hh, Wh, 64);
         s.x.ptr = plan.xp; s.x.C = 32; s.x.W = W / 2; s.x.H = H; s.x.N = N;
         s.x.sW = 8; s.x.sH = (long long)(W + 8) * 4; s.x.sN = (long long)H * (W + 8) * 4;
@@ -834,13 +848,19 @@ inline int ctx_train_forward(Ctx* ctx, const float* x, float* logits, const floa
     TrainPlan* P = nullptr;
     if (ctx_train_prepare(ctx, N, params, buffers, counters, grads, &P)) return 1;
     const int H = ctx->H, W = ctx->W;
+    ctx->prof_mark("pack_input:x", st);
     pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P->xp, N, H, W);
     UB_CUDA(cudaGetLastError());
-    for (auto& f : P->fwd) UB_CUDA(f(st));
+    for (size_t i = 0; i < P->fwd.size(); ++i) {
+        ctx->prof_mark(P->fwd_names[i], st);
+        UB_CUDA(P->fwd[i](st));
+    }
+    ctx->prof_mark("head_fwd:segmentation_head", st);
     dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
     head_conv_kernel<<<grid, 256, 0, st>>>(P->head_in, ctx->head_w, ctx->head_w + 144, logits, nullptr, nullptr, 0.f, N, H,
                                            W);
     UB_CUDA(cudaGetLastError());
+    ctx->prof_mark("end:forward", st);
     return 0;
 }
 
@@ -857,8 +877,11 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
     for (int stage = stage_first; stage <= stage_last; ++stage) {
         if (stage == 0) {
             if (!dlogits) return ctx_fail(ctx, "train_backward: dlogits is null");
+            ctx->prof_mark("memset:grads", st);
             UB_CUDA(cudaMemsetAsync(P.grads, 0, (size_t)S.n_params * sizeof(float), st));
+            ctx->prof_mark("pack_dgrad:all", st);
             if (train_pack_dgrad(ctx, T, P.params, st)) return 1;
+            ctx->prof_mark("head_bwd:segmentation_head", st);
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
             head_bwd_data_kernel<<<ew_grid(npx, 256, SM), 256, 0, st>>>(dlogits, ctx->head_w, P.d_head_in, N, H, W);
@@ -867,7 +890,11 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             sum_rows_kernel<<<2, 128, 0, st>>>(P.red_part, nb, 145, P.grads + hc.w);
             UB_CUDA(cudaGetLastError());
         }
-        for (auto& f : P.bwd[stage]) UB_CUDA(f(st));
+        for (size_t i = 0; i < P.bwd[stage].size(); ++i) {
+            ctx->prof_mark(P.bwd_names[stage][i], st);
+            UB_CUDA(P.bwd[stage][i](st));
+        }
+        if (stage == 3) ctx->prof_mark("end:backward", st);
     }
     return 0;
 }

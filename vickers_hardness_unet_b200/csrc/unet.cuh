@@ -183,6 +183,16 @@ struct Ctx {
     uint8_t* io_m = nullptr;
     cudaStream_t io_stream = nullptr;
     cudaEvent_t weights_event = nullptr;  // recorded after every weight re-pack (cross-stream ordering for io_stream)
+    // optional per-launch profiling of the train step: (name, event recorded BEFORE the launch)
+    bool prof_on = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> prof_ev;
+    void prof_mark(const std::string& name, cudaStream_t st) {
+        if (!prof_on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        prof_ev.emplace_back(name, e);
+    }
     // training state (train.cuh), type-erased so that inference-only translation units need not see it
     void* train = nullptr;
     void (*train_free)(void*) = nullptr;

@@ -62,6 +62,11 @@ def _dec_conv1_parity(x_low, skip, w, cup):
     return torch.stack(rows, -2).reshape(N, cout, 2 * Hl, 2 * Wl)              # interleave the two row parities
 
 
+# decoder blocks whose conv1 runs on the halo-resident kernel (plain bf16 3x3 weights over cat(up(x), skip), csrc/hconv.cuh);
+# the others use the parity-folded 2x2 weights on the low-res tensor (csrc/unet.cuh::build_dec1)
+HCONV_DECODER_BLOCKS = (3, 4)
+
+
 def emulated_forward(o, x, train: bool):
     """Forward of oracle `o` with the CUDA path's bf16 rounding points.
 
@@ -92,7 +97,12 @@ def emulated_forward(o, x, train: bool):
     skips = [feats[3], feats[2], feats[1], feats[0], None]
     cups = [512, 256, 128, 64, 32]
     for i, blk in enumerate(o.decoder.blocks):
-        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i])
+        if i in HCONV_DECODER_BLOCKS:
+            up = t.repeat_interleave(2, 2).repeat_interleave(2, 3)
+            cat = torch.cat([up, skips[i]], 1) if skips[i] is not None else up
+            z = F.conv2d(cat, _r(blk.conv1[0].weight), None, 1, 1)
+        else:
+            z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i])
         u = _r(F.relu(bn(z, blk.conv1[1])))
         t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
     head = o.segmentation_head[0]

@@ -384,6 +384,89 @@ static void case_head(const char* name, int N, int H, int W) {
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_mask);
 }
 
+// hconv: 3x3 s1 conv over cat(nearest2x(low), src) on the halo-resident kernel, vs the CPU conv of the materialised input
+static void case_hconv(const char* name, int N, int H, int W, int cup, int cskip, int cout, bool residual, bool relu,
+                       bool scale_shift, bool stats) {
+    const int ctot = cup + cskip;
+    HostT low(N, H / 2, W / 2, cup ? cup : 1), src(N, H, W, cskip ? cskip : 1), cat(N, H, W, ctot);
+    fill_rand_bf16(low.v, 1.0f);
+    fill_rand_bf16(src.v, 1.0f);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                for (int c = 0; c < cup; ++c) cat.at(n, h, w, c) = low.at(n, h / 2, w / 2, c);
+                for (int c = 0; c < cskip; ++c) cat.at(n, h, w, cup + c) = src.at(n, h, w, c);
+            }
+    std::vector<float> w((size_t)cout * ctot * 9);
+    const float ws = 1.0f / sqrtf((float)ctot * 9);
+    for (auto& x : w) x = bf16r(frand() * ws * 1.7f);
+    std::vector<float> sc(cout, 1.f), sh(cout, 0.f);
+    if (scale_shift)
+        for (int c = 0; c < cout; ++c) { sc[c] = 0.5f + 0.5f * fabsf(frand()); sh[c] = 0.1f * frand(); }
+    HostT res(N, H, W, cout);
+    if (residual) fill_rand_bf16(res.v, 1.0f);
+    HostT ref = cpu_conv(cat, w, cout, 3, 1, 1);
+    for (size_t i = 0; i < ref.v.size(); ++i) {
+        float v = ref.v[i] * sc[i % cout] + sh[i % cout];
+        if (residual) v += res.v[i];
+        if (relu) v = fmaxf(v, 0.f);
+        ref.v[i] = v;
+    }
+    __nv_bfloat16* d_low = to_dev_bf16(low.v);
+    __nv_bfloat16* d_src = to_dev_bf16(src.v);
+    __nv_bfloat16* d_res = to_dev_bf16(res.v);
+    float* d_w = to_dev_f32(w);
+    float* d_sc = to_dev_f32(sc);
+    float* d_sh = to_dev_f32(sh);
+    __nv_bfloat16 *d_wpk, *d_out;
+    CK(cudaMalloc(&d_wpk, w.size() * 2));
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    CK(cudaMemset(d_out, 0xFF, ref.v.size() * 2));
+    pack_hconv_w_kernel<<<64, 256>>>(d_w, d_wpk, cout, ctot, ctot, 0, 0);
+    float* d_stats = nullptr;
+    EpilogueDesc ep;
+    if (scale_shift) { ep.scale = d_sc; ep.shift = d_sh; }
+    ep.relu = relu;
+    if (residual) ep.residual = nhwc_view(d_res, N, H, W, cout);
+    if (stats) {
+        CK(cudaMalloc(&d_stats, (size_t)g_ctx->num_sms * cout * 2 * 4));
+        CK(cudaMemset(d_stats, 0, (size_t)g_ctx->num_sms * cout * 2 * 4));
+        ep.stats = d_stats;
+    }
+    HconvLaunch L;
+    std::string e = hconv_build(L, cup ? d_low : nullptr, cup, cskip ? d_src : nullptr, cskip, d_wpk, cout, N, H, W, d_out,
+                                ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %d smem %u stages %d tiles %dx%dx%d\n", name, L.grid, L.smem, L.p.stages, L.p.tiles_w,
+           L.p.tiles_h, N);
+    CK(hconv_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+        report(name, compare(got, ref.v), 6e-3, got, ref.v, cout);
+        if (stats) {
+            std::vector<float> hs((size_t)g_ctx->num_sms * cout * 2);
+            CK(cudaMemcpy(hs.data(), d_stats, hs.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<float> gs(cout * 2, 0.f), rs(cout * 2, 0.f);
+            for (int b = 0; b < L.grid; ++b)
+                for (int j = 0; j < cout * 2; ++j) gs[j] += hs[(size_t)b * cout * 2 + j];
+            for (size_t i = 0; i < got.size(); ++i) {
+                rs[(i % cout) * 2] += got[i];
+                rs[(i % cout) * 2 + 1] += got[i] * got[i];
+            }
+            std::string nm = std::string(name) + " [stats]";
+            report(nm.c_str(), compare(gs, rs), 1e-4, gs, rs, 2);
+        }
+    }
+    cudaFree(d_low); cudaFree(d_src); cudaFree(d_res); cudaFree(d_w); cudaFree(d_sc); cudaFree(d_sh);
+    cudaFree(d_wpk); cudaFree(d_out);
+    if (d_stats) cudaFree(d_stats);
+}
+
 // ------------------------------------------------------------------------------------------------ timing
 static void bench_conv(const char* name, int N, int H, int W, int cin, int cout, int k, int stride, int iters) {
     const size_t in_e = (size_t)N * H * W * cin, out_e = (size_t)N * (H / stride) * (W / stride) * cout;
@@ -421,6 +504,68 @@ static void bench_conv(const char* name, int N, int H, int W, int cin, int cout,
            flops / ms * 1e-9, bytes / ms * 1e-6, L.grid, L.p.stages);
     check_err_flag(name);
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_wpk);
+}
+
+static void bench_hconv(const char* name, int N, int H, int W, int cup, int cskip, int cout, int iters) {
+    const int ctot = cup + cskip;
+    const size_t low_e = (size_t)N * (H / 2) * (W / 2) * (cup ? cup : 8), src_e = (size_t)N * H * W * (cskip ? cskip : 8);
+    const size_t out_e = (size_t)N * H * W * cout;
+    __nv_bfloat16 *d_low, *d_src, *d_out, *d_wpk;
+    CK(cudaMalloc(&d_low, low_e * 2));
+    CK(cudaMalloc(&d_src, src_e * 2));
+    CK(cudaMalloc(&d_out, out_e * 2));
+    CK(cudaMalloc(&d_wpk, (size_t)9 * ctot * cout * 2));
+    CK(cudaMemset(d_low, 0x3C, low_e * 2));
+    CK(cudaMemset(d_src, 0x3C, src_e * 2));
+    CK(cudaMemset(d_wpk, 0x3C, (size_t)9 * ctot * cout * 2));
+    EpilogueDesc ep;
+    ep.relu = 1;
+    HconvLaunch L;
+    std::string e = hconv_build(L, cup ? d_low : nullptr, cup, cskip ? d_src : nullptr, cskip, d_wpk, cout, N, H, W, d_out,
+                                ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] bench %s: %s\n", name, e.c_str());
+        return;
+    }
+    long long* d_prof;
+    CK(cudaMalloc(&d_prof, (size_t)L.grid * 16 * 8));
+    L.p.prof = d_prof;
+    const int modes[] = {0, 8, 13, 15};
+    for (int mode : modes) {
+        L.p.dbg = mode;
+        CK(cudaMemset(d_prof, 0, (size_t)L.grid * 16 * 8));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int i = 0; i < 2; ++i) CK(hconv_launch(L, 0));
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) CK(hconv_launch(L, 0));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= iters;
+        const double flops = 2.0 * N * H * W * (double)cout * ctot * 9;
+        const double bytes = ((cup ? low_e : 0) + (cskip ? src_e : 0) + out_e) * 2.0;
+        const int tiles = L.p.tiles_w * L.p.tiles_h * N;
+        printf("[BENCH-H] %-30s skip[%s%s%s] %8.1f us %7.1f TFLOP/s %7.1f GB/s  %6.0f cyc/tile  grid %d stages %d smem %u\n",
+               name, mode & 1 ? "L" : "-", mode & 2 ? "M" : "-", mode & 4 ? "E" : "-", ms * 1e3, flops / ms * 1e-9,
+               bytes / ms * 1e-6, ms * 1e-3 * 1.965e9 / ((double)tiles / L.grid) / L.occ, L.grid, L.p.stages, L.smem);
+        if (mode & 8) {
+            std::vector<long long> hp((size_t)L.grid * 16);
+            CK(cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost));
+            const double per = (double)tiles / L.grid;  // counters hold the last launch only
+            const char* nm[10] = {"P:wait_empty", "P:issue", "P:wait_group", "P:fence+arrive", "M:wait_tempty", "M:wait_full",
+                                  "M:issue", "M:commit", "E:wait_tfull", "E:work"};
+            printf("          cycles/tile (CTA 0):");
+            for (int k = 0; k < 10; ++k) printf(" %s=%.0f", nm[k], hp[k] / per);
+            printf("\n");
+        }
+    }
+    cudaFree(d_prof);
+    check_err_flag(name);
+    cudaFree(d_low); cudaFree(d_src); cudaFree(d_out); cudaFree(d_wpk);
 }
 
 int main(int argc, char** argv) {
@@ -466,6 +611,15 @@ int main(int argc, char** argv) {
         case_dec1("dec1 up512+skip256->256 1x8x8", 1, 8, 8, 512, 256, 256);
         case_dec1("dec1 up32->16 (no skip) 2x16x32", 2, 16, 32, 32, 0, 16);
     }
+    if (want("hconv")) {
+        case_hconv("hconv 16->16 2x32x32", 2, 32, 32, 0, 16, 16, false, true, true, true);
+        case_hconv("hconv 32->32 1x48x40 (partial tiles)", 1, 48, 40, 0, 32, 32, false, true, true, true);
+        case_hconv("hconv 64->64 +res 3x24x24 (partial)", 3, 24, 24, 0, 64, 64, true, true, true, true);
+        case_hconv("hconv 64->64 raw 5x64x64 (multi-tile/CTA)", 5, 64, 64, 0, 64, 64, false, false, false, true);
+        case_hconv("hconv up32->16 2x32x64", 2, 32, 64, 32, 0, 16, false, true, true, false);
+        case_hconv("hconv up64+skip64->32 2x32x32", 2, 32, 32, 64, 64, 32, false, true, true, true);
+        case_hconv("hconv 32->64 (dgrad shape) 1x16x24", 1, 16, 24, 0, 32, 64, false, false, false, false);
+    }
     if (want("bench")) {
         bench_conv("L1 3x3 64->64 @128^2 x32", 32, 128, 128, 64, 64, 3, 1, 20);
         bench_conv("L2 3x3 128->128 @64^2 x32", 32, 64, 64, 128, 128, 3, 1, 20);
@@ -473,6 +627,13 @@ int main(int argc, char** argv) {
         bench_conv("L4 3x3 512->512 @16^2 x32", 32, 16, 16, 512, 512, 3, 1, 20);
         bench_conv("D3 3x3 32->32 @256^2 x32", 32, 256, 256, 32, 32, 3, 1, 10);
         bench_conv("D4 3x3 16->16 @512^2 x32", 32, 512, 512, 16, 16, 3, 1, 10);
+    }
+    if (want("hbench")) {
+        bench_hconv("D4c2 16->16 @512^2 x32", 32, 512, 512, 0, 16, 16, 5);
+        bench_hconv("D3c2 32->32 @256^2 x32", 32, 256, 256, 0, 32, 32, 5);
+        bench_hconv("L1 64->64 @128^2 x32", 32, 128, 128, 0, 64, 64, 10);
+        bench_hconv("D4c1 up32->16 @512^2 x32", 32, 512, 512, 32, 0, 16, 5);
+        bench_hconv("D3c1 up64+64->32 @256^2 x32", 32, 256, 256, 64, 64, 32, 5);
     }
     printf("SELFTEST %s: %d checks, %d failures\n", g_fail ? "FAILED" : "OK", g_run, g_fail);
     return g_fail ? 1 : 0;

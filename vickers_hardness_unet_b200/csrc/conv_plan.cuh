@@ -4,6 +4,7 @@
 
 #include <string>
 
+#include "hconv.cuh"
 #include "igemm.cuh"
 #include "tmap.cuh"
 
@@ -146,6 +147,82 @@ inline cudaError_t igemm_launch(const IgemmLaunch& L, cudaStream_t st) {
         attr_set = true;
     }
     igemm_kernel<<<L.grid, kIgemmThreads, L.smem, st>>>(L.a0, L.a1, L.b, L.d, L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ hconv (halo-resident 3x3)
+struct HconvLaunch {
+    HconvParams p;
+    int grid = 0;
+    uint32_t smem = 0;
+    int occ = 1;       // CTAs per SM (1 or 2)
+};
+
+// Can the halo-resident kernel run a 3x3/s1 conv with these channel counts?  (weights of all 9 taps + >= 2 halo stages
+// must fit in shared memory).  Returns the pipeline depth (0 = no).
+inline int hconv_stages(int cup, int cskip, int cout) {
+    const int ctot = cup + cskip;
+    if (!(cout == 16 || cout == 32 || cout == 64)) return 0;
+    if (!(ctot == 16 || ctot == 32 || ctot == 64 || ctot == 128) || cup % 8 || cskip % 8) return 0;
+    for (int st = 6; st >= 2; --st)
+        if (hconv_smem(ctot, cout, st).total + 1024 <= 232448u) return st;
+    return 0;
+}
+
+inline std::string hconv_build(HconvLaunch& L, const void* low, int cup, const void* src, int cskip, const void* wpk,
+                               int cout, int N, int H, int W, void* out, const EpilogueDesc& ep, int* err, int num_sms) {
+    memset(&L, 0, sizeof(L));
+    HconvParams& P = L.p;
+    const int stages = hconv_stages(cup, cskip, cout);
+    if (!stages) return "hconv: unsupported channel configuration";
+    if (cup && ((H | W) & 1)) return "hconv: up-sampled source needs even H, W";
+    if (ep.residual.ptr && (ep.residual.sW != cout || ep.residual.sH != (long long)W * cout ||
+                            ep.residual.sN != (long long)H * W * cout))
+        return "hconv: residual must be a dense NHWC tensor of the output's shape";
+    P.H = H; P.W = W; P.N = N;
+    P.tiles_w = (W + kHcTileW - 1) / kHcTileW;
+    P.tiles_h = (H + kHcTileH - 1) / kHcTileH;
+    P.cup = cup; P.cskip = cskip;
+    P.low = reinterpret_cast<const __nv_bfloat16*>(low);
+    P.src = reinterpret_cast<const __nv_bfloat16*>(src);
+    P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
+    P.cout = cout;
+    P.stages = stages;
+    P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.stats = ep.stats;
+    P.err = err;
+    L.smem = hconv_smem(cup + cskip, cout, stages).total + 1024;
+    L.occ = 1;
+    // two co-resident CTAs when both fit (shared memory incl. the 1 KB per-CTA reservation, TMEM 2 x 4 x cout <= 512)
+    for (int st = stages < 4 ? stages : 4; st >= 2; --st) {
+        const uint32_t sm2 = hconv_smem(cup + cskip, cout, st).total + 1024;
+        if (2 * (sm2 + 1024) <= 232448u) {
+            L.occ = 2;
+            P.stages = st;
+            L.smem = sm2;
+            break;
+        }
+    }
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    const int slots = num_sms * L.occ;
+    const int waves = (total_tiles + slots - 1) / slots;
+    L.grid = (total_tiles + waves - 1) / waves;
+    return "";
+}
+
+inline cudaError_t hconv_launch(const HconvLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(hconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(hconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (L.occ == 2) hconv_kernel<2><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
+    else hconv_kernel<1><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,7 @@
 // scale/shift (folded BN), residual add and ReLU, or emits raw output + per-channel batch statistics partials,
 // and writes bf16 through a swizzled smem staging tile with TMA stores (which clip partial tiles).
 #pragma once
+#include "epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ub {
@@ -211,15 +212,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     } else {
         // ================================================================= epilogue (4 warps, one TMEM lane quadrant each)
         const int q = warp & 3;
-        const int row = q * 32 + lane;          // tile row == TMEM lane == pixel index inside the tile
         const int et = threadIdx.x - 64;        // 0..127
-        const float* ss = reinterpret_cast<const float*>(sm + L.ss_off);
-        float* part = reinterpret_cast<float*>(sm + L.part_off);
-        float* cst = reinterpret_cast<float*>(sm + L.cstat_off);
-        const int cblk = P.out_cblk;
-        const int nblk = P.ntile / cblk;
-        const uint32_t row_bytes = cblk * 2;
-        const uint32_t swz_mask = (cblk >= 64) ? 7u : (cblk == 32 ? 3u : 1u);
+        EpiParams E;
+        E.ntile = P.ntile; E.out_cblk = P.out_cblk; E.relu = P.relu; E.cout = P.cout;
+        E.bw = P.bw; E.bh = P.bh; E.bn = P.bn; E.Wo = P.Wo; E.Ho = P.Ho; E.Nimg = P.Nimg;
+        E.residual = P.residual; E.res_sw = P.res_sw; E.res_sh = P.res_sh; E.res_sn = P.res_sn;
+        E.stats = P.stats;
+        EpiSmem ES;
+        ES.staging = sm + L.staging_off; ES.staging_bytes = L.staging_bytes;
+        ES.ss = reinterpret_cast<const float*>(sm + L.ss_off);
+        ES.part = reinterpret_cast<float*>(sm + L.part_off);
+        ES.cst = reinterpret_cast<float*>(sm + L.cstat_off);
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t blk_counter = 0;
@@ -230,123 +233,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             m /= P.tiles_w;
             const int th = m % P.tiles_h;
             const int tn = m / P.tiles_h;
-            const int pw = tw * P.bw + row % P.bw;
-            const int ph = th * P.bh + (row / P.bw) % P.bh;
-            const int pn = tn * P.bn + row / (P.bw * P.bh);
-            const bool valid = (pw < P.Wo) && (ph < P.Ho) && (pn < P.Nimg);
-
             if (!mbar_wait(tfull_bar(acc), acc_phase)) {
                 *s_abort = 1;
                 atomicExch(P.err, 4);
                 goto role_done;
             }
             tc_fence_after();
-            for (int cb = 0; cb < nblk; ++cb, ++blk_counter) {
-                const int cbase = nt * P.ntile + cb * cblk;  // first output channel of this block
-                uint8_t* sbuf = sm + L.staging_off + (blk_counter & 1) * L.staging_bytes;
-                if (et == 0) tma_wait_read<1>();  // the store issued two blocks ago has finished reading this buffer
-                named_bar_sync(1, 128);
-                for (int h0 = 0; h0 < cblk; h0 += 32) {
-                    const int ncol = (cblk - h0) < 32 ? (cblk - h0) : 32;  // 16 or 32
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * P.ntile + cb * cblk + h0;
-                    if (ncol == 32) {
-                        tmem_ld32(taddr, r);
-                    } else {
-                        uint32_t r16[16];
-                        tmem_ld16(taddr, r16);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) r[i] = r16[i];
-#pragma unroll
-                        for (int i = 16; i < 32; ++i) r[i] = 0;
-                    }
-                    tmem_ld_wait();
-                    if (cb == nblk - 1 && h0 + 32 >= cblk) {
-                        // last TMEM read of this accumulator: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(acc));
-                    }
-                    const __nv_bfloat16* resp = nullptr;
-                    if (P.residual && valid)
-                        resp = P.residual + pn * P.res_sn + ph * P.res_sh + pw * P.res_sw + cbase + h0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // 4 x (8 channels = 16 B)
-                        if (j * 8 >= ncol) break;
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int c = cbase + h0 + j * 8 + i;
-                            v[i] = __uint_as_float(r[j * 8 + i]) * ss[c] + ss[512 + c];
-                        }
-                        if (resp) {
-                            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + j * 8));
-                            v[0] += bf16_lo(rv.x); v[1] += bf16_hi(rv.x);
-                            v[2] += bf16_lo(rv.y); v[3] += bf16_hi(rv.y);
-                            v[4] += bf16_lo(rv.z); v[5] += bf16_hi(rv.z);
-                            v[6] += bf16_lo(rv.w); v[7] += bf16_hi(rv.w);
-                        }
-                        if (P.relu) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                        }
-                        if (!valid) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-                        }
-                        uint4 o;
-                        o.x = pack_bf16(v[0], v[1]);
-                        o.y = pack_bf16(v[2], v[3]);
-                        o.z = pack_bf16(v[4], v[5]);
-                        o.w = pack_bf16(v[6], v[7]);
-                        uint32_t off = row * row_bytes + (h0 * 2 + j * 16);
-                        off ^= ((off >> 7) & swz_mask) << 4;
-                        *reinterpret_cast<uint4*>(sbuf + off) = o;
-                    }
-                }
-                fence_async_smem();
-                named_bar_sync(2, 128);
-                if (et == 0) {
-                    tma_store_4d(&tmD, smem_u32(sbuf), cbase, tw * P.bw, th * P.bh, tn * P.bn);
-                    tma_commit();
-                }
-                if (P.stats) {
-                    // per-channel sum / sum of squares over the tile's 128 pixels, from the bf16 values just staged
-                    const int ngrp = 128 / cblk;
-                    const int c = et % cblk, g = et / cblk;
-                    float s1 = 0.f, s2 = 0.f;
-                    for (int rr = g; rr < 128; rr += ngrp) {
-                        uint32_t off = rr * row_bytes + c * 2;
-                        off ^= ((off >> 7) & swz_mask) << 4;
-                        const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sbuf + off));
-                        s1 += x;
-                        s2 += x * x;
-                    }
-                    part[(g * 64 + c) * 2 + 0] = s1;
-                    part[(g * 64 + c) * 2 + 1] = s2;
-                    named_bar_sync(3, 128);
-                    if (et < cblk) {
-                        float t1 = 0.f, t2 = 0.f;
-                        for (int gg = 0; gg < ngrp; ++gg) {
-                            t1 += part[(gg * 64 + et) * 2 + 0];
-                            t2 += part[(gg * 64 + et) * 2 + 1];
-                        }
-                        // channel cbase+et is always owned by this thread (et == channel % cblk): no race
-                        cst[2 * (cbase + et)] += t1;
-                        cst[2 * (cbase + et) + 1] += t2;
-                    }
-                    // `part` is rewritten only after the next block's named_bar_sync(1), which orders it after these reads
-                }
-            }
+            epilogue_tile(E, ES, &tmD, tmem_base + acc * P.ntile, tempty_bar(acc), tw, th, tn, nt, q, lane, et, blk_counter);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
-        if (P.stats) {
-            named_bar_sync(3, 128);
-            float* dst = P.stats + static_cast<size_t>(blockIdx.x) * P.cout * 2;
-            for (int j = et; j < 2 * P.cout; j += 128) dst[j] = cst[j];
-        }
-        if (et == 0) tma_wait_all<0>();  // all output stores complete before the CTA exits
+        epilogue_finish(E, ES, q, lane, et);
     }
 role_done:
     tc_fence_before();

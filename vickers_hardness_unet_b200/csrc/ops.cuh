@@ -62,6 +62,37 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
+// hconv operand: OIHW fp32 -> K-major rows [tap][block = c/64][co][c % 64 (or all ctot < 64 channels)] bf16 for the channel
+// slice [ci0, ci0+ctot), with the 16-byte chunks XOR-swizzled by the 128-byte line index of the byte offset inside the
+// whole array (the kernel copies the array linearly to a 1 KB-aligned shared-memory region: csrc/hconv.cuh).
+// transposed=1 builds the data-gradient operand instead: output rows are the conv's INPUT channels (cout_ := cin slice),
+// K runs over the conv's output channels and the taps are mirrored:  value = w[c][ci0 + co][2-r][2-s].
+__global__ void pack_hconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int ctot,
+                                    int dim1_total, int ci0, int transposed) {
+    const long long total = 9ll * ctot * cout;
+    const int cpr = ctot < 64 ? ctot : 64;          // channels per row
+    const int nblk = ctot > 64 ? ctot / 64 : 1;
+    const unsigned row_bytes = cpr * 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        // i enumerates the LOGICAL (unswizzled) layout
+        const int cc = int(i % cpr);
+        long long t = i / cpr;
+        const int co = int(t % cout);
+        t /= cout;
+        const int blk = int(t % nblk);
+        const int tap = int(t / nblk);
+        const int c = blk * 64 + cc;
+        const int r = tap / 3, s = tap - 3 * r;
+        float v;
+        if (!transposed) v = w[(((long long)co * dim1_total + ci0 + c) * 3 + r) * 3 + s];
+        else v = w[(((long long)c * dim1_total + ci0 + co) * 3 + (2 - r)) * 3 + (2 - s)];
+        const unsigned off = (unsigned)(i * 2);
+        const unsigned phys = off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4);
+        out[phys / 2] = __float2bfloat16(v);
+    }
+}
+
 // Stem: [64][3][7][7] -> [64][r*32 + px*4 + ch], px 0..7 <-> kernel column s = px-1 (px 0 and ch 3 are zero).
 __global__ void pack_stem_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -56,6 +56,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
     return true;
 }
 
+// Whole-warp wait with ONE polling lane (32x less shared-memory barrier traffic than every lane polling).
+__device__ __forceinline__ bool mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+    bool ok = true;
+    if (lane == 0) ok = mbar_wait(bar, parity);
+    return __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+}
+
 // ----------------------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_async_smem() {  // generic-proxy smem writes -> visible to async proxy (TMA store)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -182,6 +189,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// Same with the accumulate flag known at compile time (no predicate set-up in the issuing thread's instruction stream).
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_bf16_c(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (kAccumulate) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+    }
 }
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

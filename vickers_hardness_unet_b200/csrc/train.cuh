@@ -149,7 +149,10 @@ inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaSt
         for (auto& d : S.dec) if (d.c1 == (int)i) dd = &d;
         if (dd) {
             const int cin_total = dd->cup + dd->cskip;
-            if (dd->cskip) {
+            if (dd->cskip && hconv_stages(0, dd->cout, dd->cskip)) {
+                pack_hconv_w_kernel<<<grid(9ll * dd->cskip * dd->cout), 256, 0, st>>>(
+                    params + c.w, T.wdg + T.wdg_off[i], dd->cskip, dd->cout, cin_total, dd->cup, 1);
+            } else if (dd->cskip) {
                 TapList tl;
                 tl.n = 9;
                 for (int t = 0; t < 9; ++t) { tl.r[t] = 2 - t / 3; tl.s[t] = 2 - t % 3; }
@@ -179,6 +182,9 @@ inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaSt
                 }
                 o += (long long)c.cin * ncols;
             }
+        } else if (hconv_stages(0, c.cout, c.cin)) {
+            pack_hconv_w_kernel<<<grid(9ll * c.cin * c.cout), 256, 0, st>>>(params + c.w, T.wdg + T.wdg_off[i], c.cin, c.cout,
+                                                                           c.cin, 0, 1);
         } else {
             pack_conv_w_kernel<<<grid((long long)c.cin * 9 * c.cout), 256, 0, st>>>(params + c.w, T.wdg + T.wdg_off[i],
                                                                                    c.cout, c.cin, 3, 3, 1);
@@ -364,15 +370,25 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         if (dry) return "";
         EpilogueDesc ep;
         ep.stats = plan.stat_part;
-        IgemmLaunch L;
-        std::string e = (u.conv == S.stem)
-                            ? build_stem(ctx, L, ctx->wpk + c.wpk, in, N, H, W, u.z, ep)
-                            : build_conv(ctx, L, c, ctx->wpk + c.wpk, in, N, u.Hin, u.Win, u.z, ep);
-        if (!e.empty()) return c.name + ": " + e;
-        add_f("conv_fwd:" + c.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
         StatSegs segs;
         memset(&segs, 0, sizeof(segs));
-        segs.n = 1; segs.ptr[0] = plan.stat_part; segs.rows[0] = L.grid;
+        segs.n = 1; segs.ptr[0] = plan.stat_part;
+        if (c.hc && u.conv != S.stem) {
+            HconvLaunch HL;
+            std::string e = hconv_build(HL, nullptr, 0, in, c.cin, ctx->wpk + c.wpk, c.cout, N, u.Hin, u.Win, u.z, ep,
+                                        ctx->d_err, SM);
+            if (!e.empty()) return c.name + ": " + e;
+            add_f("conv_fwd:" + c.name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
+            segs.rows[0] = HL.grid;
+        } else {
+            IgemmLaunch L;
+            std::string e = (u.conv == S.stem)
+                                ? build_stem(ctx, L, ctx->wpk + c.wpk, in, N, H, W, u.z, ep)
+                                : build_conv(ctx, L, c, ctx->wpk + c.wpk, in, N, u.Hin, u.Win, u.z, ep);
+            if (!e.empty()) return c.name + ": " + e;
+            add_f("conv_fwd:" + c.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
+            segs.rows[0] = L.grid;
+        }
         add_bn_fwd(ui, segs, residual, relu);
         return "";
     };
@@ -433,8 +449,19 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             const Unit u1 = plan.units[r.u1];
             StatSegs segs;
             memset(&segs, 0, sizeof(segs));
-            segs.n = 4;
-            for (int par = 0; par < 4; ++par) {
+            if (S.convs[d.c1].hc) {
+                // fused nearest-2x upsample + concat in the halo loader: one launch, original 3x3 weights
+                EpilogueDesc ep;
+                ep.stats = plan.stat_part;
+                HconvLaunch HL;
+                err = hconv_build(HL, cur, d.cup, skips[i], d.cskip, ctx->wpk + S.convs[d.c1].wpk, d.cout, N, 2 * h, 2 * w,
+                                  u1.z, ep, ctx->d_err, SM);
+                if (!err.empty()) return S.convs[d.c1].name + ": " + err;
+                add_f("conv_fwd:" + S.convs[d.c1].name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
+                segs.n = 1; segs.ptr[0] = ep.stats; segs.rows[0] = HL.grid;
+            }
+            segs.n = S.convs[d.c1].hc ? 1 : 4;
+            for (int par = 0; par < (S.convs[d.c1].hc ? 0 : 4); ++par) {
                 EpilogueDesc ep;
                 ep.stats = plan.stat_part + (size_t)par * SM * 512 * 2;
                 IgemmLaunch L;
@@ -564,6 +591,14 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         t.cin = c.cout; t.cout = c.cin; t.k = 3; t.stride = 1;
         EpilogueDesc ep;
         if (residual) ep.residual = nhwc_view(residual, N, u.Hin, u.Win, c.cin);
+        if (hconv_stages(0, c.cout, c.cin)) {
+            HconvLaunch HL;
+            std::string e = hconv_build(HL, nullptr, 0, u.dz, c.cout, T.wdg + T.wdg_off[u.conv], c.cin, N, u.Ho, u.Wo, out,
+                                        ep, ctx->d_err, SM);
+            if (!e.empty()) return c.name + " dgrad: " + e;
+            add_b(stage, "dgrad:" + c.name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
+            return "";
+        }
         IgemmLaunch L;
         std::string e = build_conv(ctx, L, t, T.wdg + T.wdg_off[u.conv], u.dz, N, u.Ho, u.Wo, out, ep);
         if (!e.empty()) return c.name + " dgrad: " + e;
@@ -629,11 +664,19 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         if (d.cskip) {
             ConvRef t;
             t.cin = d.cout; t.cout = d.cskip; t.k = 3; t.stride = 1;
-            IgemmLaunch L;
             EpilogueDesc ep;
-            err = build_conv(ctx, L, t, T.wdg + T.wdg_off[d.c1], u1.dz, N, u1.Ho, u1.Wo, r.d_skip, ep);
-            if (!err.empty()) return c1.name + " dskip: " + err;
-            add_b(0, "dgrad_skip:" + c1.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
+            if (hconv_stages(0, d.cout, d.cskip)) {
+                HconvLaunch HL;
+                err = hconv_build(HL, nullptr, 0, u1.dz, d.cout, T.wdg + T.wdg_off[d.c1], d.cskip, N, u1.Ho, u1.Wo, r.d_skip,
+                                  ep, ctx->d_err, SM);
+                if (!err.empty()) return c1.name + " dskip: " + err;
+                add_b(0, "dgrad_skip:" + c1.name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
+            } else {
+                IgemmLaunch L;
+                err = build_conv(ctx, L, t, T.wdg + T.wdg_off[d.c1], u1.dz, N, u1.Ho, u1.Wo, r.d_skip, ep);
+                if (!err.empty()) return c1.name + " dskip: " + err;
+                add_b(0, "dgrad_skip:" + c1.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
+            }
         }
         {
             // gradient w.r.t. the low-res input -> becomes d_cur of the previous decoder block / layer4 output

@@ -40,6 +40,8 @@ struct ConvRef {
     int bn = -1;          // index into bns
     long long wpk = -1;   // offset (elements) into the packed bf16 weight arena
     long long wpk_elems = 0;
+    int hc = 0;           // > 0: runs on the halo-resident kernel (hconv.cuh) with this many pipeline stages
+    int hc_cup = 0;       // hconv: channels taken from the nearest-2x up-sampled low-res source (decoder conv1)
 };
 
 struct NetSpec {
@@ -139,6 +141,13 @@ struct NetSpec {
             else n = (long long)c.cout * c.cin * c.k * c.k;
             bool is_dec1 = false;
             for (auto& d : dec) if (d.c1 == (int)i) { n = 4ll * d.cout * (9 * d.cskip + 4 * d.cup); is_dec1 = true; }
+            if (c.k == 3 && c.stride == 1) {
+                int cup = 0;
+                for (auto& d : dec) if (d.c1 == (int)i) cup = d.cup;
+                c.hc = hconv_stages(cup, c.cin - cup, c.cout);
+                c.hc_cup = c.hc ? cup : 0;
+                if (c.hc && 9ll * c.cin * c.cout > n) n = 9ll * c.cin * c.cout;
+            }
             (void)is_dec1;
             c.wpk = wpk_total;
             c.wpk_elems = n;
@@ -238,7 +247,10 @@ inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers,
             continue;
         }
         __nv_bfloat16* dst = ctx->wpk + c.wpk;
-        if ((int)i == S.stem) {
+        if (c.hc) {
+            pack_hconv_w_kernel<<<ew_grid(9ll * c.cin * c.cout, 256, ctx->num_sms), 256, 0, st>>>(params + c.w, dst, c.cout,
+                                                                                                 c.cin, c.cin, 0, 0);
+        } else if ((int)i == S.stem) {
             pack_stem_w_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(params + c.w, dst);
         } else {
             const NetSpec::Dec* dd = nullptr;
@@ -398,6 +410,23 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         plan.steps.push_back({[L](cudaStream_t st) { return igemm_launch(L, st); }, name, 1});
     };
 
+    // 3x3 / 1x1 conv of the encoder or a decoder conv2: halo-resident kernel where it applies, tap-table kernel otherwise
+    auto add_conv = [&](const ConvRef& c, const void* in, int hin, int win, void* out, const EpilogueDesc& ep) -> std::string {
+        if (c.hc) {
+            HconvLaunch HL;
+            std::string e = hconv_build(HL, nullptr, 0, in, c.cin, ctx->wpk + c.wpk, c.cout, N, hin, win, out, ep, ctx->d_err,
+                                        ctx->num_sms);
+            if (!e.empty()) return c.name + ": " + e;
+            plan.steps.push_back({[HL](cudaStream_t st) { return hconv_launch(HL, st); }, c.name, 1});
+            return "";
+        }
+        IgemmLaunch L;
+        std::string e = build_conv(ctx, L, c, ctx->wpk + c.wpk, in, N, hin, win, out, ep);
+        if (!e.empty()) return c.name + ": " + e;
+        add_igemm(L, c.name);
+        return "";
+    };
+
     plan.xp = A.take((long long)N * H * (W + 8) * 4);
     __nv_bfloat16* f1 = A.take((long long)N * (H / 2) * (W / 2) * 64);
     if (!dry) {
@@ -429,21 +458,14 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
             __nv_bfloat16* ident = cur;
             if (blk.ds >= 0) ident = A.take((long long)N * ho * wo * c1.cout);
             if (!dry) {
-                IgemmLaunch L;
-                err = build_conv(ctx, L, c1, ctx->wpk + c1.wpk, cur, N, h, w, t, fold(c1.bn, 1));
-                if (!err.empty()) return c1.name + ": " + err;
-                add_igemm(L, c1.name);
+                if (!(err = add_conv(c1, cur, h, w, t, fold(c1.bn, 1))).empty()) return err;
                 if (blk.ds >= 0) {
                     const ConvRef& cd = S.convs[blk.ds];
-                    err = build_conv(ctx, L, cd, ctx->wpk + cd.wpk, cur, N, h, w, ident, fold(cd.bn, 0));
-                    if (!err.empty()) return cd.name + ": " + err;
-                    add_igemm(L, cd.name);
+                    if (!(err = add_conv(cd, cur, h, w, ident, fold(cd.bn, 0))).empty()) return err;
                 }
                 EpilogueDesc ep = fold(c2.bn, 1);
                 ep.residual = nhwc_view(ident, N, ho, wo, c1.cout);
-                err = build_conv(ctx, L, c2, ctx->wpk + c2.wpk, t, N, ho, wo, o, ep);
-                if (!err.empty()) return c2.name + ": " + err;
-                add_igemm(L, c2.name);
+                if (!(err = add_conv(c2, t, ho, wo, o, ep)).empty()) return err;
             }
             cur = o;
             h = ho;
@@ -460,16 +482,22 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         __nv_bfloat16* t = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         __nv_bfloat16* o = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         if (!dry) {
-            for (int par = 0; par < 4; ++par) {
-                IgemmLaunch L;
-                err = build_dec1(ctx, L, d, ctx->wpk + c1.wpk, par, cur, skips[i], N, h, w, t, fold(c1.bn, 1));
+            if (c1.hc) {
+                // fused nearest-2x upsample + concat inside the halo loader: ONE launch, original 3x3 weights
+                HconvLaunch HL;
+                err = hconv_build(HL, cur, d.cup, skips[i], d.cskip, ctx->wpk + c1.wpk, d.cout, N, 2 * h, 2 * w, t,
+                                  fold(c1.bn, 1), ctx->d_err, ctx->num_sms);
                 if (!err.empty()) return c1.name + ": " + err;
-                add_igemm(L, c1.name + "[parity " + std::to_string(par) + "]");
+                plan.steps.push_back({[HL](cudaStream_t st) { return hconv_launch(HL, st); }, c1.name, 1});
+            } else {
+                for (int par = 0; par < 4; ++par) {
+                    IgemmLaunch L;
+                    err = build_dec1(ctx, L, d, ctx->wpk + c1.wpk, par, cur, skips[i], N, h, w, t, fold(c1.bn, 1));
+                    if (!err.empty()) return c1.name + ": " + err;
+                    add_igemm(L, c1.name + "[parity " + std::to_string(par) + "]");
+                }
             }
-            IgemmLaunch L;
-            err = build_conv(ctx, L, c2, ctx->wpk + c2.wpk, t, N, 2 * h, 2 * w, o, fold(c2.bn, 1));
-            if (!err.empty()) return c2.name + ": " + err;
-            add_igemm(L, c2.name);
+            if (!(err = add_conv(c2, t, 2 * h, 2 * w, o, fold(c2.bn, 1))).empty()) return err;
         }
         cur = o;
         h *= 2;

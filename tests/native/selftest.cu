@@ -467,6 +467,91 @@ static void case_hconv(const char* name, int N, int H, int W, int cup, int cskip
     if (d_stats) cudaFree(d_stats);
 }
 
+// hwgrad: dW of a 3x3 s1 conv over cat(nearest2x(low), src) given dZ, vs a CPU reference; output = packed [co][9][ctot]
+static void case_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout) {
+    const int ctot = cup + cskip;
+    HostT low(N, H / 2, W / 2, cup ? cup : 1), src(N, H, W, cskip ? cskip : 1), cat(N, H, W, ctot), dz(N, H, W, cout);
+    fill_rand_bf16(low.v, 1.0f);
+    fill_rand_bf16(src.v, 1.0f);
+    fill_rand_bf16(dz.v, 1.0f);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                for (int c = 0; c < cup; ++c) cat.at(n, h, w, c) = low.at(n, h / 2, w / 2, c);
+                for (int c = 0; c < cskip; ++c) cat.at(n, h, w, cup + c) = src.at(n, h, w, c);
+            }
+    std::vector<float> ref((size_t)cout * 9 * ctot, 0.f);
+#pragma omp parallel for collapse(2)
+    for (int co = 0; co < cout; ++co)
+        for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            for (int ci = 0; ci < ctot; ++ci) {
+                double acc = 0;
+                for (int n = 0; n < N; ++n)
+                    for (int h = 0; h < H; ++h)
+                        for (int w = 0; w < W; ++w) acc += (double)dz.at(n, h, w, co) * cat.get(n, h + r - 1, w + s - 1, ci);
+                ref[((size_t)co * 9 + tap) * ctot + ci] = (float)acc;
+            }
+        }
+    __nv_bfloat16* d_low = to_dev_bf16(low.v);
+    __nv_bfloat16* d_src = to_dev_bf16(src.v);
+    __nv_bfloat16* d_dz = to_dev_bf16(dz.v);
+    float* d_g;
+    CK(cudaMalloc(&d_g, ref.size() * 4));
+    CK(cudaMemset(d_g, 0, ref.size() * 4));
+    HwgradLaunch L;
+    std::string e = hwgrad_build(L, cup ? d_low : nullptr, cup, cskip ? d_src : nullptr, cskip, d_dz, cout, N, H, W, d_g,
+                                 g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %dx%d smem %u stages %d cw %d ndh %d\n", name, L.grid.x, L.grid.y, L.smem, L.p.stages, L.p.cw,
+           L.p.ndh_max);
+    CK(hwgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> got(ref.size());
+        CK(cudaMemcpy(got.data(), d_g, got.size() * 4, cudaMemcpyDeviceToHost));
+        report(name, compare(got, ref), 2e-3, got, ref, ctot);
+    }
+    cudaFree(d_low); cudaFree(d_src); cudaFree(d_dz); cudaFree(d_g);
+}
+static void bench_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout, int iters) {
+    const int ctot = cup + cskip;
+    __nv_bfloat16 *d_low, *d_src, *d_dz;
+    float* d_g;
+    CK(cudaMalloc(&d_low, (size_t)N * (H / 2) * (W / 2) * (cup ? cup : 8) * 2));
+    CK(cudaMalloc(&d_src, (size_t)N * H * W * (cskip ? cskip : 8) * 2));
+    CK(cudaMalloc(&d_dz, (size_t)N * H * W * cout * 2));
+    CK(cudaMalloc(&d_g, (size_t)cout * 9 * ctot * 4));
+    CK(cudaMemset(d_low, 0x3C, (size_t)N * (H / 2) * (W / 2) * (cup ? cup : 8) * 2));
+    CK(cudaMemset(d_src, 0x3C, (size_t)N * H * W * (cskip ? cskip : 8) * 2));
+    CK(cudaMemset(d_dz, 0x3C, (size_t)N * H * W * cout * 2));
+    HwgradLaunch L;
+    std::string e = hwgrad_build(L, cup ? d_low : nullptr, cup, cskip ? d_src : nullptr, cskip, d_dz, cout, N, H, W, d_g,
+                                 g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) { printf("[FAIL] bench %s: %s\n", name, e.c_str()); return; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) CK(hwgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) CK(hwgrad_launch(L, 0));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double flops = 2.0 * N * H * W * (double)cout * ctot * 9;
+    printf("[BENCH-W] %-30s %8.1f us %7.1f TFLOP/s  grid %dx%d stages %d smem %u\n", name, ms * 1e3, flops / ms * 1e-9,
+           L.grid.x, L.grid.y, L.p.stages, L.smem);
+    check_err_flag(name);
+    cudaFree(d_low); cudaFree(d_src); cudaFree(d_dz); cudaFree(d_g);
+}
+
 // ------------------------------------------------------------------------------------------------ timing
 static void bench_conv(const char* name, int N, int H, int W, int cin, int cout, int k, int stride, int iters) {
     const size_t in_e = (size_t)N * H * W * cin, out_e = (size_t)N * (H / stride) * (W / stride) * cout;
@@ -627,6 +712,22 @@ int main(int argc, char** argv) {
         bench_conv("L4 3x3 512->512 @16^2 x32", 32, 16, 16, 512, 512, 3, 1, 20);
         bench_conv("D3 3x3 32->32 @256^2 x32", 32, 256, 256, 32, 32, 3, 1, 10);
         bench_conv("D4 3x3 16->16 @512^2 x32", 32, 512, 512, 16, 16, 3, 1, 10);
+    }
+    if (want("hwgrad")) {
+        case_hwgrad("hwgrad 16->16 2x32x32", 2, 32, 32, 0, 16, 16);
+        case_hwgrad("hwgrad 32->32 1x48x40 (partial tiles)", 1, 48, 40, 0, 32, 32);
+        case_hwgrad("hwgrad 64->64 3x24x24 (2 row groups)", 3, 24, 24, 0, 64, 64);
+        case_hwgrad("hwgrad 16(K)->32 1x32x16", 1, 32, 16, 0, 16, 32);
+        case_hwgrad("hwgrad up32->16 2x32x64", 2, 32, 64, 32, 0, 16);
+        case_hwgrad("hwgrad up64+skip64->32 2x32x32 (4 groups)", 2, 32, 32, 64, 64, 32);
+        case_hwgrad("hwgrad 64->64 5x64x64 (multi-tile/CTA)", 5, 64, 64, 0, 64, 64);
+    }
+    if (want("wbench")) {
+        bench_hwgrad("D4c2 16->16 @512^2 x16", 16, 512, 512, 0, 16, 16, 5);
+        bench_hwgrad("D3c2 32->32 @256^2 x16", 16, 256, 256, 0, 32, 32, 5);
+        bench_hwgrad("L1 64->64 @128^2 x16", 16, 128, 128, 0, 64, 64, 10);
+        bench_hwgrad("D4c1 up32->16 @512^2 x16", 16, 512, 512, 32, 0, 16, 5);
+        bench_hwgrad("D3c1 up64+64->32 @256^2 x16", 16, 256, 256, 64, 64, 32, 5);
     }
     if (want("hbench")) {
         bench_hconv("D4c2 16->16 @512^2 x32", 32, 512, 512, 0, 16, 16, 5);

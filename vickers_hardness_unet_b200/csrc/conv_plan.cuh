@@ -5,6 +5,7 @@
 #include <string>
 
 #include "hconv.cuh"
+#include "hwgrad.cuh"
 #include "igemm.cuh"
 #include "tmap.cuh"
 
@@ -223,6 +224,63 @@ inline cudaError_t hconv_launch(const HconvLaunch& L, cudaStream_t st) {
     }
     if (L.occ == 2) hconv_kernel<2><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
     else hconv_kernel<1><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ hwgrad (halo-resident wgrad)
+struct HwgradLaunch {
+    HwgradParams p;
+    dim3 grid;
+    uint32_t smem = 0;
+};
+inline bool hwgrad_ok(int cup, int cskip, int cout) {
+    const int ctot = cup + cskip;
+    if (!(cout == 16 || cout == 32 || cout == 64)) return false;
+    if (!(ctot == 16 || ctot == 32 || ctot == 64 || ctot == 128) || cup % 8 || cskip % 8) return false;
+    if (ctot == 128 && cup % 64) return false;  // a 64-channel block must not straddle the two sources
+    return true;
+}
+inline std::string hwgrad_build(HwgradLaunch& L, const void* low, int cup, const void* src, int cskip, const void* dz,
+                                int cout, int N, int H, int W, float* gpk, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    if (!hwgrad_ok(cup, cskip, cout)) return "hwgrad: unsupported channel configuration";
+    if (cup && ((H | W) & 1)) return "hwgrad: up-sampled source needs even H, W";
+    HwgradParams& P = L.p;
+    const int ctot = cup + cskip;
+    P.H = H; P.W = W; P.N = N;
+    P.tiles_w = (W + kHcTileW - 1) / kHcTileW;
+    P.tiles_h = (H + kHcTileH - 1) / kHcTileH;
+    P.cup = cup; P.cskip = cskip;
+    P.low = reinterpret_cast<const __nv_bfloat16*>(low);
+    P.src = reinterpret_cast<const __nv_bfloat16*>(src);
+    P.dz = reinterpret_cast<const __nv_bfloat16*>(dz);
+    P.cout = cout;
+    P.cw = ctot < 64 ? ctot : 64;
+    P.ndh_max = 9 * P.cw <= 512 ? 3 : (6 * P.cw <= 512 ? 2 : 1);
+    P.gpk = gpk;
+    P.err = err;
+    int stages = 4;
+    for (; stages >= 2; --stages)
+        if (hwgrad_smem(P.cw, cout, stages).total + 1024 <= 232448u) break;
+    if (stages < 2) return "hwgrad: does not fit in shared memory";
+    P.stages = stages;
+    L.smem = hwgrad_smem(P.cw, cout, stages).total + 1024;
+    const int ngroups = (ctot / P.cw) * ((3 + P.ndh_max - 1) / P.ndh_max);
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    int gx = num_sms / ngroups;
+    if (gx < 1) gx = 1;
+    if (gx > total_tiles) gx = total_tiles;
+    L.grid = dim3(gx, ngroups, 1);
+    return "";
+}
+inline cudaError_t hwgrad_launch(const HwgradLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(hwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    hwgrad_kernel<<<L.grid, kHcThreads, L.smem, st>>>(L.p);
     return cudaGetLastError();
 }
 

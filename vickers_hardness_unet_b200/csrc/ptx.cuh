@@ -215,6 +215,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // ----------------------------------------------------------------------------------------------- misc
+// 16-byte vector reduction (no return value) into global memory: one L2 atomic transaction instead of four.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

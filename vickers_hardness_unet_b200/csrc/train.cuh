@@ -2,6 +2,7 @@
 // on top of igemm_kernel, wgrad_kernel and the elementwise kernels.  Mirrors /root/reference/train.py:428-449
 // (zero_grad -> forward -> loss -> backward -> optimizer.step) with the autograd graph written out by hand.
 #pragma once
+#include <algorithm>
 #include <memory>
 
 #include "train_ops.cuh"
@@ -78,6 +79,7 @@ struct TrainState {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     int arena_batch = 0;
+    float* gpk = nullptr;           // packed fp32 weight gradients [co][tap][ci] (conv c at element offset convs[c].w)
     __nv_bfloat16* wdg = nullptr;   // packed dgrad operands
     long long wdg_total = 0;
     std::vector<long long> wdg_off;       // per conv: offset of its dgrad operand(s)
@@ -85,6 +87,7 @@ struct TrainState {
     ~TrainState() {
         plans.clear();
         cudaFree(arena);
+        cudaFree(gpk);
         cudaFree(wdg);
     }
 };
@@ -208,6 +211,8 @@ struct WgSpec {
     float* grad = nullptr;
     long long s_co = 0, s_ci = 0;
     int stem_mode = 0;
+    int ntaps = 9, cin_total = 0;   // packed gradient layout [co][ntaps][cin_total]
+    int conv = -1;                  // index into spec.convs (for the per-stage unpack table)
     std::string name;
 };
 
@@ -223,17 +228,20 @@ inline std::string wg_build(Ctx* ctx, TrainPlan& plan, WgLaunch& L, const WgSpec
     P.zc_box = s.cout < 64 ? s.cout : 64;
     P.xc_box = s.nsrc_c < 64 ? s.nsrc_c : 64;
     P.grad = s.grad; P.s_co = s.s_co; P.s_ci = s.s_ci; P.stem_mode = s.stem_mode;
+    P.ntaps = s.ntaps; P.cin_total = s.cin_total;
     P.err = ctx->d_err;
     const int ncin_tile = s.nsrc_c < 256 ? s.nsrc_c : 256;
     L.max_ncin = ncin_tile;
     const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
     const int co_tiles = (s.cout + 127) / 128, ci_tiles = (s.nsrc_c + ncin_tile - 1) / ncin_tile;
     const int base_items = co_tiles * ci_tiles * (int)s.taps.size();
-    int splits = (3 * ctx->num_sms + base_items - 1) / base_items;
+    // split-K over pixel tiles: just enough items to fill the SMs once or twice (every split multiplies the reduction
+    // traffic into the gradient), at least 8 pixel tiles per item where possible
+    int splits = (ctx->num_sms + base_items - 1) / base_items;
+    if (base_items * splits < 2 * ctx->num_sms && total_tiles / (splits * 2) >= 32) splits *= 2;
     if (splits > total_tiles) splits = total_tiles;
     if (splits < 1) splits = 1;
-    // keep at least 4 pixel tiles per item where possible
-    while (splits > 1 && total_tiles / splits < 4) --splits;
+    while (splits > 1 && total_tiles / splits < 8) --splits;
     const size_t first = plan.host_items.size();
     for (int sp = 0; sp < splits; ++sp) {
         const int tb = (int)((long long)total_tiles * sp / splits), te = (int)((long long)total_tiles * (sp + 1) / splits);
@@ -346,7 +354,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const float* bt = params + b.beta;
         const int C = c.cout;
         add_f("bn_finalize:" + c.name, [=](cudaStream_t st) {
-            bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(segs, C, count, gm, bt, rm, rv, cnt, 0.1f, 1e-5f,
+            bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(segs, C, count, gm, bt, rm, rv, cnt, 0.1f, 1e-5f,
                                                                u.scale, u.shift, u.mean, u.invstd);
             return cudaGetLastError();
         });
@@ -543,7 +551,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             return cudaGetLastError();
         });
         add_b(stage, "bn_bwd_finalize:" + c.name, [=](cudaStream_t st) {
-            bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nblocks, C, (double)npix, gm, u.invstd, dgm,
+            bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nblocks, C, (double)npix, gm, u.invstd, dgm,
                                                                    dbt, u.coef);
             return cudaGetLastError();
         });
@@ -553,7 +561,10 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             return cudaGetLastError();
         });
     };
+    std::vector<int> stage_convs[4];
     auto add_wg = [&](int stage, const WgSpec& s) -> std::string {
+        if (s.conv >= 0 && std::find(stage_convs[stage].begin(), stage_convs[stage].end(), s.conv) == stage_convs[stage].end())
+            stage_convs[stage].push_back(s.conv);
         WgLaunch L;
         std::string e = wg_build(ctx, plan, L, s);
         if (!e.empty()) return e;
@@ -562,18 +573,32 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         add_b(stage, "wgrad:" + s.name, LaunchFn());  // placeholder, filled after the item arena is uploaded
         return "";
     };
+    // halo-resident wgrad (hwgrad.cuh) of a narrow 3x3/s1 conv over cat(nearest2x(low)[cup], src[cskip])
+    auto add_hwg = [&](int stage, int conv, const void* low, int cup, const void* src, int cskip, const void* dz, int Hh,
+                       int Ww) -> std::string {
+        const ConvRef& c = S.convs[conv];
+        if (std::find(stage_convs[stage].begin(), stage_convs[stage].end(), conv) == stage_convs[stage].end())
+            stage_convs[stage].push_back(conv);
+        HwgradLaunch HL;
+        std::string e = hwgrad_build(HL, low, cup, src, cskip, dz, c.cout, N, Hh, Ww, T.gpk + c.w, ctx->d_err, SM);
+        if (!e.empty()) return c.name + " wgrad: " + e;
+        add_b(stage, "wgrad:" + c.name, [HL](cudaStream_t st) { return hwgrad_launch(HL, st); });
+        return "";
+    };
     auto wg_conv3 = [&](int stage, int ui, const void* x_in, int x_C, int x_H, int x_W) -> std::string {
         // regular k x k conv weight gradient
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
+        if (c.k == 3 && c.stride == 1 && hwgrad_ok(0, c.cin, c.cout))
+            return add_hwg(stage, u.conv, nullptr, 0, x_in, c.cin, u.dz, u.Ho, u.Wo);
         WgSpec s;
         s.name = c.name;
         s.z = nhwc_view(u.dz, N, u.Ho, u.Wo, c.cout);
         s.x = nhwc_view(x_in, N, x_H, x_W, x_C);
         s.es_w = s.es_h = c.stride;
         s.cout = c.cout; s.nsrc_c = c.cin; s.x_c0 = 0; s.dci0 = 0;
-        s.grad = grads + c.w;
-        s.s_co = (long long)c.cin * c.k * c.k; s.s_ci = c.k * c.k;
+        s.grad = T.gpk + c.w;
+        s.ntaps = c.k * c.k; s.cin_total = c.cin; s.conv = u.conv;
         for (int r = 0; r < c.k; ++r)
             for (int q = 0; q < c.k; ++q) {
                 WgSpec::Tap t;
@@ -618,14 +643,19 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         if (!(err = dgrad3(0, r.u2, dA[r.u1], nullptr)).empty()) return err;
         bn_bwd(0, r.u1, dA[r.u1], true, nullptr);
         const int cin_total = d.cup + d.cskip;
+        const bool c1_hwg = hwgrad_ok(d.cup, d.cskip, d.cout);
+        if (c1_hwg) {
+            // one launch over cat(nearest2x(low), skip): gradient w.r.t. the original 3x3 weights
+            if (!(err = add_hwg(0, d.c1, r.low, d.cup, r.skip, d.cskip, u1.dz, u1.Ho, u1.Wo)).empty()) return err;
+        }
         // weight gradient, skip channels: regular 3x3 over the skip tensor
-        if (d.cskip) {
+        if (d.cskip && !c1_hwg) {
             WgSpec s;
             s.name = c1.name + "[skip]";
             s.z = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, d.cout);
             s.x = nhwc_view(r.skip, N, u1.Ho, u1.Wo, d.cskip);
             s.cout = d.cout; s.nsrc_c = d.cskip; s.dci0 = d.cup;
-            s.grad = grads + c1.w; s.s_co = (long long)cin_total * 9; s.s_ci = 9;
+            s.grad = T.gpk + c1.w; s.ntaps = 9; s.cin_total = cin_total; s.conv = d.c1;
             for (int k = 0; k < 9; ++k) {
                 WgSpec::Tap t;
                 t.dh = k / 3 - 1; t.dw = k % 3 - 1; t.ndst = 1; t.dst[0] = k; t.dst[1] = t.dst[2] = t.dst[3] = 0;
@@ -634,7 +664,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             if (!(err = add_wg(0, s)).empty()) return err;
         }
         // weight gradient, up-sampled channels: per output parity a 2x2 low-res neighbourhood, fanned out to 3x3
-        for (int par = 0; par < 4; ++par) {
+        for (int par = 0; par < (c1_hwg ? 0 : 4); ++par) {
             const int ph = par >> 1, pw = par & 1;
             WgSpec s;
             s.name = c1.name + "[up parity]";
@@ -643,7 +673,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             s.z.sW = 2ll * d.cout; s.z.sH = 2ll * u1.Wo * d.cout; s.z.sN = (long long)u1.Ho * u1.Wo * d.cout;
             s.x = nhwc_view(r.low, N, r.Hl, r.Wl, d.cup);
             s.cout = d.cout; s.nsrc_c = d.cup; s.dci0 = 0;
-            s.grad = grads + c1.w; s.s_co = (long long)cin_total * 9; s.s_ci = 9;
+            s.grad = T.gpk + c1.w; s.ntaps = 9; s.cin_total = cin_total; s.conv = d.c1;
             for (int a = 0; a < 2; ++a)
                 for (int b = 0; b < 2; ++b) {
                     WgSpec::Tap t;
@@ -813,6 +843,26 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         L.p.items = plan.items + reinterpret_cast<size_t>(L.p.items);
         plan.bwd[wg_pos[k].first][wg_pos[k].second] = [L](cudaStream_t st) { return wg_launch(L, st); };
     }
+    // ---- last launch of every stage: packed [co][tap][ci] gradients -> OIHW slots of the flat gradient array
+    for (int stage = 0; stage < 4; ++stage) {
+        if (stage_convs[stage].empty()) continue;
+        UnpackTable UT;
+        memset(&UT, 0, sizeof(UT));
+        int nblocks = 0;
+        for (int ci : stage_convs[stage]) {
+            if (UT.n >= 24) return "unpack table overflow";
+            const ConvRef& c = S.convs[ci];
+            UnpackEntry& e = UT.e[UT.n++];
+            e.src_off = c.w; e.dst_off = c.w;
+            e.cout = c.cout; e.cin = c.cin; e.ntaps = c.k * c.k; e.block_begin = nblocks;
+            nblocks += (int)(((long long)c.cout * c.cin * c.k * c.k + 2047) / 2048);
+        }
+        const float* gpk = T.gpk;
+        add_b(stage, "unpack_grads:stage" + std::to_string(stage), [=](cudaStream_t st) {
+            unpack_grads_kernel<<<nblocks, 256, 0, st>>>(UT, gpk, grads);
+            return cudaGetLastError();
+        });
+    }
     plan.n_fwd = (int)plan.fwd.size() + 2;
     plan.n_bwd = 3;
     for (auto& b : plan.bwd) plan.n_bwd += (int)b.size();
@@ -859,6 +909,7 @@ inline int ctx_train_prepare(Ctx* ctx, int N, const float* params, float* buffer
         train_layout_dgrad(ctx, T);
         UB_CUDA(cudaMalloc(&T.wdg, T.wdg_total * 2));
     }
+    if (!T.gpk) UB_CUDA(cudaMalloc(&T.gpk, (size_t)ctx->spec.n_params * sizeof(float)));
     size_t need = 0;
     {
         TrainPlan probe;
@@ -921,7 +972,10 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
         if (stage == 0) {
             if (!dlogits) return ctx_fail(ctx, "train_backward: dlogits is null");
             ctx->prof_mark("memset:grads", st);
-            UB_CUDA(cudaMemsetAsync(P.grads, 0, (size_t)S.n_params * sizeof(float), st));
+            // every gradient slot is overwritten by this backward: conv weights through the packed accumulator (cleared
+            // here) + unpack, BatchNorm / head by plain stores; only the stem reduces straight into its OIHW slot
+            UB_CUDA(cudaMemsetAsync(T.gpk, 0, (size_t)S.n_params * sizeof(float), st));
+            UB_CUDA(cudaMemsetAsync(P.grads + S.convs[S.stem].w, 0, (size_t)64 * 147 * sizeof(float), st));
             ctx->prof_mark("pack_dgrad:all", st);
             if (train_pack_dgrad(ctx, T, P.params, st)) return 1;
             ctx->prof_mark("head_bwd:segmentation_head", st);

@@ -30,20 +30,32 @@ struct StatSegs {
     int rows[4];
     int n;
 };
-__global__ void bn_finalize_kernel(StatSegs segs, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, long long* __restrict__ counter, float momentum,
-                                   float eps, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && counter) *counter += 1;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// one WARP per channel: lanes stride over the partial rows (blockDim = 256 -> 8 channels per block)
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(StatSegs segs, int C, double count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, long long* __restrict__ counter, float momentum,
+                   float eps, float* __restrict__ scale, float* __restrict__ shift,
+                   float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && counter) *counter += 1;
     if (c >= C) return;
     double s1 = 0, s2 = 0;
     for (int s = 0; s < segs.n; ++s)
-        for (int r = 0; r < segs.rows[s]; ++r) {
-            s1 += segs.ptr[s][((size_t)r * C + c) * 2];
-            s2 += segs.ptr[s][((size_t)r * C + c) * 2 + 1];
+        for (int r = lane; r < segs.rows[s]; r += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(segs.ptr[s] + ((size_t)r * C + c) * 2);
+            s1 += v.x;
+            s2 += v.y;
         }
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    if (lane) return;
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0) var = 0;
@@ -139,17 +151,23 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
 }
 
 // sums the per-block partials; writes dgamma / dbeta and the apply coefficients k1 = gamma*invstd, k2 = s1/n, k3 = s2/n
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per channel (blockDim = 256 -> 8 channels per block)
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
+                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double s1 = 0, s2 = 0;
-    for (int b = 0; b < nblocks; ++b) {
-        s1 += partial[((size_t)b * C + c) * 2];
-        s2 += partial[((size_t)b * C + c) * 2 + 1];
+    for (int b = lane; b < nblocks; b += 32) {
+        const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t)b * C + c) * 2);
+        s1 += v.x;
+        s2 += v.y;
     }
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    if (lane) return;
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
     coef[c * 3 + 0] = gamma[c] * invstd[c];
@@ -457,6 +475,34 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
             p[j] = pv; m[j] = mv; v[j] = vv2;
             if (zero_grad) g[j] = 0.f;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ packed gradient unpack
+// The wgrad kernels accumulate into a packed fp32 buffer [co][tap][ci] (ci contiguous -> vector reductions); this turns
+// it into the OIHW layout of the parameter / .grad tensors:  grad[co][ci][tap] = gpk[co][tap][ci].  One launch handles a
+// table of convs (a backward stage); block b belongs to the conv whose block range contains it.
+struct UnpackEntry {
+    long long src_off, dst_off;   // element offsets into the packed buffer / the flat gradient array
+    int cout, cin, ntaps, block_begin;
+};
+struct UnpackTable {
+    int n;
+    UnpackEntry e[24];
+};
+__global__ void __launch_bounds__(256)
+unpack_grads_kernel(UnpackTable T, const float* __restrict__ gpk, float* __restrict__ grads) {
+    int k = 0;
+    while (k + 1 < T.n && (int)blockIdx.x >= T.e[k + 1].block_begin) ++k;
+    const UnpackEntry E = T.e[k];
+    const long long total = (long long)E.cout * E.cin * E.ntaps;
+    const int per = E.cin * E.ntaps;
+    for (long long i = (long long)(blockIdx.x - E.block_begin) * 2048 + threadIdx.x, it = 0; it < 8 && i < total;
+         i += 256, ++it) {
+        const int co = int(i / per);
+        const int rem = int(i - (long long)co * per);
+        const int ci = rem / E.ntaps, tap = rem - ci * E.ntaps;
+        grads[E.dst_off + i] = gpk[E.src_off + ((long long)co * E.ntaps + tap) * E.cin + ci];
     }
 }
 

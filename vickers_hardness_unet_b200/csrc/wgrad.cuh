@@ -37,8 +37,9 @@ struct WgParams {
     int stages;
     int num_items;
     const WgItem* items;
-    float* grad;            // OIHW fp32
-    long long s_co, s_ci;   // element strides of the gradient tensor
+    float* grad;            // stem_mode: OIHW fp32 [64][3][7][7]; otherwise the PACKED gradient [co][tap][cin_total] fp32
+    long long s_co, s_ci;   // stem_mode: element strides of the OIHW tensor
+    int ntaps, cin_total;   // packed layout extents (ci contiguous: 16 consecutive columns = 64 B = 4 vector reductions)
     int stem_mode;          // 1: column j of the 32-wide stem window maps to (px=j/4, ch=j%4) -> ch*49 + r*7 + px-1
     int* err;
 };
@@ -192,7 +193,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
             tc_fence_after();
             const int co = I.co0 + row;
             const bool valid = co < P.cout;
-            float* grow = P.grad + (long long)co * P.s_co;
+            float* grow = P.stem_mode ? P.grad + (long long)co * P.s_co
+                                      : P.grad + (long long)co * P.ntaps * P.cin_total + I.dci0;
             for (int c0 = 0; c0 < I.ncin; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + acc * max_ncin + c0, r);
@@ -203,16 +205,20 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
                 if (!valid) continue;
+                if (P.stem_mode) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float v = __uint_as_float(r[j]);
-                    const int col = c0 + j;
-                    if (P.stem_mode) {
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = c0 + j;
                         const int px = col >> 2, ch = col & 3;
-                        if (px >= 1 && ch < 3) atomicAdd(grow + ch * 49 + I.dst_off[0] + (px - 1), v);
-                    } else {
-                        float* gp = grow + (long long)(I.dci0 + col) * P.s_ci;
-                        for (int d = 0; d < I.ndst; ++d) atomicAdd(gp + I.dst_off[d], v);
+                        if (px >= 1 && ch < 3) atomicAdd(grow + ch * 49 + I.dst_off[0] + (px - 1), __uint_as_float(r[j]));
+                    }
+                } else {
+                    for (int d = 0; d < I.ndst; ++d) {
+                        float* gp = grow + (long long)I.dst_off[d] * P.cin_total + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            red_add_v4(gp + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                       __uint_as_float(r[j + 3]));
                     }
                 }
             }

@@ -52,6 +52,10 @@ int unetb200_num_counters(void);       /* 46 int64 num_batches_tracked */
 /* replaces: model.load_state_dict(sd) (infer_pth_gui.py:42) / the implicit use of current parameters by forward.
  * Re-packs the fp32 master tensors into the bf16 K-major operand caches and folds eval-mode BatchNorm. */
 int unetb200_load_weights(unetb200_ctx* ctx, const float* params_dev, const float* buffers_dev, void* stream);
+/* same; skip_bn_fold != 0 leaves the folded eval-mode BatchNorm constants untouched (a training step uses batch
+ * statistics, so the fold is only needed again before the next eval-mode forward). */
+int unetb200_load_weights_ex(unetb200_ctx* ctx, const float* params_dev, const float* buffers_dev, int skip_bn_fold,
+                             void* stream);
 
 /* ---- inference: model.eval(); torch.sigmoid(model(x)) >= t  (infer_pth_gui.py:50-52) ---------------------------- */
 /* x_dev: fp32 NCHW [N,3,H,W].  Any of logits/prob/mask may be NULL (at least one must not be):

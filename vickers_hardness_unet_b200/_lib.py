@@ -31,6 +31,7 @@ def _proto(lib):
         "unetb200_num_buffers": (i64, []),
         "unetb200_num_counters": (i32, []),
         "unetb200_load_weights": (i32, [vp, vp, vp, vp]),
+        "unetb200_load_weights_ex": (i32, [vp, vp, vp, i32, vp]),
         "unetb200_forward_infer": (i32, [vp, vp, vp, vp, vp, f32, i32, vp]),
         "unetb200_infer_host": (i32, [vp, vp, vp, vp, vp, f32, i32]),
         "unetb200_infer_launch_count": (i32, [vp, i32]),

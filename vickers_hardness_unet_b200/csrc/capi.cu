@@ -72,10 +72,15 @@ long long unetb200_num_buffers(void) { return spec().n_buffers; }
 int unetb200_num_counters(void) { return spec().n_counters; }
 
 int unetb200_load_weights(unetb200_ctx* h, const float* params_dev, const float* buffers_dev, void* stream) {
+    return unetb200_load_weights_ex(h, params_dev, buffers_dev, 0, stream);
+}
+
+int unetb200_load_weights_ex(unetb200_ctx* h, const float* params_dev, const float* buffers_dev, int skip_bn_fold,
+                             void* stream) {
     Ctx* ctx = h->c;
     if (!params_dev || !buffers_dev) return ctx_fail(ctx, "load_weights: null pointer");
     UB_CUDA(cudaSetDevice(ctx->device));
-    return ctx_load_weights(ctx, params_dev, buffers_dev, (cudaStream_t)stream);
+    return ctx_load_weights(ctx, params_dev, buffers_dev, (cudaStream_t)stream, !skip_bn_fold);
 }
 
 int unetb200_forward_infer(unetb200_ctx* h, const float* x_dev, float* logits_dev, float* prob_dev, uint8_t* mask_dev,

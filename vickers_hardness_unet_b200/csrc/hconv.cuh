@@ -63,8 +63,8 @@ struct HconvSmem {
 __host__ __device__ inline HconvSmem hconv_smem(int ctot, int cout, int stages) {
     HconvSmem s;
     s.ss_off = 0;                               // scale[64], shift[64]
-    s.cstat_off = s.ss_off + 2 * 64 * 4;        // per-CTA running statistics [64][2]
-    s.w_off = 1024;                              // swizzle patterns are functions of the smem address: 1 KB alignment
+    s.cstat_off = s.ss_off + 2 * 64 * 4;        // per-CTA running statistics [4 epilogue warps][64][2]
+    s.w_off = 4096;                              // swizzle patterns are functions of the smem address: 1 KB alignment
     s.w_bytes = 9u * ctot * cout * 2;
     s.halo_off = (s.w_off + s.w_bytes + 1023u) & ~1023u;
     s.halo_bytes = hc_nblk(ctot) * hc_blk_bytes(ctot);
@@ -195,9 +195,8 @@ hconv_kernel(const __grid_constant__ HconvParams P) {
         for (int c = threadIdx.x; c < 64; c += blockDim.x) {
             ss[c] = (P.scale && c < P.cout) ? P.scale[c] : 1.f;
             ss[64 + c] = (P.shift && c < P.cout) ? P.shift[c] : 0.f;
-            cst[2 * c] = 0.f;
-            cst[2 * c + 1] = 0.f;
         }
+        for (int c = threadIdx.x; c < 4 * 128; c += blockDim.x) cst[c] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -408,8 +407,10 @@ hconv_kernel(const __grid_constant__ HconvParams P) {
                     }
                     const float t1 = warp_reduce16(s1, lane), t2 = warp_reduce16(s2, lane);
                     if (lane < 16) {
-                        atomicAdd(&cst[2 * (c0 + lane)], t1);
-                        atomicAdd(&cst[2 * (c0 + lane) + 1], t2);
+                        // channel c0+lane of warp q's private slot is only ever touched by this lane: plain adds in a fixed
+                        // order, i.e. the batch statistics (and with them the whole forward) are run-to-run deterministic
+                        cst[q * 128 + 2 * (c0 + lane)] += t1;
+                        cst[q * 128 + 2 * (c0 + lane) + 1] += t2;
                     }
                 }
             }
@@ -422,7 +423,7 @@ hconv_kernel(const __grid_constant__ HconvParams P) {
         if (P.stats) {
             named_bar_sync(1, 128);
             float* dst = P.stats + static_cast<size_t>(blockIdx.x) * P.cout * 2;
-            for (int j = et; j < 2 * P.cout; j += 128) dst[j] = cst[j];
+            for (int j = et; j < 2 * P.cout; j += 128) dst[j] = (cst[j] + cst[128 + j]) + (cst[256 + j] + cst[384 + j]);
         }
         if (prof && et == 0) {
             P.prof[blockIdx.x * 16 + 8] = t_wait;

@@ -1,0 +1,152 @@
+// Table-driven weight re-pack: ONE launch converts every fp32 OIHW master tensor of a table into its bf16 operand layout
+// (instead of ~50 small launches per optimizer step).  An entry describes one destination matrix; the element functions
+// are the same layouts as the stand-alone kernels in ops.cuh / train_ops.cuh (which remain for the unit-test entry points).
+#pragma once
+#include <vector>
+
+#include "ops.cuh"
+
+namespace ub {
+
+enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5 };
+
+struct PackEntry {
+    int type;
+    int cout, cin;            // PK_CONV: OIHW dims; PK_DEC1/PK_DLOW: cout, cup; PK_HCONV: rows (cout_), ctot; PK_TAPS: cout, cin
+    int a, b, c, d;           // type-specific (see pack_elem)
+    int ntaps;                // PK_TAPS
+    unsigned long long taps;  // PK_TAPS: 4 bits per tap = (r << 2) | s
+    long long src_off;        // element offset into the flat fp32 parameter array
+    long long dst_off;        // element offset into the bf16 destination arena
+    long long total;          // logical elements of this entry
+    int block_begin;          // first block (2048 elements per block) of this entry in the launch
+    int pad;
+};
+
+// value of logical element i of entry E and the destination index (relative to E.dst_off) it is stored at
+__device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __restrict__ w, long long i, long long& dst) {
+    dst = i;
+    switch (E.type) {
+        case PK_CONV: {  // a = R, b = S, c = flip: [co][(r*S+s)*cin + ci]   (flip: [ci][((R-1-r)*S + (S-1-s))*cout + co])
+            const int R = E.a, S = E.b;
+            if (!E.c) {
+                const int ci = int(i % E.cin);
+                const long long t = i / E.cin;
+                const int rs = int(t % (R * S)), co = int(t / (R * S));
+                return w[((long long)co * E.cin + ci) * R * S + rs];
+            }
+            const int co = int(i % E.cout);
+            const long long t = i / E.cout;
+            const int rs = int(t % (R * S)), ci = int(t / (R * S));
+            const int r = R - 1 - rs / S, s = S - 1 - rs % S;
+            return w[(((long long)co * E.cin + ci) * R + r) * S + s];
+        }
+        case PK_STEM: {  // [64][r*32 + px*4 + ch], px 0..7 <-> kernel column px-1 (px 0 and ch 3 are zero)
+            const int ch = int(i % 4), px = int((i / 4) % 8), r = int((i / 32) % 7), co = int(i / 224);
+            return (ch < 3 && px >= 1) ? w[((co * 3 + ch) * 7 + r) * 7 + (px - 1)] : 0.f;
+        }
+        case PK_DEC1: {  // cin = cup, a = cskip: out[parity][cout][9*cskip + 4*cup] (parity-folded 2x2 taps on the low-res x)
+            const int cup = E.cin, cskip = E.a, kt = 9 * cskip + 4 * cup, cint = cup + cskip;
+            const int k = int(i % kt), co = int((i / kt) % E.cout), par = int(i / ((long long)kt * E.cout));
+            const int ph = par >> 1, pw = par & 1;
+            if (k < 9 * cskip) {
+                const int c = k % cskip, rs = k / cskip;
+                return w[((long long)co * cint + cup + c) * 9 + rs];
+            }
+            const int kk = k - 9 * cskip, c = kk % cup, ab = kk / cup, aa = ab >> 1, bb = ab & 1;
+            const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
+            const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
+            float v = 0.f;
+            for (int r = r0; r <= r1; ++r)
+                for (int s = s0; s <= s1; ++s) v += w[((long long)co * cint + c) * 9 + r * 3 + s];
+            return v;
+        }
+        case PK_DLOW: {  // cin = cup, a = cin_total: out[c][t*cout + co], t = ((ph*2 + a)*2 + pw)*2 + b
+            const int co = int(i % E.cout), t = int((i / E.cout) % 16), c = int(i / ((long long)E.cout * 16));
+            const int bb = t & 1, pw = (t >> 1) & 1, aa = (t >> 2) & 1, ph = (t >> 3) & 1;
+            const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
+            const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
+            float v = 0.f;
+            for (int r = r0; r <= r1; ++r)
+                for (int s = s0; s <= s1; ++s) v += w[((long long)co * E.a + c) * 9 + r * 3 + s];
+            return v;
+        }
+        case PK_TAPS: {  // a = cin_total, b = ci0, c = (R << 8) | S, d = (ld << 0); pad = col0:  out[ci][col0 + t*cout + co]
+            const int co = int(i % E.cout), t = int((i / E.cout) % E.ntaps), ci = int(i / ((long long)E.cout * E.ntaps));
+            const int R = E.c >> 8, S = E.c & 0xFF;
+            const int rs = int((E.taps >> (4 * t)) & 0xF), r = rs >> 2, s = rs & 3;
+            dst = (long long)ci * E.d + E.pad + t * E.cout + co;
+            return w[(((long long)co * E.a + E.b + ci) * R + r) * S + s];
+        }
+        default: {  // PK_HCONV: cout = rows, cin = ctot, a = dim1_total, b = ci0, c = transposed (see pack_hconv_w_kernel)
+            const int ctot = E.cin, cpr = ctot < 64 ? ctot : 64, nblk = ctot > 64 ? ctot / 64 : 1;
+            const unsigned row_bytes = cpr * 2;
+            const int cc = int(i % cpr);
+            long long t = i / cpr;
+            const int co = int(t % E.cout);
+            t /= E.cout;
+            const int blk = int(t % nblk), tap = int(t / nblk);
+            const int c = blk * 64 + cc, r = tap / 3, s = tap - 3 * r;
+            const unsigned off = (unsigned)(i * 2);
+            dst = (off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4)) / 2;
+            if (!E.c) return w[(((long long)co * E.a + E.b + c) * 3 + r) * 3 + s];
+            return w[(((long long)c * E.a + E.b + co) * 3 + (2 - r)) * 3 + (2 - s)];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pack_table_kernel(const PackEntry* __restrict__ tab, int n, const float* __restrict__ params,
+                  __nv_bfloat16* __restrict__ dst_base) {
+    int lo = 0, hi = n - 1;  // last entry whose block_begin <= blockIdx.x
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tab[mid].block_begin <= (int)blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    const PackEntry E = tab[lo];
+    const float* w = params + E.src_off;
+    __nv_bfloat16* out = dst_base + E.dst_off;
+    long long i = (long long)(blockIdx.x - E.block_begin) * 2048 + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 8; ++it, i += 256) {
+        if (i >= E.total) break;
+        long long d;
+        const float v = pack_elem(E, w, i, d);
+        out[d] = __float2bfloat16(v);
+    }
+}
+
+// host side: a table under construction, uploaded once (the layouts only depend on the network description)
+struct PackTable {
+    std::vector<PackEntry> host;
+    PackEntry* dev = nullptr;
+    int nblocks = 0;
+    void add(PackEntry e) {
+        e.block_begin = nblocks;
+        nblocks += (int)((e.total + 2047) / 2048);
+        host.push_back(e);
+    }
+    cudaError_t upload() {
+        cudaFree(dev);
+        dev = nullptr;
+        cudaError_t e = cudaMalloc(&dev, host.size() * sizeof(PackEntry));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(dev, host.data(), host.size() * sizeof(PackEntry), cudaMemcpyHostToDevice);
+    }
+    cudaError_t launch(const float* params, __nv_bfloat16* dst_base, cudaStream_t st) const {
+        if (!nblocks) return cudaSuccess;
+        pack_table_kernel<<<nblocks, 256, 0, st>>>(dev, (int)host.size(), params, dst_base);
+        return cudaGetLastError();
+    }
+    ~PackTable() { cudaFree(dev); }
+};
+
+inline PackEntry pk_entry(int type, long long src_off, long long dst_off, long long total) {
+    PackEntry e;
+    memset(&e, 0, sizeof(e));
+    e.type = type; e.src_off = src_off; e.dst_off = dst_off; e.total = total;
+    return e;
+}
+
+}  // namespace ub

@@ -79,6 +79,7 @@ struct TrainState {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     int arena_batch = 0;
+    PackTable dg_pack;              // all dgrad operand layouts (one launch per step)
     float* gpk = nullptr;           // packed fp32 weight gradients [co][tap][ci] (conv c at element offset convs[c].w)
     __nv_bfloat16* wdg = nullptr;   // packed dgrad operands
     long long wdg_total = 0;
@@ -142,9 +143,19 @@ inline void train_layout_dgrad(Ctx* ctx, TrainState& T) {
     T.wdg_total = off;
 }
 
-inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaStream_t st) {
+// Table of every data-gradient operand (built once: the layouts only depend on the network description); the re-pack
+// after an optimizer step is then a single launch of pack_table_kernel.
+inline std::string train_build_dgrad_table(Ctx* ctx, TrainState& T) {
     const NetSpec& S = ctx->spec;
-    auto grid = [&](long long n) { return ew_grid(n, 256, ctx->num_sms); };
+    PackTable& PT = T.dg_pack;
+    auto taps_entry = [&](long long src, long long dst, int cout, int cin_total, int ci0, int cin, int R, int Sx, int ld,
+                          int col0, const TapList& tl) {
+        PackEntry e = pk_entry(PK_TAPS, src, dst, (long long)cin * tl.n * cout);
+        e.cout = cout; e.cin = cin; e.a = cin_total; e.b = ci0; e.c = (R << 8) | Sx; e.d = ld; e.pad = col0;
+        e.ntaps = tl.n;
+        for (int t = 0; t < tl.n; ++t) e.taps |= (unsigned long long)((tl.r[t] << 2) | tl.s[t]) << (4 * t);
+        PT.add(e);
+    };
     for (size_t i = 0; i < S.convs.size(); ++i) {
         if (T.wdg_off[i] < 0 && T.wdg_off2[i] < 0) continue;
         const ConvRef& c = S.convs[i];
@@ -153,20 +164,20 @@ inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaSt
         if (dd) {
             const int cin_total = dd->cup + dd->cskip;
             if (dd->cskip && hconv_stages(0, dd->cout, dd->cskip)) {
-                pack_hconv_w_kernel<<<grid(9ll * dd->cskip * dd->cout), 256, 0, st>>>(
-                    params + c.w, T.wdg + T.wdg_off[i], dd->cskip, dd->cout, cin_total, dd->cup, 1);
+                PackEntry e = pk_entry(PK_HCONV, c.w, T.wdg_off[i], 9ll * dd->cskip * dd->cout);
+                e.cout = dd->cskip; e.cin = dd->cout; e.a = cin_total; e.b = dd->cup; e.c = 1;
+                PT.add(e);
             } else if (dd->cskip) {
                 TapList tl;
                 tl.n = 9;
                 for (int t = 0; t < 9; ++t) { tl.r[t] = 2 - t / 3; tl.s[t] = 2 - t % 3; }
-                pack_dgrad_w_kernel<<<grid((long long)dd->cskip * 9 * dd->cout), 256, 0, st>>>(
-                    params + c.w, T.wdg + T.wdg_off[i], dd->cout, cin_total, dd->cup, dd->cskip, 3, 3, 9 * dd->cout, 0, tl);
+                taps_entry(c.w, T.wdg_off[i], dd->cout, cin_total, dd->cup, dd->cskip, 3, 3, 9 * dd->cout, 0, tl);
             }
-            pack_dec1_dlow_w_kernel<<<grid((long long)dd->cup * 16 * dd->cout), 256, 0, st>>>(
-                params + c.w, T.wdg + T.wdg_off2[i], dd->cout, dd->cup, cin_total);
+            PackEntry e = pk_entry(PK_DLOW, c.w, T.wdg_off2[i], (long long)dd->cup * 16 * dd->cout);
+            e.cout = dd->cout; e.cin = dd->cup; e.a = cin_total;
+            PT.add(e);
         } else if (c.stride == 2) {
-            // find the block's downsample conv
-            int ds = -1;
+            int ds = -1;  // the block's downsample conv: its single tap rides along in the parity-0 matrix
             for (int l = 0; l < 4; ++l)
                 for (auto& b : S.enc_blocks[l]) if (b.c1 == (int)i) ds = b.ds;
             long long o = T.wdg_off[i];
@@ -175,25 +186,29 @@ inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaSt
                 int dh[4], dw[4];
                 s2_parity_taps(par, tl, dh, dw);
                 const int ncols = (tl.n + (par == 0 ? 1 : 0)) * c.cout;
-                pack_dgrad_w_kernel<<<grid((long long)c.cin * tl.n * c.cout), 256, 0, st>>>(
-                    params + c.w, T.wdg + o, c.cout, c.cin, 0, c.cin, 3, 3, ncols, 0, tl);
+                taps_entry(c.w, o, c.cout, c.cin, 0, c.cin, 3, 3, ncols, 0, tl);
                 if (par == 0) {
                     TapList t1;
                     t1.n = 1; t1.r[0] = 0; t1.s[0] = 0;
-                    pack_dgrad_w_kernel<<<grid((long long)c.cin * c.cout), 256, 0, st>>>(
-                        params + S.convs[ds].w, T.wdg + o, c.cout, c.cin, 0, c.cin, 1, 1, ncols, tl.n * c.cout, t1);
+                    taps_entry(S.convs[ds].w, o, c.cout, c.cin, 0, c.cin, 1, 1, ncols, tl.n * c.cout, t1);
                 }
                 o += (long long)c.cin * ncols;
             }
         } else if (hconv_stages(0, c.cout, c.cin)) {
-            pack_hconv_w_kernel<<<grid(9ll * c.cin * c.cout), 256, 0, st>>>(params + c.w, T.wdg + T.wdg_off[i], c.cin, c.cout,
-                                                                           c.cin, 0, 1);
+            PackEntry e = pk_entry(PK_HCONV, c.w, T.wdg_off[i], 9ll * c.cin * c.cout);
+            e.cout = c.cin; e.cin = c.cout; e.a = c.cin; e.b = 0; e.c = 1;
+            PT.add(e);
         } else {
-            pack_conv_w_kernel<<<grid((long long)c.cin * 9 * c.cout), 256, 0, st>>>(params + c.w, T.wdg + T.wdg_off[i],
-                                                                                   c.cout, c.cin, 3, 3, 1);
+            PackEntry e = pk_entry(PK_CONV, c.w, T.wdg_off[i], (long long)c.cin * 9 * c.cout);
+            e.cout = c.cout; e.cin = c.cin; e.a = 3; e.b = 3; e.c = 1;
+            PT.add(e);
         }
     }
-    UB_CUDA(cudaGetLastError());
+    return PT.upload() == cudaSuccess ? "" : "dgrad pack table upload failed";
+}
+
+inline int train_pack_dgrad(Ctx* ctx, TrainState& T, const float* params, cudaStream_t st) {
+    UB_CUDA(T.dg_pack.launch(params, T.wdg, st));
     return 0;
 }
 
@@ -407,11 +422,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     int h = H / 4, w = W / 4;
     __nv_bfloat16* p1 = A.take((long long)N * h * w * 64);
     __nv_bfloat16* d_p1 = A.take((long long)N * h * w * 64);
+    uint8_t* pool_idx = reinterpret_cast<uint8_t*>(A.take((long long)N * h * w * 64 / 2));  // 1 byte per pooled element
     if (!dry) {
         const int Hh = H / 2, Wh = W / 2;
         add_f("maxpool:encoder.maxpool", [=](cudaStream_t st) {
-            maxpool3x3s2_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, SM), 256, 0, st>>>(f1, p1, N, Hh,
-                                                                                                        Wh, 64);
+            maxpool3x3s2_idx_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, SM), 256, 0, st>>>(
+                f1, p1, pool_idx, N, Hh, Wh, 64);
             return cudaGetLastError();
         });
     }
@@ -539,15 +555,19 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const int C = c.cout;
         const int ppb = 256 / (C / 8);
         long long nb = (npix + ppb - 1) / ppb;
-        if (nb > 2 * SM) nb = 2 * SM;
+        if (nb > 6 * SM) nb = 6 * SM;
         const int nblocks = (int)nb;
         float* part = plan.red_part;
-        const __nv_bfloat16* mask = relu_mask ? u.a : nullptr;
+        // ReLU mask: units with a residual input (g_out != nullptr) read the stored activation; the others recompute
+        // it from z with the forward's scale / shift; no ReLU (downsample BN) -> no mask
+        const __nv_bfloat16* mask = (relu_mask && g_out) ? u.a : nullptr;
+        const float* msc = (relu_mask && !g_out) ? u.scale : nullptr;
+        const float* msh = (relu_mask && !g_out) ? u.shift : nullptr;
         const float* gm = params + b.gamma;
         float* dgm = grads + b.gamma;
         float* dbt = grads + b.beta;
         add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
-            bn_bwd_reduce_kernel<<<nblocks, 256, 0, st>>>(dA_in, mask, u.z, u.mean, u.invstd, part, npix, C);
+            bn_bwd_reduce_kernel<<<nblocks, 256, 0, st>>>(dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
             return cudaGetLastError();
         });
         add_b(stage, "bn_bwd_finalize:" + c.name, [=](cudaStream_t st) {
@@ -556,8 +576,8 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             return cudaGetLastError();
         });
         add_b(stage, "bn_bwd_apply:" + c.name, [=](cudaStream_t st) {
-            bn_bwd_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(dA_in, mask, u.z, u.mean, u.invstd,
-                                                                                 u.coef, u.dz, g_out, npix, C);
+            bn_bwd_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(dA_in, mask, msc, msh, u.z, u.mean,
+                                                                                 u.invstd, u.coef, u.dz, g_out, npix, C);
             return cudaGetLastError();
         });
     };
@@ -809,8 +829,8 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const __nv_bfloat16* dsk = d_skips[3];
         __nv_bfloat16* dF1 = dA[u_stem];
         add_b(3, "maxpool_bwd:encoder.maxpool", [=](cudaStream_t st) {
-            maxpool_bwd_kernel<<<ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st>>>(d_p1, f1, dsk, dF1, N, Hh, Wh,
-                                                                                            64);
+            maxpool_bwd_kernel<<<ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st>>>(d_p1, pool_idx, dsk, dF1, N, Hh,
+                                                                                            Wh, 64);
             return cudaGetLastError();
         });
         bn_bwd(3, u_stem, dF1, true, nullptr);
@@ -908,6 +928,8 @@ inline int ctx_train_prepare(Ctx* ctx, int N, const float* params, float* buffer
     if (!T.wdg) {
         train_layout_dgrad(ctx, T);
         UB_CUDA(cudaMalloc(&T.wdg, T.wdg_total * 2));
+        std::string pe = train_build_dgrad_table(ctx, T);
+        if (!pe.empty()) return ctx_fail(ctx, pe);
     }
     if (!T.gpk) UB_CUDA(cudaMalloc(&T.gpk, (size_t)ctx->spec.n_params * sizeof(float)));
     size_t need = 0;
@@ -982,9 +1004,9 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
             head_bwd_data_kernel<<<ew_grid(npx, 256, SM), 256, 0, st>>>(dlogits, ctx->head_w, P.d_head_in, N, H, W);
-            const int nb = 2 * SM;
-            head_bwd_weight_kernel<<<nb, 256, 0, st>>>(P.head_in, dlogits, P.red_part, N, H, W);
-            sum_rows_kernel<<<2, 128, 0, st>>>(P.red_part, nb, 145, P.grads + hc.w);
+            const int nb = 8 * SM;
+            head_bwd_weight_kernel<<<nb, 288, 0, st>>>(P.head_in, dlogits, P.red_part, N, H, W);
+            sum_rows_kernel<<<(145 + 7) / 8, 256, 0, st>>>(P.red_part, nb, 145, P.grads + hc.w);
             UB_CUDA(cudaGetLastError());
         }
         for (size_t i = 0; i < P.bwd[stage].size(); ++i) {

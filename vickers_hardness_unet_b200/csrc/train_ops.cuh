@@ -10,6 +10,11 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
     f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
@@ -30,11 +35,6 @@ struct StatSegs {
     int rows[4];
     int n;
 };
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 // one WARP per channel: lanes stride over the partial rows (blockDim = 256 -> 8 channels per block)
 __global__ void __launch_bounds__(256)
 bn_finalize_kernel(StatSegs segs, int C, double count, const float* __restrict__ gamma,
@@ -72,22 +72,30 @@ bn_finalize_kernel(StatSegs segs, int C, double count, const float* __restrict__
     }
 }
 
-// a = [relu]( z*scale + shift [+ residual] ), 8 channels per thread
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
-                                __nv_bfloat16* __restrict__ out, long long npix, int C) {
+// a = [relu]( z*scale + shift [+ residual] ), 8 channels per thread.  blockDim * gridDim is a multiple of C/8, so a
+// thread's channel group never changes inside the grid-stride loop: its 16 constants are loaded once.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
+                __nv_bfloat16* __restrict__ out, long long npix, int C) {
     const int C8 = C / 8;
     const long long total = npix * C8;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = int(i % C8) * 8;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c0 = int(i0 % C8) * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        sc[k] = __ldg(scale + c0 + k);
+        sh[k] = __ldg(shift + c0 + k);
+    }
+    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
         float v[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), v);
         float r[8];
         if (residual) unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            float y = v[k] * __ldg(scale + c0 + k) + __ldg(shift + c0 + k);
+            float y = v[k] * sc[k] + sh[k];
             if (residual) y += r[k];
             if (relu) y = fmaxf(y, 0.f);
             v[k] = y;
@@ -98,9 +106,12 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float
 
 // ------------------------------------------------------------------------------------------------ BN backward
 // g = dA * [a > 0] ; partial sums per block of (sum g, sum g*zhat), zhat = (z - mean) * invstd.
+// The ReLU mask comes from the stored activation `a_mask` (units with a residual input) or, when a_mask == nullptr and
+// scale != nullptr, is recomputed from z (a = relu(z*scale + shift) > 0  <=>  z*scale + shift > 0): one tensor less to read.
 // blockDim = 256; thread t owns channel group t % C8 for the pixels t / C8 + k * (256 / C8).
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
                      const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                      const float* __restrict__ invstd, float* __restrict__ partial, long long npix, int C) {
     __shared__ float red[256 * 16];
@@ -108,12 +119,14 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
     const int cg = threadIdx.x % C8;
     const int lane_p = threadIdx.x / C8;
     const int ppb = 256 / C8;  // pixels per block iteration
-    float s1[8], s2[8], mu[8], is[8];
+    float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         s1[k] = s2[k] = 0.f;
         mu[k] = mean[cg * 8 + k];
         is[k] = invstd[cg * 8 + k];
+        sc[k] = scale ? scale[cg * 8 + k] : 0.f;
+        sh[k] = scale ? shift[cg * 8 + k] : 1.f;   // no mask: 0*z + 1 > 0 always
     }
     if (lane_p < ppb) {
         for (long long p = (long long)blockIdx.x * ppb + lane_p; p < npix; p += (long long)gridDim.x * ppb) {
@@ -126,6 +139,9 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
                 unpack8(__ldg(reinterpret_cast<const uint4*>(a_mask) + idx), m);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -175,17 +191,31 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, do
     coef[c * 3 + 2] = (float)(s2 / count);
 }
 
-// dz = k1 * (g - k2 - zhat*k3);  optionally also writes g (the masked gradient, for the residual identity path)
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
-                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, const float* __restrict__ coef,
-                                    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long npix,
-                                    int C) {
+// dz = k1 * (g - k2 - zhat*k3);  optionally also writes g (the masked gradient, for the residual identity path).
+// Mask as in bn_bwd_reduce_kernel; per-thread channel constants are loop invariant (see bn_apply_kernel).
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ coef,
+                    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long npix, int C) {
     const int C8 = C / 8;
     const long long total = npix * C8;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = int(i % C8) * 8;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int c0 = int(i0 % C8) * 8;
+    float mu[8], is[8], k1[8], k2[8], k3[8], sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        mu[k] = __ldg(mean + c);
+        is[k] = __ldg(invstd + c);
+        k1[k] = __ldg(coef + c * 3);
+        k2[k] = __ldg(coef + c * 3 + 1);
+        k3[k] = __ldg(coef + c * 3 + 2);
+        sc[k] = scale ? __ldg(scale + c) : 0.f;
+        sh[k] = scale ? __ldg(shift + c) : 1.f;
+    }
+    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
         float g[8], zz[8], o[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(dA) + i), g);
         unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
@@ -194,23 +224,70 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const 
             unpack8(__ldg(reinterpret_cast<const uint4*>(a_mask) + i), m);
 #pragma unroll
             for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int c = c0 + k;
-            const float zh = (zz[k] - __ldg(mean + c)) * __ldg(invstd + c);
-            o[k] = __ldg(coef + c * 3) * (g[k] - __ldg(coef + c * 3 + 1) - zh * __ldg(coef + c * 3 + 2));
+            const float zh = (zz[k] - mu[k]) * is[k];
+            o[k] = k1[k] * (g[k] - k2[k] - zh * k3[k]);
         }
         reinterpret_cast<uint4*>(dz)[i] = pack8(o);
         if (g_out) reinterpret_cast<uint4*>(g_out)[i] = pack8(g);
     }
 }
 
-// ------------------------------------------------------------------------------------------------ max-pool backward
-// dF[n,h,w,c] = sum over the (<=4) 3x3/s2 windows containing (h,w) whose FIRST maximum (scan order r, s — the
-// element PyTorch's max_pool2d backward picks) is this element, of dP[window]  (+ dSkip, the decoder's gradient
-// into the same feature map).
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const __nv_bfloat16* __restrict__ F,
+// ------------------------------------------------------------------------------------------------ max-pool (train)
+// Forward that also records, per output element, WHICH of the 9 window positions (r*3+s, first maximum in scan order —
+// the element PyTorch's max_pool2d backward picks) won; the backward is then a pure gather.
+__global__ void maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                        uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    const long long total = (long long)N * Ho * Wo * C8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = int(i % C8);
+        long long t = i / C8;
+        const int wo = int(t % Wo);
+        t /= Wo;
+        const int ho = int(t % Ho);
+        const int n = int(t / Ho);
+        float best[8];
+        uint32_t bi[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            best[k] = -INFINITY;
+            bi[k] = 0;
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int h = ho * 2 - 1 + r;
+            if (h < 0 || h >= H) continue;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const int w = wo * 2 - 1 + s;
+                if (w < 0 || w >= W) continue;
+                float v[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(in + (((long long)n * H + h) * W + w) * C) + c8), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (v[k] > best[k]) {
+                        best[k] = v[k];
+                        bi[k] = r * 3 + s;
+                    }
+            }
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8(best);
+        uint2 o;
+        o.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        o.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        reinterpret_cast<uint2*>(idx)[i] = o;
+    }
+}
+
+// dF[n,h,w,c] = dSkip[n,h,w,c] + sum over the (<= 4) windows containing (h,w) whose recorded winner is (h,w) of dP[window]
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
                                    int H, int W, int C) {
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
@@ -223,52 +300,33 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const _
         t /= W;
         const int h = int(t % H);
         const int n = int(t / H);
-        float me[8], acc[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(F) + i), me);
+        float acc[8];
         if (dSkip) unpack8(__ldg(reinterpret_cast<const uint4*>(dSkip) + i), acc);
         else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = 0.f;
         }
         // windows (ho,wo) with 2*ho-1 <= h <= 2*ho+1
-        for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {
-            if (ho < 0 || ho >= Ho) continue;
-            for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
-                if (wo < 0 || wo >= Wo) continue;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ho = h / 2 + a;
+            if (ho >= Ho || 2 * ho - 1 > h) continue;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int wo = w / 2 + b;
+                if (wo >= Wo || 2 * wo - 1 > w) continue;
+                const uint32_t pos = (h - (2 * ho - 1)) * 3 + (w - (2 * wo - 1));
+                const long long o = (((long long)n * Ho + ho) * Wo + wo) * C8 + c8;
+                const uint2 id = __ldg(reinterpret_cast<const uint2*>(idx) + o);
                 float d[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(dP + (((long long)n * Ho + ho) * Wo + wo) * C) + c8), d);
-                // is (h,w) the first maximum of this window?
-                bool first[8];
-                float best[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(dP) + o), d);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    best[k] = -INFINITY;
-                    first[k] = false;
+                for (int k = 0; k < 4; ++k) {
+                    if (((id.x >> (8 * k)) & 0xFF) == pos) acc[k] += d[k];
+                    if (((id.y >> (8 * k)) & 0xFF) == pos) acc[4 + k] += d[4 + k];
                 }
-                for (int r = 0; r < 3; ++r) {
-                    const int hh = 2 * ho - 1 + r;
-                    if (hh < 0 || hh >= H) continue;
-                    for (int s = 0; s < 3; ++s) {
-                        const int ww = 2 * wo - 1 + s;
-                        if (ww < 0 || ww >= W) continue;
-                        float v[8];
-                        unpack8(__ldg(reinterpret_cast<const uint4*>(F + (((long long)n * H + hh) * W + ww) * C) + c8),
-                                v);
-                        const bool is_me = (hh == h && ww == w);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (v[k] > best[k]) {
-                                best[k] = v[k];
-                                first[k] = is_me;
-                            }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (first[k]) acc[k] += d[k];
             }
         }
-        (void)me;
         reinterpret_cast<uint4*>(dF)[i] = pack8(acc);
     }
 }
@@ -314,57 +372,57 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* 
 }
 
 // per-block partials of dW[c][r][s] = sum a[n,h+r-1,w+s-1,c] * dL[n,h,w] and dbias = sum dL   -> partial[block][145]
-__global__ void __launch_bounds__(256)
+// blockDim = 288 = 9 warps: warp t owns filter tap t = r*3+s, its lanes own 32 consecutive pixels of a row segment, so
+// every load is a contiguous 128 B (dL) / 1 KB (activations) per warp and each thread keeps only 16 accumulators.
+__global__ void __launch_bounds__(288)
 head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ dL, float* __restrict__ partial,
                        int N, int H, int W) {
-    float acc[145];
+    const int tap = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = tap / 3, s = tap - 3 * r;
+    float acc[16], bsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 145; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    const long long groups = ((long long)N * H * W + 31) / 32;
     const long long total = (long long)N * H * W;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        const long long i = g * 32 + lane;
+        if (i >= total) continue;
         const int x = int(i % W);
         const int y = int((i / W) % H);
-        const long long nb = (i / ((long long)W * H)) * H * W;
         const float d = __ldg(dL + i);
-        acc[144] += d;
+        bsum += d;
+        const int yy = y + r - 1, xx = x + s - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const uint4* ap = reinterpret_cast<const uint4*>(A + (i + (long long)(r - 1) * W + (s - 1)) * 16);
+        float v[8];
+        unpack8(__ldg(ap), v);
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 8; ++k) acc[k] += v[k] * d;
+        unpack8(__ldg(ap + 1), v);
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                const int yy = y + r - 1, xx = x + s - 1;
-                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                const uint4* ap = reinterpret_cast<const uint4*>(A + (nb + (long long)yy * W + xx) * 16);
-                float v[8];
-                unpack8(__ldg(ap), v);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[k * 9 + r * 3 + s] += v[k] * d;
-                unpack8(__ldg(ap + 1), v);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[(8 + k) * 9 + r * 3 + s] += v[k] * d;
-            }
+        for (int k = 0; k < 8; ++k) acc[8 + k] += v[k] * d;
     }
-    __shared__ float red[8][145];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* out = partial + (size_t)blockIdx.x * 145;
 #pragma unroll
-    for (int k = 0; k < 145; ++k) {
+    for (int k = 0; k < 16; ++k) {
         const float v = warp_sum(acc[k]);
-        if (lane == 0) red[warp][k] = v;
+        if (lane == 0) out[k * 9 + tap] = v;   // [c][r][s]
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < 145; k += 256) {
-        float s = 0.f;
-        for (int wv = 0; wv < 8; ++wv) s += red[wv][k];
-        partial[(size_t)blockIdx.x * 145 + k] = s;
+    if (tap == 4) {
+        const float v = warp_sum(bsum);
+        if (lane == 0) out[144] = v;
     }
 }
-// out[j] (+)= sum_b partial[b][j]
-__global__ void sum_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// out[j] = sum_b partial[b][j]; one WARP per column j (blockDim = 256 -> 8 columns per block)
+__global__ void __launch_bounds__(256)
+sum_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (j >= width) return;
     double s = 0;
-    for (int b = 0; b < nrows; ++b) s += partial[(size_t)b * width + j];
-    out[j] = (float)s;
+    for (int b = lane; b < nrows; b += 32) s += partial[(size_t)b * width + j];
+    s = warp_sum_d(s);
+    if (lane == 0) out[j] = (float)s;
 }
 
 // ------------------------------------------------------------------------------------------------ BCE + Dice loss

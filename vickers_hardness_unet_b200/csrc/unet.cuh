@@ -9,6 +9,7 @@
 
 #include "conv_plan.cuh"
 #include "ops.cuh"
+#include "pack.cuh"
 
 namespace ub {
 
@@ -169,6 +170,8 @@ struct Ctx {
     float* fold_shift = nullptr;
     float* head_w = nullptr;         // fp32 copy [144] + bias [1]
     bool weights_ready = false;
+    PackTable fwd_pack;              // forward operand layouts of all convs (one launch)
+    int* fold_tab = nullptr;         // [n_bn][5]: gamma, beta, mean, var offsets, fold offset (one launch for all BN folds)
     // activation arena
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
@@ -218,6 +221,7 @@ struct Ctx {
         cudaFree(fold_scale);
         cudaFree(fold_shift);
         cudaFree(head_w);
+        cudaFree(fold_tab);
         cudaFree(arena);
     }
 };
@@ -236,40 +240,69 @@ inline int ctx_fail(Ctx* ctx, const std::string& msg) {
     return 1;
 }
 
-// Re-pack fp32 master weights (flat params / buffers in state-dict order) into the bf16 operand caches and fold BN.
-inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers, cudaStream_t st) {
+// all eval-mode BatchNorm folds in one launch: tab[b] = {gamma, beta, mean, var, fold} offsets, channel count
+__global__ void bn_fold_all_kernel(const int* __restrict__ tab, int nbn, const float* __restrict__ params,
+                                   const float* __restrict__ buffers, float eps, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+    const int b = blockIdx.x;
+    if (b >= nbn) return;
+    const int* t = tab + b * 6;
+    for (int c = threadIdx.x; c < t[5]; c += blockDim.x) {
+        const float s = params[t[0] + c] * rsqrtf(buffers[t[3] + c] + eps);
+        scale[t[4] + c] = s;
+        shift[t[4] + c] = params[t[1] + c] - buffers[t[2] + c] * s;
+    }
+}
+
+inline std::string ctx_build_pack_tables(Ctx* ctx) {
     const NetSpec& S = ctx->spec;
+    PackTable& T = ctx->fwd_pack;
     for (size_t i = 0; i < S.convs.size(); ++i) {
         const ConvRef& c = S.convs[i];
-        if ((int)i == S.head) {
-            UB_CUDA(cudaMemcpyAsync(ctx->head_w, params + c.w, 144 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-            UB_CUDA(cudaMemcpyAsync(ctx->head_w + 144, params + c.bias, sizeof(float), cudaMemcpyDeviceToDevice, st));
-            continue;
-        }
-        __nv_bfloat16* dst = ctx->wpk + c.wpk;
+        if ((int)i == S.head) continue;
+        PackEntry e;
         if (c.hc) {
-            pack_hconv_w_kernel<<<ew_grid(9ll * c.cin * c.cout, 256, ctx->num_sms), 256, 0, st>>>(params + c.w, dst, c.cout,
-                                                                                                 c.cin, c.cin, 0, 0);
+            e = pk_entry(PK_HCONV, c.w, c.wpk, 9ll * c.cin * c.cout);
+            e.cout = c.cout; e.cin = c.cin; e.a = c.cin; e.b = 0; e.c = 0;
         } else if ((int)i == S.stem) {
-            pack_stem_w_kernel<<<(64 * 224 + 255) / 256, 256, 0, st>>>(params + c.w, dst);
+            e = pk_entry(PK_STEM, c.w, c.wpk, 64 * 224);
         } else {
             const NetSpec::Dec* dd = nullptr;
             for (auto& d : S.dec) if (d.c1 == (int)i) dd = &d;
             if (dd) {
-                pack_dec1_w_kernel<<<ew_grid(c.wpk_elems, 256, ctx->num_sms), 256, 0, st>>>(params + c.w, dst, dd->cout,
-                                                                                          dd->cup, dd->cskip);
+                e = pk_entry(PK_DEC1, c.w, c.wpk, 4ll * dd->cout * (9 * dd->cskip + 4 * dd->cup));
+                e.cout = dd->cout; e.cin = dd->cup; e.a = dd->cskip;
             } else {
-                pack_conv_w_kernel<<<ew_grid(c.wpk_elems, 256, ctx->num_sms), 256, 0, st>>>(params + c.w, dst, c.cout,
-                                                                                          c.cin, c.k, c.k, 0);
+                e = pk_entry(PK_CONV, c.w, c.wpk, (long long)c.cout * c.cin * c.k * c.k);
+                e.cout = c.cout; e.cin = c.cin; e.a = c.k; e.b = c.k; e.c = 0;
             }
         }
+        T.add(e);
     }
+    if (T.upload() != cudaSuccess) return "pack table upload failed";
+    std::vector<int> ft;
     for (const BnRef& b : S.bns) {
-        bn_fold_kernel<<<(b.c + 127) / 128, 128, 0, st>>>(params + b.gamma, params + b.beta, buffers + b.mean,
-                                                         buffers + b.var, 1e-5f, ctx->fold_scale + b.fold,
-                                                         ctx->fold_shift + b.fold, b.c);
+        ft.push_back((int)b.gamma); ft.push_back((int)b.beta); ft.push_back((int)b.mean); ft.push_back((int)b.var);
+        ft.push_back((int)b.fold); ft.push_back(b.c);
     }
-    UB_CUDA(cudaGetLastError());
+    if (cudaMalloc(&ctx->fold_tab, ft.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(ctx->fold_tab, ft.data(), ft.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+        return "fold table upload failed";
+    return "";
+}
+
+// Re-pack fp32 master weights (flat params / buffers in state-dict order) into the bf16 operand caches and (unless
+// fold_bn == false: training uses batch statistics) fold eval-mode BatchNorm.  Three launches in total.
+inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers, cudaStream_t st, bool fold_bn = true) {
+    const NetSpec& S = ctx->spec;
+    const ConvRef& hc = S.convs[S.head];
+    UB_CUDA(cudaMemcpyAsync(ctx->head_w, params + hc.w, 145 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // weight + bias
+    UB_CUDA(ctx->fwd_pack.launch(params, ctx->wpk, st));
+    if (fold_bn) {
+        bn_fold_all_kernel<<<(int)S.bns.size(), 128, 0, st>>>(ctx->fold_tab, (int)S.bns.size(), params, buffers, 1e-5f,
+                                                              ctx->fold_scale, ctx->fold_shift);
+        UB_CUDA(cudaGetLastError());
+    }
     if (!ctx->weights_event) UB_CUDA(cudaEventCreateWithFlags(&ctx->weights_event, cudaEventDisableTiming));
     UB_CUDA(cudaEventRecord(ctx->weights_event, st));
     ctx->weights_ready = true;
@@ -600,6 +633,14 @@ inline int ctx_create(Ctx** out, int device, int max_batch, int H, int W, std::s
         *err = std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete ctx;
         return 1;
+    }
+    {
+        std::string pe = ctx_build_pack_tables(ctx);
+        if (!pe.empty()) {
+            *err = pe;
+            delete ctx;
+            return 1;
+        }
     }
     *out = ctx;
     return 0;

@@ -177,12 +177,16 @@ class Unet(nn.Module):
             self._packed_version = None
         return c
 
-    def _sync_weights(self, ctx, stream):
+    def _sync_weights(self, ctx, stream, fold_bn=None):
+        """Refresh the library's bf16 operand caches when the master tensors changed.  fold_bn: also fold eval-mode
+        BatchNorm (default: only in eval mode — a training step normalises with batch statistics)."""
+        fold_bn = (not self.training) if fold_bn is None else fold_bn
         ver = (self._flat["p"]._version, self._flat["b"]._version, id(ctx), self._params_epoch,
-               self._buffers_epoch if not self.training else -1)
+               self._buffers_epoch if fold_bn else -1)
         if ver != self._packed_version:
-            ctx.check(ctx.lib.unetb200_load_weights(ctx.handle, self._flat["p"].data_ptr(), self._flat["b"].data_ptr(),
-                                                    stream), "load_weights")
+            ctx.check(ctx.lib.unetb200_load_weights_ex(ctx.handle, self._flat["p"].data_ptr(),
+                                                       self._flat["b"].data_ptr(), int(not fold_bn), stream),
+                      "load_weights")
             self._packed_version = ver
 
     # ------------------------------------------------------------------ forward
@@ -207,7 +211,7 @@ class Unet(nn.Module):
         ctx = self._context(x)
         x = x.detach().to(torch.float32).contiguous()
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        self._sync_weights(ctx, stream)
+        self._sync_weights(ctx, stream, fold_bn=True)
         N, _, H, W = x.shape
         mask = torch.empty((N, 1, H, W), dtype=torch.uint8, device=x.device)
         prob = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device) if return_prob else None

@@ -66,6 +66,26 @@ int unetb200_forward_infer(unetb200_ctx* ctx, const float* x_dev, float* logits_
  * This is the end-to-end call a non-PyTorch host (the reference GUIs' numpy path) would bind. */
 int unetb200_infer_host(unetb200_ctx* ctx, const float* x_host, float* logits_host, float* prob_host,
                         uint8_t* mask_host, float thresh, int N);
+/* Pipelined form of the same call: submit returns as soon as the work is enqueued; wait blocks until the outputs of
+ * that slot are in the host buffers.  Two slots (0 / 1): while slot k computes, the H2D copy of the other slot's next
+ * request and the D2H copy of its previous result run on the copy engines (three streams inside the library), which
+ * is how a caller streaming frames keeps PCIe traffic off the critical path.  Host buffers should be pinned; they
+ * must stay valid until the matching wait.  A slot must be waited on before it is submitted again. */
+int unetb200_infer_host_submit(unetb200_ctx* ctx, int slot, const float* x_host, float* logits_host,
+                               float* prob_host, uint8_t* mask_host, float thresh, int N);
+int unetb200_infer_host_wait(unetb200_ctx* ctx, int slot);
+/* Camera-frame input: img uint8 HWC [N,H,W,3] (bgr != 0: B,G,R order as cv2.imread returns it).  The reference's host
+ * pre-processing — BGR->RGB, /255, (x - mean) / std (infer_pth_gui.py:46-48, ui_infer_rectangle.py:530-533) — runs
+ * inside the input-pack kernel; mean3 / std3 are the per-RGB-channel constants (NULL: 0 / 1).  Letterboxing stays on
+ * the host (it is an OpenCV resize).  4x fewer bytes cross the bus than with the fp32 tensor. */
+int unetb200_infer_host_u8(unetb200_ctx* ctx, const uint8_t* img_host, int bgr, const float* mean3, const float* std3,
+                           float* logits_host, float* prob_host, uint8_t* mask_host, float thresh, int N);
+int unetb200_infer_host_u8_submit(unetb200_ctx* ctx, int slot, const uint8_t* img_host, int bgr, const float* mean3,
+                                  const float* std3, float* logits_host, float* prob_host, uint8_t* mask_host,
+                                  float thresh, int N);
+int unetb200_forward_infer_u8(unetb200_ctx* ctx, const uint8_t* img_dev, int bgr, const float* mean3,
+                              const float* std3, float* logits_dev, float* prob_dev, uint8_t* mask_dev, float thresh,
+                              int N, void* stream);
 /* number of kernel launches one forward_infer call issues at batch N (after the plan for N exists) */
 int unetb200_infer_launch_count(unetb200_ctx* ctx, int N);
 

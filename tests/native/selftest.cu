@@ -615,7 +615,7 @@ static void bench_hconv(const char* name, int N, int H, int W, int cup, int cski
     long long* d_prof;
     CK(cudaMalloc(&d_prof, (size_t)L.grid * 16 * 8));
     L.p.prof = d_prof;
-    const int modes[] = {0, 8, 13, 15};
+    const int modes[] = {0, 8, 13, 15, 15 + 16, 15 + 32, 15 + 48};
     for (int mode : modes) {
         L.p.dbg = mode;
         CK(cudaMemset(d_prof, 0, (size_t)L.grid * 16 * 8));

@@ -233,3 +233,58 @@ def test_errors_are_loud(models):
     with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
         y2 = m(torch.zeros(1, 3, 64, 64, device="cuda"))
     assert y2.dtype == torch.float32 and torch.equal(y, y2)
+
+
+# ----------------------------------------------------------------------------------------------- host-buffer entry points
+def test_host_submit_wait_two_slots_match_device_call(models):
+    """unetb200_infer_host_submit/_wait: two requests in flight, each slot returns the result of ITS request,
+    bit-identical to the device-tensor call on the same input."""
+    o, m = models
+    _calibrate(o, m, 64)
+    g = torch.Generator().manual_seed(5)
+    xa = torch.randn(3, 3, 64, 96, generator=g).pin_memory()
+    xb = torch.randn(3, 3, 64, 96, generator=g).pin_memory()
+    want = [m.predict_mask(x.cuda(), return_prob=True) for x in (xa, xb)]
+    mk = [torch.empty(3, 1, 64, 96, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pr = [torch.empty(3, 1, 64, 96).pin_memory() for _ in range(2)]
+    lg = [torch.empty(3, 1, 64, 96).pin_memory() for _ in range(2)]
+    for rep in range(3):  # slots are reusable
+        m.submit_host(0, xa, mask_out=mk[0], prob_out=pr[0], logits_out=lg[0])
+        m.submit_host(1, xb, mask_out=mk[1], prob_out=pr[1], logits_out=lg[1])
+        with pytest.raises(_lib.UnetB200Error):
+            m.submit_host(1, xb, mask_out=mk[1])  # still in flight
+        m.wait_host(0)
+        m.wait_host(1)
+        for s in range(2):
+            assert torch.equal(mk[s], want[s][0].cpu())
+            assert torch.equal(pr[s], want[s][1].cpu())
+            assert torch.equal(torch.sigmoid(lg[s]) >= 0.5, mk[s] > 0)
+    assert torch.equal(m.predict_mask_host(xa), want[0][0].cpu())
+    assert m._ctx.device_error_flag() == 0
+
+
+def test_uint8_frames_equal_host_preprocessing(models):
+    """uint8 BGR HWC frames through the fused pre-processing pack == the reference's host pre-processing
+    (infer_pth_gui.py:46-48: BGR->RGB, /255, (x-mean)/std, HWC->CHW) followed by the fp32-tensor call."""
+    o, m = models
+    _calibrate(o, m, 64)
+    g = torch.Generator().manual_seed(6)
+    frames = torch.randint(0, 256, (2, 64, 96, 3), dtype=torch.uint8, generator=g)
+    mean = torch.tensor(vb.Unet.IMAGENET_MEAN)
+    std = torch.tensor(vb.Unet.IMAGENET_STD)
+    rgb = frames.flip(-1).float() / 255.0
+    x = ((rgb - mean) / std).permute(0, 3, 1, 2).contiguous()
+    ref = m(x.cuda()).cpu()
+    lg = torch.empty(2, 1, 64, 96).pin_memory()
+    mk = torch.empty(2, 1, 64, 96, dtype=torch.uint8).pin_memory()
+    m.submit_host(0, frames.pin_memory(), mask_out=mk, logits_out=lg, bgr=True)
+    m.wait_host(0)
+    # the only difference is fp32 rounding of (v/255 - mean) * (1/std) vs (v/255 - mean) / std before the bf16 pack
+    d = (lg - ref).abs()
+    print(f"uint8 path vs host pre-processing: max {float(d.max()):.3e} mean {float(d.mean()):.3e}")
+    assert float(d.max()) <= 2e-2 and float(d.mean()) <= 1e-3
+    assert _iou(mk > 0, ref >= 0) >= 0.999
+    # RGB-ordered frames with bgr=False give the same result
+    m.submit_host(1, frames.flip(-1).contiguous().pin_memory(), logits_out=lg, bgr=False)
+    m.wait_host(1)
+    assert float((lg - ref).abs().max()) <= 2e-2

@@ -34,6 +34,11 @@ def _proto(lib):
         "unetb200_load_weights_ex": (i32, [vp, vp, vp, i32, vp]),
         "unetb200_forward_infer": (i32, [vp, vp, vp, vp, vp, f32, i32, vp]),
         "unetb200_infer_host": (i32, [vp, vp, vp, vp, vp, f32, i32]),
+        "unetb200_infer_host_submit": (i32, [vp, i32, vp, vp, vp, vp, f32, i32]),
+        "unetb200_infer_host_wait": (i32, [vp, i32]),
+        "unetb200_infer_host_u8": (i32, [vp, vp, i32, P(f32), P(f32), vp, vp, vp, f32, i32]),
+        "unetb200_infer_host_u8_submit": (i32, [vp, i32, vp, i32, P(f32), P(f32), vp, vp, vp, f32, i32]),
+        "unetb200_forward_infer_u8": (i32, [vp, vp, i32, P(f32), P(f32), vp, vp, vp, f32, i32, vp]),
         "unetb200_infer_launch_count": (i32, [vp, i32]),
         "unetb200_profile_infer": (i32, [vp, vp, vp, i32, vp, P(f32), P(i32), i32, P(i32)]),
         "unetb200_profile_name": (i32, [vp, i32, i32, C.c_char_p, i32]),

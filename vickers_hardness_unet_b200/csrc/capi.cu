@@ -92,33 +92,117 @@ int unetb200_forward_infer(unetb200_ctx* h, const float* x_dev, float* logits_de
     return ctx_forward_infer(ctx, x_dev, logits_dev, prob_dev, mask_dev, thresh, N, (cudaStream_t)stream);
 }
 
+// ---- host-buffer inference: two staging slots, three streams (H2D / compute / D2H) ---------------------------------
+static int io_prepare(Ctx* ctx) {
+    if (ctx->io_stream) return 0;
+    const size_t mpx = (size_t)ctx->max_batch * ctx->H * ctx->W;
+    for (Ctx::IoSlot& sl : ctx->io) {
+        UB_CUDA(cudaMalloc(&sl.x, mpx * 3 * sizeof(float)));
+        UB_CUDA(cudaMalloc(&sl.x8, mpx * 3));
+        UB_CUDA(cudaMalloc(&sl.f, mpx * 2 * sizeof(float)));
+        UB_CUDA(cudaMalloc(&sl.m, mpx));
+        UB_CUDA(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+        UB_CUDA(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+        UB_CUDA(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+    }
+    UB_CUDA(cudaStreamCreateWithFlags(&ctx->io_in, cudaStreamNonBlocking));
+    UB_CUDA(cudaStreamCreateWithFlags(&ctx->io_out, cudaStreamNonBlocking));
+    UB_CUDA(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
+    return 0;
+}
+
+static int io_submit(Ctx* ctx, int slot, const float* x_host, const uint8_t* img_host, int bgr, const float* mean,
+                     const float* stdv, float* logits_host, float* prob_host, uint8_t* mask_host, float thresh, int N) {
+    if (slot < 0 || slot > 1) return ctx_fail(ctx, "infer_host: slot must be 0 or 1");
+    if (!x_host && !img_host) return ctx_fail(ctx, "infer_host: input is null");
+    if (N < 1 || N > ctx->max_batch) return ctx_fail(ctx, "infer_host: batch outside [1, max_batch]");
+    if (!logits_host && !prob_host && !mask_host) return ctx_fail(ctx, "infer_host: no output requested");
+    if (!ctx->weights_ready) return ctx_fail(ctx, "infer_host: weights not loaded");
+    UB_CUDA(cudaSetDevice(ctx->device));
+    if (io_prepare(ctx)) return 1;
+    Ctx::IoSlot& sl = ctx->io[slot];
+    if (sl.busy) return ctx_fail(ctx, "infer_host: slot still in flight (call unetb200_infer_host_wait first)");
+    const size_t px = (size_t)N * ctx->H * ctx->W;
+    NormParams np;
+    if (img_host) {
+        for (int c = 0; c < 3; ++c) {
+            np.mean[c] = mean ? mean[c] : 0.f;
+            np.inv_std[c] = 1.f / (stdv ? stdv[c] : 1.f);
+        }
+        UB_CUDA(cudaMemcpyAsync(sl.x8, img_host, px * 3, cudaMemcpyHostToDevice, ctx->io_in));
+    } else {
+        UB_CUDA(cudaMemcpyAsync(sl.x, x_host, px * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->io_in));
+    }
+    UB_CUDA(cudaEventRecord(sl.h2d_done, ctx->io_in));
+    cudaStream_t st = ctx->io_stream;
+    UB_CUDA(cudaStreamWaitEvent(st, sl.h2d_done, 0));
+    if (ctx->weights_event) UB_CUDA(cudaStreamWaitEvent(st, ctx->weights_event, 0));
+    float* dl = logits_host ? sl.f : nullptr;
+    float* dp = prob_host ? sl.f + (size_t)ctx->max_batch * ctx->H * ctx->W : nullptr;
+    uint8_t* dm = mask_host ? sl.m : nullptr;
+    if (ctx_forward_infer(ctx, img_host ? nullptr : sl.x, dl, dp, dm, thresh, N, st, nullptr, img_host ? sl.x8 : nullptr,
+                          bgr, &np))
+        return 1;
+    UB_CUDA(cudaEventRecord(sl.compute_done, st));
+    UB_CUDA(cudaStreamWaitEvent(ctx->io_out, sl.compute_done, 0));
+    if (dl) UB_CUDA(cudaMemcpyAsync(logits_host, dl, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->io_out));
+    if (dp) UB_CUDA(cudaMemcpyAsync(prob_host, dp, px * sizeof(float), cudaMemcpyDeviceToHost, ctx->io_out));
+    if (dm) UB_CUDA(cudaMemcpyAsync(mask_host, dm, px, cudaMemcpyDeviceToHost, ctx->io_out));
+    UB_CUDA(cudaEventRecord(sl.d2h_done, ctx->io_out));
+    sl.busy = true;
+    return 0;
+}
+
+int unetb200_infer_host_submit(unetb200_ctx* h, int slot, const float* x_host, float* logits_host, float* prob_host,
+                               uint8_t* mask_host, float thresh, int N) {
+    return io_submit(h->c, slot, x_host, nullptr, 0, nullptr, nullptr, logits_host, prob_host, mask_host, thresh, N);
+}
+
+int unetb200_infer_host_u8_submit(unetb200_ctx* h, int slot, const uint8_t* img_host, int bgr, const float* mean3,
+                                  const float* std3, float* logits_host, float* prob_host, uint8_t* mask_host,
+                                  float thresh, int N) {
+    return io_submit(h->c, slot, nullptr, img_host, bgr, mean3, std3, logits_host, prob_host, mask_host, thresh, N);
+}
+
+int unetb200_infer_host_wait(unetb200_ctx* h, int slot) {
+    Ctx* ctx = h->c;
+    if (slot < 0 || slot > 1) return ctx_fail(ctx, "infer_host_wait: slot must be 0 or 1");
+    Ctx::IoSlot& sl = ctx->io[slot];
+    if (!sl.busy) return 0;
+    sl.busy = false;
+    UB_CUDA(cudaEventSynchronize(sl.d2h_done));
+    return 0;
+}
+
 int unetb200_infer_host(unetb200_ctx* h, const float* x_host, float* logits_host, float* prob_host, uint8_t* mask_host,
                         float thresh, int N) {
+    if (unetb200_infer_host_wait(h, 0)) return 1;
+    if (unetb200_infer_host_submit(h, 0, x_host, logits_host, prob_host, mask_host, thresh, N)) return 1;
+    return unetb200_infer_host_wait(h, 0);
+}
+
+int unetb200_infer_host_u8(unetb200_ctx* h, const uint8_t* img_host, int bgr, const float* mean3, const float* std3,
+                           float* logits_host, float* prob_host, uint8_t* mask_host, float thresh, int N) {
+    if (unetb200_infer_host_wait(h, 0)) return 1;
+    if (unetb200_infer_host_u8_submit(h, 0, img_host, bgr, mean3, std3, logits_host, prob_host, mask_host, thresh, N))
+        return 1;
+    return unetb200_infer_host_wait(h, 0);
+}
+
+/* uint8 HWC device input (frames already on the GPU): same fused pre-processing, caller's stream */
+int unetb200_forward_infer_u8(unetb200_ctx* h, const uint8_t* img_dev, int bgr, const float* mean3, const float* std3,
+                              float* logits_dev, float* prob_dev, uint8_t* mask_dev, float thresh, int N, void* stream) {
     Ctx* ctx = h->c;
-    if (!x_host) return ctx_fail(ctx, "infer_host: x is null");
-    if (N < 1 || N > ctx->max_batch) return ctx_fail(ctx, "infer_host: batch outside [1, max_batch]");
+    if (!img_dev) return ctx_fail(ctx, "forward_infer_u8: img is null");
+    if (!logits_dev && !prob_dev && !mask_dev) return ctx_fail(ctx, "forward_infer_u8: no output requested");
     UB_CUDA(cudaSetDevice(ctx->device));
-    const size_t px = (size_t)N * ctx->H * ctx->W;
-    if (!ctx->io_x) {
-        const size_t mpx = (size_t)ctx->max_batch * ctx->H * ctx->W;
-        UB_CUDA(cudaMalloc(&ctx->io_x, mpx * 3 * sizeof(float)));
-        UB_CUDA(cudaMalloc(&ctx->io_f, mpx * 2 * sizeof(float)));
-        UB_CUDA(cudaMalloc(&ctx->io_m, mpx));
-        UB_CUDA(cudaStreamCreateWithFlags(&ctx->io_stream, cudaStreamNonBlocking));
+    NormParams np;
+    for (int c = 0; c < 3; ++c) {
+        np.mean[c] = mean3 ? mean3[c] : 0.f;
+        np.inv_std[c] = 1.f / (std3 ? std3[c] : 1.f);
     }
-    cudaStream_t st = ctx->io_stream;
-    if (ctx->weights_event) UB_CUDA(cudaStreamWaitEvent(st, ctx->weights_event, 0));
-    UB_CUDA(cudaMemcpyAsync(ctx->io_x, x_host, px * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    float* dl = logits_host ? ctx->io_f : nullptr;
-    float* dp = prob_host ? ctx->io_f + (size_t)ctx->max_batch * ctx->H * ctx->W : nullptr;
-    uint8_t* dm = mask_host ? ctx->io_m : nullptr;
-    if (!dl && !dp && !dm) return ctx_fail(ctx, "infer_host: no output requested");
-    if (ctx_forward_infer(ctx, ctx->io_x, dl, dp, dm, thresh, N, st)) return 1;
-    if (dl) UB_CUDA(cudaMemcpyAsync(logits_host, dl, px * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (dp) UB_CUDA(cudaMemcpyAsync(prob_host, dp, px * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (dm) UB_CUDA(cudaMemcpyAsync(mask_host, dm, px, cudaMemcpyDeviceToHost, st));
-    UB_CUDA(cudaStreamSynchronize(st));
-    return 0;
+    return ctx_forward_infer(ctx, nullptr, logits_dev, prob_dev, mask_dev, thresh, N, (cudaStream_t)stream, nullptr,
+                             img_dev, bgr, &np);
 }
 
 int unetb200_infer_launch_count(unetb200_ctx* h, int N) {

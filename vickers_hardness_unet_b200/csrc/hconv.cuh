@@ -311,8 +311,13 @@ hconv_kernel(const __grid_constant__ HconvParams P) {
                     }
                 }
                 UB_HC_TICK(t_work)
-                umma_commit(empty_bar(stage));
-                umma_commit(tfull_bar(acc));
+                if (P.dbg & 32) {
+                    mbar_arrive(empty_bar(stage));
+                    mbar_arrive(tfull_bar(acc));
+                } else {
+                    umma_commit(empty_bar(stage));
+                    umma_commit(tfull_bar(acc));
+                }
                 UB_HC_TICK(t_b)
                 if (++stage == P.stages) {
                     stage = 0;
@@ -355,8 +360,10 @@ hconv_kernel(const __grid_constant__ HconvParams P) {
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * P.cout;
             for (int c0 = 0; c0 < P.cout; c0 += 16) {
                 uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
+                if (!(P.dbg & 16)) {
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                }
                 if (c0 + 16 >= P.cout) {  // last TMEM read of this accumulator: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();

@@ -36,6 +36,42 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     }
 }
 
+// Same packed layout straight from camera frames: img uint8 HWC [N,H,W,3] (bgr != 0: channel order B,G,R as cv2.imread
+// delivers it) -> ((v / 255) - mean[c]) / std[c] per RGB channel, i.e. the reference's host-side pre-processing
+// (/root/reference/infer_pth_gui.py:46-48, ui_infer_rectangle.py:530-533) fused into the pack: 0.75 MB instead of
+// 3 MB per 512x512 image cross the PCIe bus and the host never touches the pixels.
+struct NormParams {
+    float mean[3], inv_std[3];
+};
+__global__ void pack_input_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ xp, int N, int H, int W,
+                                     int bgr, NormParams np) {
+    const int Wp = W + 8;
+    const long long total = (long long)N * H * (Wp / 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int wp2 = int(i % (Wp / 2));
+        const long long nh = i / (Wp / 2);
+        float v[2][3];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int w = wp2 * 2 + k - 4;
+            const bool in = (w >= 0 && w < W);
+            const uint8_t* px = img + (nh * W + (in ? w : 0)) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float raw = (float)__ldg(px + (bgr ? 2 - c : c)) * (1.f / 255.f);
+                v[k][c] = in ? (raw - np.mean[c]) * np.inv_std[c] : 0.f;
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16(v[0][0], v[0][1]);
+        o.y = pack_bf16(v[0][2], 0.f);
+        o.z = pack_bf16(v[1][0], v[1][1]);
+        o.w = pack_bf16(v[1][2], 0.f);
+        *reinterpret_cast<uint4*>(xp + (nh * Wp + wp2 * 2) * 4) = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ weight re-pack
 // OIHW fp32 [co][ci][R][S] -> K-major bf16 [co][(r*S+s)*cin + ci]; flip=1 additionally mirrors r,s and swaps the
 // roles of co/ci (the dgrad operand: [ci][( (R-1-r)*S + (S-1-s) )*cout + co]).

@@ -189,12 +189,24 @@ struct Ctx {
         int launches = 0;
     };
     std::map<int, InferPlan> infer_plans;  // keyed by batch size
-    // staging for the host-buffer entry point (unetb200_infer_host)
-    float* io_x = nullptr;
-    float* io_f = nullptr;
-    uint8_t* io_m = nullptr;
-    cudaStream_t io_stream = nullptr;
+    // staging for the host-buffer entry points (unetb200_infer_host / _submit / _wait): two slots, so that the H2D
+    // copy of request k+1 and the D2H copy of request k-1 run on the copy engines while request k computes
+    struct IoSlot {
+        float* x = nullptr;       // fp32 NCHW input staging [max_batch,3,H,W]
+        uint8_t* x8 = nullptr;    // uint8 HWC input staging [max_batch,H,W,3]
+        float* f = nullptr;       // logits | prob staging [2][max_batch,H,W]
+        uint8_t* m = nullptr;     // mask staging
+        cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+        bool busy = false;
+    };
+    IoSlot io[2];
+    cudaStream_t io_in = nullptr, io_stream = nullptr, io_out = nullptr;  // H2D, compute, D2H
     cudaEvent_t weights_event = nullptr;  // recorded after every weight re-pack (cross-stream ordering for io_stream)
+    // the activation arena is shared by every forward of this context: a forward enqueued on a different stream than
+    // the previous one first waits for that one to finish (caller's stream vs the library's io_stream)
+    cudaEvent_t arena_event = nullptr;
+    cudaStream_t arena_stream = nullptr;
+    bool arena_used = false;
     // optional per-launch profiling of the train step: (name, event recorded BEFORE the launch)
     bool prof_on = false;
     std::vector<std::pair<std::string, cudaEvent_t>> prof_ev;
@@ -212,10 +224,19 @@ struct Ctx {
     ~Ctx() {
         if (train && train_free) train_free(train);
         if (weights_event) cudaEventDestroy(weights_event);
-        cudaFree(io_x);
-        cudaFree(io_f);
-        cudaFree(io_m);
+        if (arena_event) cudaEventDestroy(arena_event);
+        for (IoSlot& sl : io) {
+            cudaFree(sl.x);
+            cudaFree(sl.x8);
+            cudaFree(sl.f);
+            cudaFree(sl.m);
+            if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+            if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+            if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+        }
+        if (io_in) cudaStreamDestroy(io_in);
         if (io_stream) cudaStreamDestroy(io_stream);
+        if (io_out) cudaStreamDestroy(io_out);
         cudaFree(d_err);
         cudaFree(wpk);
         cudaFree(fold_scale);
@@ -544,8 +565,10 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
 
 // logits / prob / mask: any may be null (at least one non-null). x: fp32 NCHW [N,3,H,W] device pointer.
 // ev != nullptr: record an event before every launch and one at the end (per-launch timing for bench.py).
+// x8 != nullptr: the input is uint8 HWC [N,H,W,3] instead (pack_input_u8_kernel; norm / bgr describe the pre-processing).
 inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* prob, uint8_t* mask, float thresh, int N,
-                             cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr) {
+                             cudaStream_t st, std::vector<cudaEvent_t>* ev = nullptr, const uint8_t* x8 = nullptr,
+                             int bgr = 0, const NormParams* norm = nullptr) {
     auto mark = [&]() {
         if (!ev) return;
         cudaEvent_t e;
@@ -564,8 +587,14 @@ inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* pro
     }
     Ctx::InferPlan& P = it->second;
     const int H = ctx->H, W = ctx->W;
+    if (!ctx->arena_event) UB_CUDA(cudaEventCreateWithFlags(&ctx->arena_event, cudaEventDisableTiming));
+    if (ctx->arena_used && ctx->arena_stream != st) UB_CUDA(cudaStreamWaitEvent(st, ctx->arena_event, 0));
     mark();
-    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P.xp, N, H, W);
+    if (x8)
+        pack_input_u8_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x8, P.xp, N, H,
+                                                                                                          W, bgr, *norm);
+    else
+        pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P.xp, N, H, W);
     UB_CUDA(cudaGetLastError());
     for (auto& s : P.steps) {
         mark();
@@ -580,6 +609,9 @@ inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* pro
     head_conv_kernel<<<grid, 256, 0, st>>>(P.head_in, ctx->head_w, ctx->head_w + 144, logits, prob, mask, tl, N, H, W);
     UB_CUDA(cudaGetLastError());
     mark();
+    UB_CUDA(cudaEventRecord(ctx->arena_event, st));
+    ctx->arena_stream = st;
+    ctx->arena_used = true;
     return 0;
 }
 

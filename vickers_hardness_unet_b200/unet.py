@@ -219,3 +219,74 @@ class Unet(nn.Module):
                                                  prob.data_ptr() if return_prob else None, mask.data_ptr(),
                                                  float(threshold), N, stream), "forward_infer")
         return (mask, prob) if return_prob else mask
+
+    # ------------------------------------------------------------------ host-buffer inference (numpy / pinned tensors)
+    IMAGENET_MEAN = (0.485, 0.456, 0.406)   # /root/reference/infer_pth_gui.py:15-16, ui_infer_rectangle.py:41-42
+    IMAGENET_STD = (0.229, 0.224, 0.225)
+
+    def _host_context(self, N: int, H: int, W: int) -> "_lib.Context":
+        dev = self._flat["p"].device
+        if dev.type != "cuda":
+            raise _lib.UnetB200Error("the model must live on a CUDA (sm_100a) device; there is no CPU fallback")
+        if H % 32 or W % 32:
+            raise ValueError(f"H and W must be divisible by 32 (got {H}x{W})")
+        c = self._ctx
+        if c is None or c.H != H or c.W != W or c.max_batch < N or c.device != dev.index:
+            if c is not None:
+                torch.cuda.synchronize(dev)
+                c.close()
+            self._ctx = c = _lib.Context(dev.index, N, H, W)
+            self._packed_version = None
+        self._sync_weights(c, torch.cuda.current_stream(dev).cuda_stream, fold_bn=True)
+        return c
+
+    @torch.no_grad()
+    def submit_host(self, slot: int, x: torch.Tensor, mask_out: torch.Tensor = None, prob_out: torch.Tensor = None,
+                    logits_out: torch.Tensor = None, threshold: float = 0.5, bgr: bool = True,
+                    mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """Enqueue one inference request from HOST memory (ideally pinned) and return immediately; `wait_host(slot)`
+        blocks until the requested outputs are in the given host tensors.  x: fp32 [N,3,H,W] (already normalised, as
+        infer_pth_gui.py:46-49 builds it) or uint8 [N,H,W,3] camera frames, in which case BGR->RGB, /255 and
+        (x-mean)/std run on the device.  Two slots let request k+1's upload overlap request k's compute."""
+        import ctypes as C
+        if x.is_cuda or not x.is_contiguous():
+            raise ValueError("submit_host takes a contiguous CPU tensor")
+        u8 = x.dtype == torch.uint8
+        if u8:
+            N, H, W, Cc = x.shape
+        else:
+            if x.dtype != torch.float32:
+                raise ValueError("submit_host takes float32 NCHW or uint8 NHWC input")
+            N, Cc, H, W = x.shape
+        if Cc != 3:
+            raise ValueError(f"expected 3 channels, got {tuple(x.shape)}")
+        outs = []
+        for t, dt in ((logits_out, torch.float32), (prob_out, torch.float32), (mask_out, torch.uint8)):
+            if t is not None and (t.is_cuda or t.dtype != dt or t.numel() != N * H * W or not t.is_contiguous()):
+                raise ValueError("output tensors must be contiguous CPU tensors of N*H*W elements (float32 / uint8)")
+            outs.append(t.data_ptr() if t is not None else None)
+        ctx = self._host_context(N, H, W)
+        if u8:
+            m3 = (C.c_float * 3)(*mean)
+            s3 = (C.c_float * 3)(*std)
+            rc = ctx.lib.unetb200_infer_host_u8_submit(ctx.handle, slot, x.data_ptr(), int(bool(bgr)), m3, s3, outs[0],
+                                                       outs[1], outs[2], float(threshold), N)
+        else:
+            rc = ctx.lib.unetb200_infer_host_submit(ctx.handle, slot, x.data_ptr(), outs[0], outs[1], outs[2],
+                                                    float(threshold), N)
+        ctx.check(rc, "infer_host_submit")
+
+    def wait_host(self, slot: int):
+        ctx = self._ctx
+        if ctx is None:
+            raise _lib.UnetB200Error("wait_host: nothing was submitted")
+        ctx.check(ctx.lib.unetb200_infer_host_wait(ctx.handle, slot), "infer_host_wait")
+
+    def predict_mask_host(self, x: torch.Tensor, threshold: float = 0.5, **kw) -> torch.Tensor:
+        """Blocking host-to-host `sigmoid(model(x)) >= threshold`: uint8 {0,255} CPU tensor [N,1,H,W]."""
+        N = x.shape[0]
+        H, W = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[2], x.shape[3])
+        mask = torch.empty((N, 1, H, W), dtype=torch.uint8)
+        self.submit_host(0, x, mask_out=mask, threshold=threshold, **kw)
+        self.wait_host(0)
+        return mask

@@ -467,6 +467,157 @@ static void case_hconv(const char* name, int N, int H, int W, int cup, int cskip
     if (d_stats) cudaFree(d_stats);
 }
 
+// tconv: TMA halo conv (plain: src at output resolution; parity: nearest-2x upsample of a low-res source folded into
+// 2x2 taps) vs the CPU conv of the materialised input
+static void case_tconv(const char* name, int N, int H, int W, int cin, int cout, bool parity, bool residual, bool relu,
+                       bool scale_shift, bool stats) {
+    HostT src(N, parity ? H / 2 : H, parity ? W / 2 : W, cin), cat(N, H, W, cin);
+    fill_rand_bf16(src.v, 1.0f);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w)
+                for (int c = 0; c < cin; ++c) cat.at(n, h, w, c) = parity ? src.at(n, h / 2, w / 2, c) : src.at(n, h, w, c);
+    std::vector<float> w((size_t)cout * cin * 9);
+    const float ws = 1.0f / sqrtf((float)cin * 9);
+    for (auto& x : w) x = bf16r(frand() * ws * 1.7f);
+    std::vector<float> sc(cout, 1.f), sh(cout, 0.f);
+    if (scale_shift)
+        for (int c = 0; c < cout; ++c) { sc[c] = 0.5f + 0.5f * fabsf(frand()); sh[c] = 0.1f * frand(); }
+    HostT res(N, H, W, cout);
+    if (residual) fill_rand_bf16(res.v, 1.0f);
+    HostT ref = cpu_conv(cat, w, cout, 3, 1, 1);
+    for (size_t i = 0; i < ref.v.size(); ++i) {
+        float v = ref.v[i] * sc[i % cout] + sh[i % cout];
+        if (residual) v += res.v[i];
+        if (relu) v = fmaxf(v, 0.f);
+        ref.v[i] = v;
+    }
+    __nv_bfloat16* d_src = to_dev_bf16(src.v);
+    __nv_bfloat16* d_res = to_dev_bf16(res.v);
+    float* d_w = to_dev_f32(w);
+    float* d_sc = to_dev_f32(sc);
+    float* d_sh = to_dev_f32(sh);
+    __nv_bfloat16 *d_wpk, *d_out;
+    CK(cudaMalloc(&d_wpk, (size_t)tconv_w_elems(cin, cout, parity) * 2));
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    CK(cudaMemset(d_out, 0xFF, ref.v.size() * 2));
+    {
+        PackTable T;
+        PackEntry e = pk_entry(parity ? PK_HPAR : PK_HCONV, 0, 0, tconv_w_elems(cin, cout, parity));
+        e.cout = cout; e.cin = cin; e.a = cin; e.b = 0; e.c = 0;
+        T.add(e);
+        CK(T.upload());
+        CK(T.launch(d_w, d_wpk, 0));
+        CK(cudaDeviceSynchronize());
+    }
+    float* d_stats = nullptr;
+    EpilogueDesc ep;
+    if (scale_shift) { ep.scale = d_sc; ep.shift = d_sh; }
+    ep.relu = relu;
+    if (residual) ep.residual = nhwc_view(d_res, N, H, W, cout);
+    if (stats) {
+        CK(cudaMalloc(&d_stats, (size_t)2 * g_ctx->num_sms * cout * 2 * 4));
+        CK(cudaMemset(d_stats, 0, (size_t)2 * g_ctx->num_sms * cout * 2 * 4));
+        ep.stats = d_stats;
+    }
+    TconvLaunch L;
+    std::string e = tconv_build(L, d_src, cin, parity, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %d occ %d iph %d smem %u stages %d nacc %d nt %d tiles %dx%dx%d\n", name, L.grid, L.occ,
+           L.iph, L.smem, L.p.stages, L.p.nacc, L.p.nt, L.p.tiles_w, L.p.tiles_h, N);
+    CK(tconv_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+        report(name, compare(got, ref.v), parity ? 1.2e-2 : 6e-3, got, ref.v, cout);
+        if (stats) {
+            std::vector<float> hs((size_t)L.grid * cout * 2);
+            CK(cudaMemcpy(hs.data(), d_stats, hs.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<float> gs(cout * 2, 0.f), rs(cout * 2, 0.f);
+            for (int b = 0; b < L.grid; ++b)
+                for (int j = 0; j < cout * 2; ++j) gs[j] += hs[(size_t)b * cout * 2 + j];
+            for (size_t i = 0; i < got.size(); ++i) {
+                rs[(i % cout) * 2] += got[i];
+                rs[(i % cout) * 2 + 1] += got[i] * got[i];
+            }
+            std::string nm = std::string(name) + " [stats]";
+            report(nm.c_str(), compare(gs, rs), 1e-4, gs, rs, 2);
+        }
+    }
+    cudaFree(d_src); cudaFree(d_res); cudaFree(d_w); cudaFree(d_sc); cudaFree(d_sh);
+    cudaFree(d_wpk); cudaFree(d_out);
+    if (d_stats) cudaFree(d_stats);
+}
+
+static void bench_tconv(const char* name, int N, int H, int W, int cin, int cout, bool parity, bool residual, int iters) {
+    const size_t src_e = (size_t)N * (parity ? H / 2 : H) * (parity ? W / 2 : W) * cin, out_e = (size_t)N * H * W * cout;
+    __nv_bfloat16 *d_src, *d_out, *d_wpk, *d_res = nullptr;
+    CK(cudaMalloc(&d_src, src_e * 2));
+    CK(cudaMalloc(&d_out, out_e * 2));
+    CK(cudaMalloc(&d_wpk, (size_t)tconv_w_elems(cin, cout, parity) * 2));
+    CK(cudaMemset(d_src, 0x3C, src_e * 2));
+    CK(cudaMemset(d_wpk, 0x3C, (size_t)tconv_w_elems(cin, cout, parity) * 2));
+    EpilogueDesc ep;
+    ep.relu = 1;
+    if (residual) {
+        CK(cudaMalloc(&d_res, out_e * 2));
+        CK(cudaMemset(d_res, 0x3C, out_e * 2));
+        ep.residual = nhwc_view(d_res, N, H, W, cout);
+    }
+    TconvLaunch L;
+    std::string e = tconv_build(L, d_src, cin, parity, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] bench %s: %s\n", name, e.c_str());
+        return;
+    }
+    long long* d_prof;
+    CK(cudaMalloc(&d_prof, (size_t)L.grid * 16 * 8));
+    L.p.prof = d_prof;
+    const int modes[] = {0, 8, 9, 12, 13, 15};
+    for (int mode : modes) {
+        L.p.dbg = mode;
+        CK(cudaMemset(d_prof, 0, (size_t)L.grid * 16 * 8));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int i = 0; i < 2; ++i) CK(tconv_launch(L, 0));
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) CK(tconv_launch(L, 0));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= iters;
+        const double flops = 2.0 * N * H * W * (double)cout * cin * 9;
+        const double bytes = (src_e + out_e * (residual ? 2 : 1)) * 2.0;
+        const int tiles = L.p.tiles_w * L.p.tiles_h * N;
+        printf("[BENCH-T] %-30s skip[%s%s%s] %8.1f us %7.1f TFLOP/s(3x3-eq) %7.1f GB/s %6.0f cyc/tile/CTA grid %d occ %d iph %d stages %d nacc %d nt %d smem %u\n",
+               name, mode & 1 ? "L" : "-", mode & 2 ? "M" : "-", mode & 4 ? "E" : "-", ms * 1e3, flops / ms * 1e-9,
+               bytes / ms * 1e-6, ms * 1e-3 * 1.965e9 / ((double)tiles / L.grid), L.grid, L.occ, L.iph, L.p.stages, L.p.nacc,
+               L.p.nt, L.smem);
+        if (mode & 8) {
+            std::vector<long long> hp((size_t)L.grid * 16);
+            CK(cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost));
+            const double per = (double)tiles / L.grid;
+            const char* nm[12] = {"P:wait_empty", "P:issue", "", "", "M:wait_tempty", "M:wait_full", "M:issue", "M:commit",
+                                  "E:prefetch", "E:wait_tfull", "E:ld+arrive", "E:work"};
+            printf("          cycles/tile (CTA 0):");
+            for (int k = 0; k < 12; ++k)
+                if (nm[k][0]) printf(" %s=%.0f", nm[k], hp[k] / per);
+            printf("\n");
+        }
+    }
+    cudaFree(d_prof);
+    check_err_flag(name);
+    cudaFree(d_src); cudaFree(d_out); cudaFree(d_wpk);
+    if (d_res) cudaFree(d_res);
+}
+
 // hwgrad: dW of a 3x3 s1 conv over cat(nearest2x(low), src) given dZ, vs a CPU reference; output = packed [co][9][ctot]
 static void case_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout) {
     const int ctot = cup + cskip;
@@ -704,6 +855,25 @@ int main(int argc, char** argv) {
         case_hconv("hconv up32->16 2x32x64", 2, 32, 64, 32, 0, 16, false, true, true, false);
         case_hconv("hconv up64+skip64->32 2x32x32", 2, 32, 32, 64, 64, 32, false, true, true, true);
         case_hconv("hconv 32->64 (dgrad shape) 1x16x24", 1, 16, 24, 0, 32, 64, false, false, false, false);
+    }
+    if (want("tconv")) {
+        case_tconv("tconv 16->16 2x32x32", 2, 32, 32, 16, 16, false, false, true, true, true);
+        case_tconv("tconv 32->32 1x48x40 (partial tiles)", 1, 48, 40, 32, 32, false, false, true, true, true);
+        case_tconv("tconv 64->64 +res 3x24x24 (partial)", 3, 24, 24, 64, 64, false, true, true, true, true);
+        case_tconv("tconv 64->64 raw 5x64x64 (multi-tile/CTA)", 5, 64, 64, 64, 64, false, false, false, false, true);
+        case_tconv("tconv 16->16 +res 9x64x96 (multi-tile/CTA)", 9, 64, 96, 16, 16, false, true, true, true, true);
+        case_tconv("tconv 32->64 (dgrad shape) 1x16x24", 1, 16, 24, 32, 64, false, false, false, false, false);
+        case_tconv("tconv 64->32 2x16x8 (narrow)", 2, 16, 8, 64, 32, false, false, true, true, true);
+        case_tconv("tconv parity up32->16 2x32x64", 2, 32, 64, 32, 16, true, false, true, true, true);
+        case_tconv("tconv parity up32->16 7x96x80 (multi-tile, partial)", 7, 96, 80, 32, 16, true, false, true, true, true);
+        case_tconv("tconv parity up64->32 1x32x32", 1, 32, 32, 64, 32, true, false, true, true, false);
+    }
+    if (want("tbench")) {
+        bench_tconv("D4c2 16->16 @512^2 x32", 32, 512, 512, 16, 16, false, false, 5);
+        bench_tconv("D3c2 32->32 @256^2 x32", 32, 256, 256, 32, 32, false, false, 5);
+        bench_tconv("L1 64->64 @128^2 x32", 32, 128, 128, 64, 64, false, false, 10);
+        bench_tconv("L1 64->64 +res @128^2 x32", 32, 128, 128, 64, 64, false, true, 10);
+        bench_tconv("D4c1 up32->16 @512^2 x32 (parity)", 32, 512, 512, 32, 16, true, false, 5);
     }
     if (want("bench")) {
         bench_conv("L1 3x3 64->64 @128^2 x32", 32, 128, 128, 64, 64, 3, 1, 20);

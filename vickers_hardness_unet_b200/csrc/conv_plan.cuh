@@ -7,6 +7,7 @@
 #include "hconv.cuh"
 #include "hwgrad.cuh"
 #include "igemm.cuh"
+#include "tconv.cuh"
 #include "tmap.cuh"
 
 namespace ub {
@@ -224,6 +225,122 @@ inline cudaError_t hconv_launch(const HconvLaunch& L, cudaStream_t st) {
     }
     if (L.occ == 2) hconv_kernel<2><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
     else hconv_kernel<1><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ tconv (TMA halo conv)
+struct TconvLaunch {
+    CUtensorMap a;
+    TconvParams p;
+    int grid = 0;
+    uint32_t smem = 0;
+    int occ = 1, iph = 1;
+};
+
+// plain mode: 3x3/s1 conv src[N,H,W,cin] -> out[N,H,W,cout]; parity mode (low_res != 0): src is the LOW-RES tensor
+// [N,H/2,W/2,cin] and the conv is nearest-2x-upsample + 3x3 (weights = PK_HPAR parity-folded 2x2 taps).
+inline bool tconv_ok(int cin, int cout, bool parity) {
+    if (!(cout == 16 || cout == 32 || cout == 64)) return false;
+    if (!(cin == 16 || cin == 32 || cin == 64)) return false;
+    if (parity && cout > 32) return false;  // 4 accumulators x cout x >= 2 sets must fit the TMEM budget
+    return true;
+}
+inline long long tconv_w_elems(int cin, int cout, bool parity) { return (parity ? 16ll : 9ll) * cin * cout; }
+
+inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool parity, const void* wpk, int cout, int N,
+                               int H, int W, void* out, const EpilogueDesc& ep, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    TconvParams& P = L.p;
+    if (!tconv_ok(cin, cout, parity)) return "tconv: unsupported channel configuration";
+    if (parity && ((H | W) & 1)) return "tconv: parity mode needs even H, W";
+    if (ep.residual.ptr && (ep.residual.sW != cout || ep.residual.sH != (long long)W * cout ||
+                            ep.residual.sN != (long long)H * W * cout))
+        return "tconv: residual must be a dense NHWC tensor of the output's shape";
+    const uint32_t row_bytes = cin * 2;
+    P.H = H; P.W = W; P.N = N;
+    P.mode = parity ? 1 : 0;
+    P.cin = cin; P.cout = cout;
+    int nt;
+    if (parity) nt = 4;
+    else {
+        nt = cout == 16 ? 4 : 2;
+        while (nt > 1 && 8 * (nt / 2) >= W) nt /= 2;  // narrow images: do not allocate sub-tiles that are all padding
+    }
+    P.nt = nt;
+    const int src_h = parity ? H / 2 : H, src_w = parity ? W / 2 : W;
+    P.tiles_w = parity ? (src_w + 7) / 8 : (W + 8 * nt - 1) / (8 * nt);
+    P.tiles_h = (src_h + 15) / 16;
+    P.halo_w = parity ? 10 : 8 * nt + 2;
+    P.tx_bytes = (uint32_t)P.halo_w * kTcHaloH * row_bytes;
+    P.stage_bytes = (P.tx_bytes + 1023u) & ~1023u;
+    P.w_bytes = (uint32_t)tconv_w_elems(cin, cout, parity) * 2;
+    P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
+    P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.stats = ep.stats;
+    P.err = err;
+    // occupancy: two CTAs per SM (8 epilogue warps each) when TMEM (<= 256 columns each), the accumulator column
+    // groups (<= 4: two per epilogue thread) and shared memory allow; otherwise one CTA with 16 epilogue warps
+    const int items = nt * (cout / 16);
+    if (items > 8) return "tconv: too many accumulator column groups";
+    const int acc_cols = nt * cout;
+    L.occ = 1;
+    int stages = 0;
+    if (items <= 4 && 2 * acc_cols <= 256) {
+        for (int st = 4; st >= 2; --st)
+            if (2 * (tconv_smem(P.w_bytes, P.stage_bytes, st).total + 1024 + 1024) <= 232448u) {
+                L.occ = 2;
+                stages = st;
+                break;
+            }
+    }
+    if (L.occ == 1)
+        for (int st = 6; st >= 2; --st)
+            if (tconv_smem(P.w_bytes, P.stage_bytes, st).total + 1024 <= 232448u) {
+                stages = st;
+                break;
+            }
+    const int groups = tc_epi_warps(L.occ) / 4;
+    L.iph = (items + groups - 1) / groups;
+    if (stages < 2) return "tconv: does not fit in shared memory";
+    P.stages = stages;
+    const int tmem_budget = L.occ == 2 ? 256 : 512;
+    P.nacc = tmem_budget / acc_cols >= 4 ? 4 : (tmem_budget / acc_cols >= 2 ? 2 : 0);
+    if (!P.nacc) return "tconv: accumulators do not fit in TMEM";
+    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, stages).total + 1024;
+    {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)src_w, (uint64_t)src_h, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)src_w * cin * 2, (uint64_t)src_h * src_w * cin * 2};
+        uint32_t box[4] = {(uint32_t)cin, (uint32_t)P.halo_w, (uint32_t)kTcHaloH, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.a, src, 4, dims, str, box, es, swizzle_for_bytes(row_bytes));
+        if (!e.empty()) return "tconv A map: " + e;
+    }
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    const int slots = num_sms * L.occ;
+    const int waves = (total_tiles + slots - 1) / slots;
+    L.grid = (total_tiles + waves - 1) / waves;
+    return "";
+}
+
+inline cudaError_t tconv_launch(const TconvLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (L.occ == 2) {
+        if (L.iph == 1) tconv_kernel<2, 1><<<L.grid, tc_threads(2), L.smem, st>>>(L.a, L.p);
+        else tconv_kernel<2, 2><<<L.grid, tc_threads(2), L.smem, st>>>(L.a, L.p);
+    } else {
+        if (L.iph == 1) tconv_kernel<1, 1><<<L.grid, tc_threads(1), L.smem, st>>>(L.a, L.p);
+        else tconv_kernel<1, 2><<<L.grid, tc_threads(1), L.smem, st>>>(L.a, L.p);
+    }
     return cudaGetLastError();
 }
 

@@ -8,7 +8,7 @@
 
 namespace ub {
 
-enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5 };
+enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5, PK_HPAR = 6 };
 
 struct PackEntry {
     int type;
@@ -77,6 +77,26 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int rs = int((E.taps >> (4 * t)) & 0xF), r = rs >> 2, s = rs & 3;
             dst = (long long)ci * E.d + E.pad + t * E.cout + co;
             return w[(((long long)co * E.a + E.b + ci) * R + r) * S + s];
+        }
+        case PK_HPAR: {  // tconv parity operand: cout = rows, cin = cup (<= 64), a = cin_total of the OIHW tensor.
+            // logical [parity][a*2+b][co][c] = sum of the 3x3 taps that land on low-res neighbour (a, b) for output
+            // parity (ph, pw) (same row/column sets as PK_DEC1), 16-byte chunks swizzled like PK_HCONV
+            const int cup = E.cin;
+            const unsigned row_bytes = cup * 2;
+            const int c = int(i % cup);
+            long long t = i / cup;
+            const int co = int(t % E.cout);
+            t /= E.cout;
+            const int ab = int(t % 4), par = int(t / 4);
+            const int aa = ab >> 1, bb = ab & 1, ph = par >> 1, pw = par & 1;
+            const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
+            const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
+            float v = 0.f;
+            for (int r = r0; r <= r1; ++r)
+                for (int s = s0; s <= s1; ++s) v += w[((long long)co * E.a + c) * 9 + r * 3 + s];
+            const unsigned off = (unsigned)(i * 2);
+            dst = (off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4)) / 2;
+            return v;
         }
         default: {  // PK_HCONV: cout = rows, cin = ctot, a = dim1_total, b = ci0, c = transposed (see pack_hconv_w_kernel)
             const int ctot = E.cin, cpr = ctot < 64 ? ctot : 64, nblk = ctot > 64 ? ctot / 64 : 1;

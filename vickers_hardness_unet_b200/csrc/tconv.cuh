@@ -1,0 +1,424 @@
+// TMA-fed halo-resident 3x3 / stride-1 / pad-1 convolution on tcgen05 (sm_100a), second generation of hconv.cuh for
+// the narrow, high-resolution layers (Cin, Cout <= 64): encoder.layer1, decoder blocks 2-4 conv2, their data gradients,
+// and — in "parity" mode — decoder.blocks.4.conv1, whose nearest-2x upsample is folded into four 2x2-tap convolutions
+// on the low-resolution tensor.
+//
+// What the role-cycle counters of hconv.cuh showed on a B200 (profiles/r1s3_hconv_role_cycles.txt): with 128-pixel
+// tiles every producer -> MMA -> epilogue hand-off costs ~1000 cycles per tile per CTA (mbarrier round trips, tcgen05
+// fences, per-tile address arithmetic of single warps) while the tile's MMAs need 300-1700 and its HBM traffic 350;
+// and the cp.async halo loader is issue-bound for wide rows.  Hence here:
+//   * one pipeline step covers NT = 2..4 sub-tiles of 128 output pixels (a 16..32 x 16 output rectangle, or the four
+//     output parities of an 8 x 16 low-res tile): one hand-off per 256..512 pixels, halo overhead 1.2x instead of 1.4x,
+//   * the halo is ONE 4-D TMA box load [C, 8*NT+2, 18, 1] issued by one thread: out-of-bounds zero fill is the conv
+//     padding, the hardware swizzle writes the K-major operand layout, completion is an mbarrier transaction count
+//     (no proxy fence, no producer warps),
+//   * a tap is a whole-row shift of the A descriptor's start address inside the resident halo (fully unrolled issue
+//     loop on the uniform datapath); the weights of all taps stay resident in smem,
+//   * 8 or 16 epilogue warps (two / four per TMEM lane quadrant) split the sub-tiles / channel groups, batch their TMEM loads,
+//     prefetch the residual before waiting for the accumulator and store straight from registers.
+// Roles: warp 0 = TMA producer, warp 1 = tcgen05 issuer + TMEM owner, warps 2.. = epilogue.
+#pragma once
+#include "hconv.cuh"
+#include "ptx.cuh"
+
+namespace ub {
+
+// epilogue warps per CTA: 8 when two CTAs share an SM, 16 (four per TMEM lane quadrant) when one CTA owns it
+__host__ __device__ constexpr int tc_epi_warps(int occ) { return occ == 2 ? 8 : 16; }
+__host__ __device__ constexpr int tc_threads(int occ) { return 64 + 32 * tc_epi_warps(occ); }
+constexpr int kTcHaloH = 18;        // 16 output rows + 2
+
+struct TconvParams {
+    int H, W, N;                    // OUTPUT extent
+    int mode;                       // 0: plain 3x3 over src[N,H,W,cin]; 1: parity (src = low-res [N,H/2,W/2,cin], 2x2 taps)
+    int nt;                         // accumulators (sub-tiles) per pipeline step
+    int tiles_w, tiles_h;           // tile grid per image (plain: 8*nt x 16 output px; parity: 8 x 16 low-res px)
+    int cin, cout;
+    int halo_w;                     // halo pixels per row
+    uint32_t stage_bytes, tx_bytes; // smem per stage (1 KB multiple) / bytes one halo box delivers
+    int stages, nacc;
+    uint32_t w_bytes;
+    const __nv_bfloat16* wpk;       // resident weights, pre-swizzled rows of cin channels (pack_hconv_w / PK_HPAR)
+    const float* scale;
+    const float* shift;
+    int relu;
+    __nv_bfloat16* out;             // [N, H, W, cout]
+    const __nv_bfloat16* residual;  // same shape or nullptr
+    float* stats;                   // [gridDim.x][cout][2] or nullptr
+    int* err;
+    long long* prof;                // selftest only: [grid][16] cycle counters per role phase (dbg & 8)
+    int dbg;                        // selftest only: 1 = skip halo loads, 2 = skip MMA issue, 4 = skip epilogue math + stores
+};
+
+struct TconvSmem {
+    uint32_t ss_off, cstat_off, bar_off, w_off, halo_off, total;
+};
+__host__ __device__ inline TconvSmem tconv_smem(uint32_t w_bytes, uint32_t stage_bytes, int stages) {
+    TconvSmem s;
+    s.ss_off = 0;                                  // scale[64], shift[64]
+    s.cstat_off = 512;                             // [<= 16 epilogue warps][64 ch][2]
+    s.bar_off = s.cstat_off + 16 * 128 * 4;        // 8704
+    s.w_off = 9216;
+    s.halo_off = (s.w_off + w_bytes + 1023u) & ~1023u;
+    s.total = s.halo_off + stages * stage_bytes;
+    return s;
+}
+
+// All tcgen05.mma of one pipeline step, fully unrolled over taps and 16-channel K steps so that every descriptor is a
+// uniform base plus a compile-time multiple of the (uniform) row pitch: the issuing thread's instruction stream stays on
+// the uniform datapath (an offset table read from shared memory costs an R2UR round trip per MMA: 130 instead of 55
+// cycles per MMA measured).  KS = cin / 16; rows are cin*2 bytes; pitch16 = halo row pitch in 16-byte units.
+template <int KS>
+__device__ __forceinline__ void tc_issue_plain(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t pitch16,
+                                               uint32_t cout, uint32_t idesc, int nt) {
+    constexpr uint32_t kRow16 = KS * 2;                      // row bytes / 16
+    const uint32_t b_tap = cout * kRow16;                    // one tap's weight slab in 16-byte units
+    for (int s = 0; s < nt; ++s) {
+        const uint64_t a_s = a_base + (uint32_t)(8 * s) * kRow16;
+        const uint32_t d = d_tmem + s * cout;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const uint64_t ad = a_s + (uint32_t)(tap / 3) * pitch16 + (uint32_t)((tap % 3) * kRow16 + kk * 2);
+                const uint64_t bd = b_base + (uint32_t)tap * b_tap + (uint32_t)(kk * 2);
+                if (tap == 0 && kk == 0) umma_bf16_c<false>(d, ad, bd, idesc);
+                else umma_bf16_c<true>(d, ad, bd, idesc);
+            }
+        }
+    }
+}
+// parity mode: accumulator s = (ph, pw); low-res neighbour (a, b) sits at halo pixel (a + ph, b + pw)
+template <int KS>
+__device__ __forceinline__ void tc_issue_parity(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t pitch16,
+                                                uint32_t cout, uint32_t idesc) {
+    constexpr uint32_t kRow16 = KS * 2;
+    const uint32_t b_tap = cout * kRow16;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t d = d_tmem + s * cout;
+#pragma unroll
+        for (int ab = 0; ab < 4; ++ab) {
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const uint64_t ad = a_base + (uint32_t)((ab >> 1) + (s >> 1)) * pitch16 +
+                                    (uint32_t)(((ab & 1) + (s & 1)) * kRow16 + kk * 2);
+                const uint64_t bd = b_base + (uint32_t)(s * 4 + ab) * b_tap + (uint32_t)(kk * 2);
+                if (ab == 0 && kk == 0) umma_bf16_c<false>(d, ad, bd, idesc);
+                else umma_bf16_c<true>(d, ad, bd, idesc);
+            }
+        }
+    }
+}
+
+// kIph = accumulator column groups (16 channels of one sub-tile) each epilogue thread handles per pipeline step
+template <int kOcc, int kIph>
+__global__ void __launch_bounds__(tc_threads(kOcc), kOcc)
+tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TconvParams P) {
+    constexpr int kEw = tc_epi_warps(kOcc), kTcThreads = tc_threads(kOcc);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_addr);
+    const TconvSmem L = tconv_smem(P.w_bytes, P.stage_bytes, P.stages);
+    const uint32_t bar0 = base + L.bar_off;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (P.stages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * P.stages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * P.stages + P.nacc + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bar_off + (2 * P.stages + 2 * P.nacc) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = P.tiles_w * P.tiles_h * P.N;
+    const int acc_cols = P.nt * P.cout;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(P.nacc * acc_cols)) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        for (int s = 0; s < P.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < P.nacc; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), kEw);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
+        tmem_relinquish();
+    }
+    {
+        float* ss = reinterpret_cast<float*>(sm + L.ss_off);
+        float* cst = reinterpret_cast<float*>(sm + L.cstat_off);
+        for (int c = threadIdx.x; c < 64; c += kTcThreads) {
+            ss[c] = (P.scale && c < P.cout) ? P.scale[c] : 1.f;
+            ss[64 + c] = (P.shift && c < P.cout) ? P.shift[c] : 0.f;
+        }
+        for (int c = threadIdx.x; c < kEw * 128; c += kTcThreads) cst[c] = 0.f;
+        // resident weights: linear copy (the array is pre-swizzled relative to a 1 KB-aligned origin)
+        const uint4* wsrc = reinterpret_cast<const uint4*>(P.wpk);
+        uint4* wdst = reinterpret_cast<uint4*>(sm + L.w_off);
+        for (uint32_t i = threadIdx.x; i < P.w_bytes / 16; i += kTcThreads) wdst[i] = __ldg(wsrc + i);
+        fence_async_smem();  // generic-proxy writes of the weights -> visible to the tensor core (async proxy)
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t row_bytes = (uint32_t)P.cin * 2;
+    const bool prof = (P.dbg & 8) != 0;
+    long long t_wait = 0, t_work = 0, t_a = 0, t_b = 0, tc = prof ? clock64() : 0;
+#define UB_TC_TICK(var)                         \
+    if (prof) {                                 \
+        const long long now_ = clock64();       \
+        var += now_ - tc;                       \
+        tc = now_;                              \
+    }
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (HcTileIter it(P.tiles_w, P.tiles_h, total_tiles); it.valid(); it.next()) {
+                if (!mbar_wait(empty_bar(stage), phase ^ 1)) {
+                    atomicExch(P.err, 31);
+                    break;
+                }
+                UB_TC_TICK(t_wait)
+                const int x0 = (P.mode ? it.tw * 8 : it.tw * 8 * P.nt) - 1, y0 = it.th * 16 - 1;
+                if (P.dbg & 1) {
+                    mbar_arrive(full_bar(stage));
+                } else {
+                    mbar_expect_tx(full_bar(stage), P.tx_bytes);
+                    tma_load_4d(base + L.halo_off + stage * P.stage_bytes, &tmA, full_bar(stage), 0, x0, y0, it.tn);
+                }
+                UB_TC_TICK(t_work)
+                if (++stage == P.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (prof) {
+                P.prof[blockIdx.x * 16 + 0] = t_wait;
+                P.prof[blockIdx.x * 16 + 1] = t_work;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one thread)
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            const uint32_t idesc = umma_idesc_bf16(128, P.cout, 0, 0);
+            const uint32_t layout = row_bytes == 32 ? 6u : (row_bytes == 64 ? 4u : 2u);
+            const uint64_t b_base = umma_desc(base + L.w_off, 16, 8 * row_bytes, layout);
+            const uint64_t a_base0 = umma_desc(base + L.halo_off, 16, P.halo_w * row_bytes, layout);
+            const uint32_t pitch16 = ((uint32_t)P.halo_w * row_bytes) >> 4;
+            const int ks = P.cin >> 4;
+            for (int n = blockIdx.x; n < total_tiles; n += gridDim.x) {
+                if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1)) {
+                    atomicExch(P.err, 32);
+                    break;
+                }
+                UB_TC_TICK(t_a)
+                if (!mbar_wait(full_bar(stage), phase)) {
+                    atomicExch(P.err, 33);
+                    break;
+                }
+                tc_fence_after();
+                UB_TC_TICK(t_wait)
+                const uint64_t a_base = a_base0 + (uint64_t)((stage * P.stage_bytes) >> 4);
+                const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                if (!(P.dbg & 2)) {
+                    if (P.mode) {
+                        switch (ks) {
+                            case 1: tc_issue_parity<1>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
+                            case 2: tc_issue_parity<2>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
+                            default: tc_issue_parity<4>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
+                        }
+                    } else {
+                        switch (ks) {
+                            case 1: tc_issue_plain<1>(d_tmem, a_base, b_base, pitch16, P.cout, idesc, P.nt); break;
+                            case 2: tc_issue_plain<2>(d_tmem, a_base, b_base, pitch16, P.cout, idesc, P.nt); break;
+                            default: tc_issue_plain<4>(d_tmem, a_base, b_base, pitch16, P.cout, idesc, P.nt); break;
+                        }
+                    }
+                }
+                UB_TC_TICK(t_work)
+                umma_commit(empty_bar(stage));
+                umma_commit(tfull_bar(acc));
+                UB_TC_TICK(t_b)
+                if (++stage == P.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                if (++acc == P.nacc) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+            if (prof) {
+                P.prof[blockIdx.x * 16 + 4] = t_a;
+                P.prof[blockIdx.x * 16 + 5] = t_wait;
+                P.prof[blockIdx.x * 16 + 6] = t_work;
+                P.prof[blockIdx.x * 16 + 7] = t_b;
+            }
+        }
+    } else {
+        // ================================================================= epilogue (kEw warps): thread = pixel of a sub-tile
+        const int e = warp - 2;
+        const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+        const int half = e >> 2;                       // which share of the accumulator column groups
+        const int row = q * 32 + lane;
+        const int wl = row & 7, hl = row >> 3;
+        const int cgs = P.cout >> 4;                   // 16-channel groups per sub-tile
+        const int items = P.nt * cgs;
+        const int i0 = half * kIph;                    // this thread's items: [i0, min(i0 + kIph, items))
+        const float* ss = reinterpret_cast<const float*>(sm + L.ss_off);
+        float* cst = reinterpret_cast<float*>(sm + L.cstat_off) + e * 128;
+        // per-item constants: sub-tile, channel group, pixel offset inside the tile
+        int it_s[kIph], it_c0[kIph], it_dh[kIph], it_dw[kIph];
+#pragma unroll
+        for (int k = 0; k < kIph; ++k) {
+            const int i = i0 + k < items ? i0 + k : items - 1;
+            it_s[k] = i / cgs;
+            it_c0[k] = (i - it_s[k] * cgs) * 16;
+            if (P.mode) {
+                it_dh[k] = 2 * hl + (it_s[k] >> 1);
+                it_dw[k] = 2 * wl + (it_s[k] & 1);
+            } else {
+                it_dh[k] = hl;
+                it_dw[k] = 8 * it_s[k] + wl;
+            }
+        }
+        const int n_mine = items - i0 < kIph ? (items - i0 > 0 ? items - i0 : 0) : kIph;
+        const int th_px = P.mode ? 32 : 16, tw_px = P.mode ? 16 : 8 * P.nt;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (HcTileIter it(P.tiles_w, P.tiles_h, total_tiles); it.valid(); it.next()) {
+            const int h0 = it.th * th_px, w0 = it.tw * tw_px;
+            size_t off[kIph];
+            bool valid[kIph];
+            uint4 rv[kIph][2];
+#pragma unroll
+            for (int k = 0; k < kIph; ++k) {
+                const int ph = h0 + it_dh[k], pw = w0 + it_dw[k];
+                valid[k] = k < n_mine && ph < P.H && pw < P.W;
+                off[k] = (((size_t)it.tn * P.H + ph) * P.W + pw) * P.cout + it_c0[k];
+                if (P.residual && valid[k]) {  // issued before the accumulator wait: the loads overlap the tile's MMAs
+                    rv[k][0] = __ldg(reinterpret_cast<const uint4*>(P.residual + off[k]));
+                    rv[k][1] = __ldg(reinterpret_cast<const uint4*>(P.residual + off[k]) + 1);
+                }
+            }
+            UB_TC_TICK(t_a)
+            if (!mbar_wait_warp(tfull_bar(acc), acc_phase, lane)) {
+                atomicExch(P.err, 34);
+                break;
+            }
+            tc_fence_after();
+            UB_TC_TICK(t_wait)
+            uint32_t r[kIph][16];
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * acc_cols;
+#pragma unroll
+            for (int k = 0; k < kIph; ++k) tmem_ld16(taddr + it_s[k] * P.cout + it_c0[k], r[k]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: hand it back to the MMA warp
+            UB_TC_TICK(t_b)
+#pragma unroll
+            for (int k = 0; k < kIph; ++k) {
+                if (k >= n_mine || (P.dbg & 4)) break;
+                const int c0 = it_c0[k];
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + 4 * j);
+                    const float4 sh = *reinterpret_cast<const float4*>(ss + 64 + c0 + 4 * j);
+                    v[4 * j + 0] = __uint_as_float(r[k][4 * j + 0]) * sc.x + sh.x;
+                    v[4 * j + 1] = __uint_as_float(r[k][4 * j + 1]) * sc.y + sh.y;
+                    v[4 * j + 2] = __uint_as_float(r[k][4 * j + 2]) * sc.z + sh.z;
+                    v[4 * j + 3] = __uint_as_float(r[k][4 * j + 3]) * sc.w + sh.w;
+                }
+                if (P.residual && valid[k]) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        v[j * 8 + 0] += bf16_lo(rv[k][j].x); v[j * 8 + 1] += bf16_hi(rv[k][j].x);
+                        v[j * 8 + 2] += bf16_lo(rv[k][j].y); v[j * 8 + 3] += bf16_hi(rv[k][j].y);
+                        v[j * 8 + 4] += bf16_lo(rv[k][j].z); v[j * 8 + 5] += bf16_hi(rv[k][j].z);
+                        v[j * 8 + 6] += bf16_lo(rv[k][j].w); v[j * 8 + 7] += bf16_hi(rv[k][j].w);
+                    }
+                }
+                if (P.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                uint4 o[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    o[j].x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+                    o[j].y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+                    o[j].z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+                    o[j].w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                }
+                if (valid[k]) {
+                    reinterpret_cast<uint4*>(P.out + off[k])[0] = o[0];
+                    reinterpret_cast<uint4*>(P.out + off[k])[1] = o[1];
+                }
+                if (P.stats) {
+                    // statistics of the bf16 values just stored (masked pixels contribute 0); fixed summation order
+                    float s1[16], s2[16];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t w4[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const float lo = valid[k] ? bf16_lo(w4[m]) : 0.f, hi = valid[k] ? bf16_hi(w4[m]) : 0.f;
+                            s1[j * 8 + 2 * m] = lo; s1[j * 8 + 2 * m + 1] = hi;
+                            s2[j * 8 + 2 * m] = lo * lo; s2[j * 8 + 2 * m + 1] = hi * hi;
+                        }
+                    }
+                    const float t1 = warp_reduce16(s1, lane), t2 = warp_reduce16(s2, lane);
+                    if (lane < 16) {
+                        cst[2 * (c0 + lane)] += t1;
+                        cst[2 * (c0 + lane) + 1] += t2;
+                    }
+                }
+            }
+            UB_TC_TICK(t_work)
+            if (++acc == P.nacc) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (prof && threadIdx.x == 64) {
+            P.prof[blockIdx.x * 16 + 8] = t_a;
+            P.prof[blockIdx.x * 16 + 9] = t_wait;
+            P.prof[blockIdx.x * 16 + 10] = t_b;
+            P.prof[blockIdx.x * 16 + 11] = t_work;
+        }
+        if (P.stats) {
+            named_bar_sync(1, 32 * kEw);
+            const float* call = reinterpret_cast<const float*>(sm + L.cstat_off);
+            float* dst = P.stats + static_cast<size_t>(blockIdx.x) * P.cout * 2;
+            for (int j = threadIdx.x - 64; j < 2 * P.cout; j += 32 * kEw) {
+                float a = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < kEw; ++w8) a += call[w8 * 128 + j];
+                dst[j] = a;
+            }
+        }
+    }
+#undef UB_TC_TICK
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace ub

@@ -396,7 +396,14 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         StatSegs segs;
         memset(&segs, 0, sizeof(segs));
         segs.n = 1; segs.ptr[0] = plan.stat_part;
-        if (c.hc && u.conv != S.stem) {
+        if (c.tc == 1 && u.conv != S.stem) {
+            TconvLaunch TL;
+            std::string e = tconv_build(TL, in, c.cin, false, ctx->wpk + c.wpk, c.cout, N, u.Hin, u.Win, u.z, ep, ctx->d_err,
+                                        SM);
+            if (!e.empty()) return c.name + ": " + e;
+            add_f("conv_fwd:" + c.name, [TL](cudaStream_t st) { return tconv_launch(TL, st); });
+            segs.rows[0] = TL.grid;
+        } else if (c.hc && u.conv != S.stem) {
             HconvLaunch HL;
             std::string e = hconv_build(HL, nullptr, 0, in, c.cin, ctx->wpk + c.wpk, c.cout, N, u.Hin, u.Win, u.z, ep,
                                         ctx->d_err, SM);
@@ -473,7 +480,17 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             const Unit u1 = plan.units[r.u1];
             StatSegs segs;
             memset(&segs, 0, sizeof(segs));
-            if (S.convs[d.c1].hc) {
+            if (S.convs[d.c1].tc == 2) {
+                // nearest-2x upsample folded into four parity convolutions on the low-res tensor (tconv.cuh)
+                EpilogueDesc ep;
+                ep.stats = plan.stat_part;
+                TconvLaunch TL;
+                err = tconv_build(TL, cur, d.cup, true, ctx->wpk + S.convs[d.c1].wpk, d.cout, N, 2 * h, 2 * w, u1.z, ep,
+                                  ctx->d_err, SM);
+                if (!err.empty()) return S.convs[d.c1].name + ": " + err;
+                add_f("conv_fwd:" + S.convs[d.c1].name, [TL](cudaStream_t st) { return tconv_launch(TL, st); });
+                segs.n = 1; segs.ptr[0] = ep.stats; segs.rows[0] = TL.grid;
+            } else if (S.convs[d.c1].hc) {
                 // fused nearest-2x upsample + concat in the halo loader: one launch, original 3x3 weights
                 EpilogueDesc ep;
                 ep.stats = plan.stat_part;
@@ -636,6 +653,14 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         t.cin = c.cout; t.cout = c.cin; t.k = 3; t.stride = 1;
         EpilogueDesc ep;
         if (residual) ep.residual = nhwc_view(residual, N, u.Hin, u.Win, c.cin);
+        if (tconv_ok(c.cout, c.cin, false)) {
+            TconvLaunch TL;
+            std::string e = tconv_build(TL, u.dz, c.cout, false, T.wdg + T.wdg_off[u.conv], c.cin, N, u.Ho, u.Wo, out, ep,
+                                        ctx->d_err, SM);
+            if (!e.empty()) return c.name + " dgrad: " + e;
+            add_b(stage, "dgrad:" + c.name, [TL](cudaStream_t st) { return tconv_launch(TL, st); });
+            return "";
+        }
         if (hconv_stages(0, c.cout, c.cin)) {
             HconvLaunch HL;
             std::string e = hconv_build(HL, nullptr, 0, u.dz, c.cout, T.wdg + T.wdg_off[u.conv], c.cin, N, u.Ho, u.Wo, out,
@@ -715,7 +740,13 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             ConvRef t;
             t.cin = d.cout; t.cout = d.cskip; t.k = 3; t.stride = 1;
             EpilogueDesc ep;
-            if (hconv_stages(0, d.cout, d.cskip)) {
+            if (tconv_ok(d.cout, d.cskip, false)) {
+                TconvLaunch TL;
+                err = tconv_build(TL, u1.dz, d.cout, false, T.wdg + T.wdg_off[d.c1], d.cskip, N, u1.Ho, u1.Wo, r.d_skip, ep,
+                                  ctx->d_err, SM);
+                if (!err.empty()) return c1.name + " dskip: " + err;
+                add_b(0, "dgrad_skip:" + c1.name, [TL](cudaStream_t st) { return tconv_launch(TL, st); });
+            } else if (hconv_stages(0, d.cout, d.cskip)) {
                 HconvLaunch HL;
                 err = hconv_build(HL, nullptr, 0, u1.dz, d.cout, T.wdg + T.wdg_off[d.c1], d.cskip, N, u1.Ho, u1.Wo, r.d_skip,
                                   ep, ctx->d_err, SM);

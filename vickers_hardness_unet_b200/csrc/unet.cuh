@@ -43,6 +43,7 @@ struct ConvRef {
     long long wpk_elems = 0;
     int hc = 0;           // > 0: runs on the halo-resident kernel (hconv.cuh) with this many pipeline stages
     int hc_cup = 0;       // hconv: channels taken from the nearest-2x up-sampled low-res source (decoder conv1)
+    int tc = 0;           // 1: runs on the TMA halo kernel (tconv.cuh), 2: its parity mode (up-sampled input, no skip)
 };
 
 struct NetSpec {
@@ -148,6 +149,11 @@ struct NetSpec {
                 c.hc = hconv_stages(cup, c.cin - cup, c.cout);
                 c.hc_cup = c.hc ? cup : 0;
                 if (c.hc && 9ll * c.cin * c.cout > n) n = 9ll * c.cin * c.cout;
+                if (c.hc && cup == 0 && tconv_ok(c.cin, c.cout, false)) c.tc = 1;
+                if (c.hc && cup == c.cin && tconv_ok(c.cin, c.cout, true)) {
+                    c.tc = 2;
+                    if (tconv_w_elems(c.cin, c.cout, true) > n) n = tconv_w_elems(c.cin, c.cout, true);
+                }
             }
             (void)is_dec1;
             c.wpk = wpk_total;
@@ -282,7 +288,10 @@ inline std::string ctx_build_pack_tables(Ctx* ctx) {
         const ConvRef& c = S.convs[i];
         if ((int)i == S.head) continue;
         PackEntry e;
-        if (c.hc) {
+        if (c.tc == 2) {
+            e = pk_entry(PK_HPAR, c.w, c.wpk, tconv_w_elems(c.cin, c.cout, true));
+            e.cout = c.cout; e.cin = c.cin; e.a = c.cin; e.b = 0; e.c = 0;
+        } else if (c.hc) {
             e = pk_entry(PK_HCONV, c.w, c.wpk, 9ll * c.cin * c.cout);
             e.cout = c.cout; e.cin = c.cin; e.a = c.cin; e.b = 0; e.c = 0;
         } else if ((int)i == S.stem) {
@@ -466,6 +475,14 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
 
     // 3x3 / 1x1 conv of the encoder or a decoder conv2: halo-resident kernel where it applies, tap-table kernel otherwise
     auto add_conv = [&](const ConvRef& c, const void* in, int hin, int win, void* out, const EpilogueDesc& ep) -> std::string {
+        if (c.tc == 1) {
+            TconvLaunch TL;
+            std::string e = tconv_build(TL, in, c.cin, false, ctx->wpk + c.wpk, c.cout, N, hin, win, out, ep, ctx->d_err,
+                                        ctx->num_sms);
+            if (!e.empty()) return c.name + ": " + e;
+            plan.steps.push_back({[TL](cudaStream_t st) { return tconv_launch(TL, st); }, c.name, 1});
+            return "";
+        }
         if (c.hc) {
             HconvLaunch HL;
             std::string e = hconv_build(HL, nullptr, 0, in, c.cin, ctx->wpk + c.wpk, c.cout, N, hin, win, out, ep, ctx->d_err,
@@ -536,7 +553,14 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         __nv_bfloat16* t = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         __nv_bfloat16* o = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         if (!dry) {
-            if (c1.hc) {
+            if (c1.tc == 2) {
+                // nearest-2x upsample folded into four 2x2-tap parity convolutions on the low-res tensor: ONE launch
+                TconvLaunch TL;
+                err = tconv_build(TL, cur, d.cup, true, ctx->wpk + c1.wpk, d.cout, N, 2 * h, 2 * w, t, fold(c1.bn, 1),
+                                  ctx->d_err, ctx->num_sms);
+                if (!err.empty()) return c1.name + ": " + err;
+                plan.steps.push_back({[TL](cudaStream_t st) { return tconv_launch(TL, st); }, c1.name, 1});
+            } else if (c1.hc) {
                 // fused nearest-2x upsample + concat inside the halo loader: ONE launch, original 3x3 weights
                 HconvLaunch HL;
                 err = hconv_build(HL, cur, d.cup, skips[i], d.cskip, ctx->wpk + c1.wpk, d.cout, N, 2 * h, 2 * w, t,

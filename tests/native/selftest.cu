@@ -618,6 +618,114 @@ static void bench_tconv(const char* name, int N, int H, int W, int cin, int cout
     if (d_res) cudaFree(d_res);
 }
 
+// wconv: wide halo conv with streamed weights vs the CPU conv
+static void case_wconv(const char* name, int N, int H, int W, int cin, int cout, bool residual, bool relu, bool scale_shift,
+                       bool stats) {
+    HostT src(N, H, W, cin);
+    fill_rand_bf16(src.v, 1.0f);
+    std::vector<float> w((size_t)cout * cin * 9);
+    const float ws = 1.0f / sqrtf((float)cin * 9);
+    for (auto& x : w) x = bf16r(frand() * ws * 1.7f);
+    std::vector<float> sc(cout, 1.f), sh(cout, 0.f);
+    if (scale_shift)
+        for (int c = 0; c < cout; ++c) { sc[c] = 0.5f + 0.5f * fabsf(frand()); sh[c] = 0.1f * frand(); }
+    HostT res(N, H, W, cout);
+    if (residual) fill_rand_bf16(res.v, 1.0f);
+    HostT ref = cpu_conv(src, w, cout, 3, 1, 1);
+    for (size_t i = 0; i < ref.v.size(); ++i) {
+        float v = ref.v[i] * sc[i % cout] + sh[i % cout];
+        if (residual) v += res.v[i];
+        if (relu) v = fmaxf(v, 0.f);
+        ref.v[i] = v;
+    }
+    __nv_bfloat16* d_src = to_dev_bf16(src.v);
+    __nv_bfloat16* d_res = to_dev_bf16(res.v);
+    float* d_w = to_dev_f32(w);
+    float* d_sc = to_dev_f32(sc);
+    float* d_sh = to_dev_f32(sh);
+    __nv_bfloat16 *d_wpk, *d_out;
+    CK(cudaMalloc(&d_wpk, w.size() * 2));
+    CK(cudaMalloc(&d_out, ref.v.size() * 2));
+    CK(cudaMemset(d_out, 0xFF, ref.v.size() * 2));
+    pack_conv_w_kernel<<<256, 256>>>(d_w, d_wpk, cout, cin, 3, 3, 0);
+    float* d_stats = nullptr;
+    EpilogueDesc ep;
+    if (scale_shift) { ep.scale = d_sc; ep.shift = d_sh; }
+    ep.relu = relu;
+    if (residual) ep.residual = nhwc_view(d_res, N, H, W, cout);
+    if (stats) {
+        CK(cudaMalloc(&d_stats, (size_t)g_ctx->num_sms * cout * 2 * 4));
+        CK(cudaMemset(d_stats, 0, (size_t)g_ctx->num_sms * cout * 2 * 4));
+        ep.stats = d_stats;
+    }
+    WconvLaunch L;
+    std::string e = wconv_build(L, d_src, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %d smem %u bstages %d tiles %dx%dx%d n_tiles %d\n", name, L.grid, L.smem, L.p.bstages,
+           L.p.tiles_w, L.p.tiles_h, N, L.p.n_tiles);
+    CK(wconv_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+        report(name, compare(got, ref.v), 6e-3, got, ref.v, cout);
+        if (stats) {
+            std::vector<float> hs((size_t)L.grid * cout * 2);
+            CK(cudaMemcpy(hs.data(), d_stats, hs.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<float> gs(cout * 2, 0.f), rs(cout * 2, 0.f);
+            for (int b = 0; b < L.grid; ++b)
+                for (int j = 0; j < cout * 2; ++j) gs[j] += hs[(size_t)b * cout * 2 + j];
+            for (size_t i = 0; i < got.size(); ++i) {
+                rs[(i % cout) * 2] += got[i];
+                rs[(i % cout) * 2 + 1] += got[i] * got[i];
+            }
+            std::string nm = std::string(name) + " [stats]";
+            report(nm.c_str(), compare(gs, rs), 1e-4, gs, rs, 2);
+        }
+    }
+    cudaFree(d_src); cudaFree(d_res); cudaFree(d_w); cudaFree(d_sc); cudaFree(d_sh);
+    cudaFree(d_wpk); cudaFree(d_out);
+    if (d_stats) cudaFree(d_stats);
+}
+
+static void bench_wconv(const char* name, int N, int H, int W, int cin, int cout, int iters) {
+    const size_t in_e = (size_t)N * H * W * cin, out_e = (size_t)N * H * W * cout;
+    __nv_bfloat16 *d_in, *d_out, *d_wpk;
+    CK(cudaMalloc(&d_in, in_e * 2));
+    CK(cudaMalloc(&d_out, out_e * 2));
+    CK(cudaMalloc(&d_wpk, (size_t)cout * cin * 9 * 2));
+    CK(cudaMemset(d_in, 0x3C, in_e * 2));
+    CK(cudaMemset(d_wpk, 0x3C, (size_t)cout * cin * 9 * 2));
+    EpilogueDesc ep;
+    ep.relu = 1;
+    WconvLaunch L;
+    std::string e = wconv_build(L, d_in, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] bench %s: %s\n", name, e.c_str());
+        return;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) CK(wconv_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) CK(wconv_launch(L, 0));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double flops = 2.0 * N * H * W * (double)cout * cin * 9;
+    printf("[BENCH-WC] %-34s %8.1f us  %7.1f TFLOP/s  grid %d bstages %d\n", name, ms * 1e3, flops / ms * 1e-9, L.grid,
+           L.p.bstages);
+    check_err_flag(name);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_wpk);
+}
+
 // hwgrad: dW of a 3x3 s1 conv over cat(nearest2x(low), src) given dZ, vs a CPU reference; output = packed [co][9][ctot]
 static void case_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout) {
     const int ctot = cup + cskip;
@@ -867,6 +975,25 @@ int main(int argc, char** argv) {
         case_tconv("tconv parity up32->16 2x32x64", 2, 32, 64, 32, 16, true, false, true, true, true);
         case_tconv("tconv parity up32->16 7x96x80 (multi-tile, partial)", 7, 96, 80, 32, 16, true, false, true, true, true);
         case_tconv("tconv parity up64->32 1x32x32", 1, 32, 32, 64, 32, true, false, true, true, false);
+    }
+    if (want("wide")) {
+        case_wconv("wide 128->128 1x16x16", 1, 16, 16, 128, 128, false, true, true, true);
+        case_wconv("wide 64->128 2x24x40 (partial tiles)", 2, 24, 40, 64, 128, true, true, true, true);
+        case_wconv("wide 256->256 +res 3x32x32 (multi-item/CTA)", 3, 32, 32, 256, 256, true, true, true, true);
+        case_wconv("wide 256->512 raw 40x16x16 (multi-item/CTA)", 40, 16, 16, 256, 512, false, false, false, true);
+        case_wconv("wide 512->128 (dgrad shape) 2x16x16", 2, 16, 16, 512, 128, false, false, false, false);
+    }
+    if (want("xbench")) {
+        bench_wconv("L2 3x3 128->128 @64^2 x32", 32, 64, 64, 128, 128, 20);
+        bench_wconv("L3 3x3 256->256 @32^2 x32", 32, 32, 32, 256, 256, 20);
+        bench_wconv("L4 3x3 512->512 @16^2 x32", 32, 16, 16, 512, 512, 20);
+        bench_wconv("L3 3x3 256->256 @32^2 x16", 16, 32, 32, 256, 256, 20);
+        bench_wconv("L4 3x3 512->512 @16^2 x16", 16, 16, 16, 512, 512, 20);
+        bench_conv("igemm L2 3x3 128->128 @64^2 x32", 32, 64, 64, 128, 128, 3, 1, 20);
+        bench_conv("igemm L3 3x3 256->256 @32^2 x32", 32, 32, 32, 256, 256, 3, 1, 20);
+        bench_conv("igemm L4 3x3 512->512 @16^2 x32", 32, 16, 16, 512, 512, 3, 1, 20);
+        bench_conv("igemm L3 3x3 256->256 @32^2 x16", 16, 32, 32, 256, 256, 3, 1, 20);
+        bench_conv("igemm L4 3x3 512->512 @16^2 x16", 16, 16, 16, 512, 512, 3, 1, 20);
     }
     if (want("tbench")) {
         bench_tconv("D4c2 16->16 @512^2 x32", 32, 512, 512, 16, 16, false, false, 5);

@@ -1,5 +1,6 @@
 // Host-side description of one implicit-GEMM launch: tensor maps + IgemmParams + grid/smem sizing.
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -8,6 +9,7 @@
 #include "hwgrad.cuh"
 #include "igemm.cuh"
 #include "tconv.cuh"
+#include "wconv.cuh"
 #include "tmap.cuh"
 
 namespace ub {
@@ -63,6 +65,55 @@ inline int igemm_m_tiles(const View4& out) {
     return ((out.W + bw - 1) / bw) * ((out.H + bh - 1) / bh) * ((out.N + bn - 1) / bn);
 }
 
+inline cudaError_t igemm_set_attr() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    return cudaSuccess;
+}
+// Weight-tile multicast across a thread-block cluster is implemented and parity-tested but OFF by default: measured on
+// B200 (profiles/r1s3_igemm_cluster_ab.txt) it does not speed up the wide layers (L3 256->256: 43.9 us without, 44.8 us
+// with clusters of 4) because the limit is what ONE SM can ingest (~40 B/clk: A + B tile = 48 KB per 512 MMA cycles),
+// not the L2 read rate that multicast relieves.  wconv.cuh attacks the ingest instead.  UB_IGEMM_CLUSTER=1 enables it.
+inline bool igemm_cluster_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* v = getenv("UB_IGEMM_CLUSTER");
+        on = (v && v[0] == '1') ? 1 : 0;
+    }
+    return on != 0;
+}
+// co-resident clusters of `csize` one-CTA-per-SM blocks (GPC boundaries can strand a few SMs); queried once per size
+inline int igemm_max_clusters(int csize, int num_sms) {
+    if (csize == 1) return num_sms;
+    static int cached[5] = {0, 0, 0, 0, 0};
+    if (!cached[csize]) {
+        int n = 0;
+        if (igemm_set_attr() == cudaSuccess) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(num_sms / csize * csize, 1, 1);
+            cfg.blockDim = dim3(kIgemmThreads, 1, 1);
+            cfg.dynamicSmemBytes = 200 * 1024;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = csize;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&n, igemm_kernel, &cfg) != cudaSuccess) n = 0;
+            cudaGetLastError();
+        }
+        if (n <= 0 || n > num_sms / csize) n = (num_sms / csize) * 3 / 4 > 0 ? (num_sms / csize) * 3 / 4 : 1;
+        cached[csize] = n;
+    }
+    return cached[csize];
+}
+
 inline std::string igemm_build(IgemmLaunch& L, const SrcDesc* src, int nsrc, const IgemmTap* taps, int ntaps,
                                int chunk_elems, const void* wpk, int ktotal, int cout, const View4& out,
                                const EpilogueDesc& ep, int* err, int num_sms) {
@@ -107,6 +158,16 @@ inline std::string igemm_build(IgemmLaunch& L, const SrcDesc* src, int nsrc, con
     P.stages = stages;
     L.smem = igemm_smem(P.ntile, chunk_elems, stages, P.out_cblk).total + 1024;
 
+    // cluster multicast of the weight tile for the wide layers (L2 -> SM bandwidth bound otherwise): csize CTAs on
+    // adjacent M tiles share one copy of B.  Needs 1 KB-aligned B parts (>= 8 rows of 128 B) and enough M tiles.
+    const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    int csize = 1;
+    if (igemm_cluster_enabled() && chunk_elems == 64 && P.ntile >= 128) {
+        if (m_tiles >= 8) csize = 4;
+        else if (m_tiles >= 2) csize = 2;
+    }
+    P.csize = csize;
+
     const CUtensorMapSwizzle swz = swizzle_for_bytes(chunk_elems * 2);
     for (int i = 0; i < 2; ++i) {
         const SrcDesc& s = src[i < nsrc ? i : 0];
@@ -122,7 +183,7 @@ inline std::string igemm_build(IgemmLaunch& L, const SrcDesc* src, int nsrc, con
     {
         uint64_t dims[2] = {(uint64_t)ktotal, (uint64_t)cout};
         uint64_t str[1] = {(uint64_t)ktotal * 2};
-        uint32_t box[2] = {(uint32_t)chunk_elems, (uint32_t)P.ntile};
+        uint32_t box[2] = {(uint32_t)chunk_elems, (uint32_t)(P.ntile / csize)};
         uint32_t es[2] = {1, 1};
         std::string e = make_tmap_bf16(&L.b, wpk, 2, dims, str, box, es, swz);
         if (!e.empty()) return "B map: " + e;
@@ -135,21 +196,34 @@ inline std::string igemm_build(IgemmLaunch& L, const SrcDesc* src, int nsrc, con
         std::string e = make_tmap_bf16(&L.d, out.ptr, 4, dims, str, box, es, swizzle_for_bytes(P.out_cblk * 2));
         if (!e.empty()) return "D map: " + e;
     }
-    const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
-    const int waves = (total_tiles + num_sms - 1) / num_sms;
-    L.grid = (total_tiles + waves - 1) / waves;
+    const int total_groups = ((m_tiles + csize - 1) / csize) * P.n_tiles;
+    const int max_clusters = igemm_max_clusters(csize, num_sms);
+    const int waves = (total_groups + max_clusters - 1) / max_clusters;
+    L.grid = ((total_groups + waves - 1) / waves) * csize;
     return "";
 }
 
 inline cudaError_t igemm_launch(const IgemmLaunch& L, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    cudaError_t e = igemm_set_attr();
+    if (e != cudaSuccess) return e;
+    if (L.p.csize == 1) {
+        igemm_kernel<<<L.grid, kIgemmThreads, L.smem, st>>>(L.a0, L.a1, L.b, L.d, L.p);
+        return cudaGetLastError();
     }
-    igemm_kernel<<<L.grid, kIgemmThreads, L.smem, st>>>(L.a0, L.a1, L.b, L.d, L.p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(L.grid, 1, 1);
+    cfg.blockDim = dim3(kIgemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = L.p.csize;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, igemm_kernel, L.a0, L.a1, L.b, L.d, L.p);
 }
 
 // ------------------------------------------------------------------------------------------------ hconv (halo-resident 3x3)
@@ -341,6 +415,70 @@ inline cudaError_t tconv_launch(const TconvLaunch& L, cudaStream_t st) {
         if (L.iph == 1) tconv_kernel<1, 1><<<L.grid, tc_threads(1), L.smem, st>>>(L.a, L.p);
         else tconv_kernel<1, 2><<<L.grid, tc_threads(1), L.smem, st>>>(L.a, L.p);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ wconv (wide halo conv)
+struct WconvLaunch {
+    CUtensorMap a, b;
+    WconvParams p;
+    int grid = 0;
+    uint32_t smem = 0;
+};
+inline bool wconv_ok(int cin, int cout) { return cin >= 64 && cin % 64 == 0 && cout >= 128 && cout % 128 == 0 && cout <= 512; }
+
+// 3x3/s1/p1 conv src[N,H,W,cin] -> out[N,H,W,cout]; wpk = K-major packed weights [cout][(r*3+s)*cin + ci] (pack_conv_w)
+inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const void* wpk, int cout, int N, int H, int W,
+                               void* out, const EpilogueDesc& ep, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    WconvParams& P = L.p;
+    if (!wconv_ok(cin, cout)) return "wconv: unsupported channel configuration";
+    if (ep.residual.ptr && (ep.residual.sW != cout || ep.residual.sH != (long long)W * cout ||
+                            ep.residual.sN != (long long)H * W * cout))
+        return "wconv: residual must be a dense NHWC tensor of the output's shape";
+    P.H = H; P.W = W; P.N = N;
+    P.tiles_w = (W + 15) / 16;
+    P.tiles_h = (H + 15) / 16;
+    P.n_tiles = cout / kWcN;
+    P.cin = cin; P.cout = cout;
+    P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.stats = ep.stats;
+    P.err = err;
+    int bst = 8;
+    while (bst > 2 && wconv_smem(bst).total + 1024 > 232448u) --bst;
+    P.bstages = bst;
+    L.smem = wconv_smem(bst).total + 1024;
+    {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+        uint32_t box[4] = {64, 18, 18, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.a, src, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!e.empty()) return "wconv A map: " + e;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)cout};
+        uint64_t str[1] = {(uint64_t)9 * cin * 2};
+        uint32_t box[2] = {64, (uint32_t)kWcN};
+        uint32_t es[2] = {1, 1};
+        std::string e = make_tmap_bf16(&L.b, wpk, 2, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!e.empty()) return "wconv B map: " + e;
+    }
+    const int total = P.tiles_w * P.tiles_h * N * P.n_tiles;
+    const int waves = (total + num_sms - 1) / num_sms;
+    L.grid = (total + waves - 1) / waves;
+    return "";
+}
+inline cudaError_t wconv_launch(const WconvLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    wconv_kernel<<<L.grid, kWcThreads, L.smem, st>>>(L.a, L.b, L.p);
     return cudaGetLastError();
 }
 

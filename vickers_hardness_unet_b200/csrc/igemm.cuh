@@ -32,6 +32,10 @@ struct IgemmParams {
     int ntile;                               // UMMA N: 16..256, multiple of 16
     int chunk_elems;                         // K elements per pipeline stage: 16, 32 or 64 (32/64/128-byte swizzle)
     int stages;
+    int csize;                               // thread-block cluster size (1, 2 or 4): the CTAs of a cluster work on csize
+                                             // adjacent M tiles of the same N tile and share ONE copy of the weight tile:
+                                             // each loads ntile/csize rows and multicasts them to all (L2 -> SM traffic
+                                             // per MMA drops from A + B to A + B/csize)
     int num_taps, total_chunks;
     IgemmTap taps[kMaxTaps];
     int mulw[2], mulh[2];                    // source coordinate = tile origin * mul + tap offset
@@ -86,7 +90,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
+    const int csize = P.csize;
+    const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+    const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_n;
+    // work groups: csize adjacent M tiles x one N tile; cluster c takes groups c, c + #clusters, ...  A CTA whose M tile
+    // lies beyond the tensor (last, partial group) runs on zero-filled operands and its stores are clipped.
+    const int total_groups = ((m_tiles + csize - 1) / csize) * P.n_tiles;
+    const int group0 = blockIdx.x / csize, group_step = gridDim.x / csize;
     uint32_t tmem_cols = 32;
     while (tmem_cols < 2u * P.ntile) tmem_cols <<= 1;
 
@@ -97,7 +108,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tma_prefetch_desc(&tmD);
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), csize);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -124,6 +135,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (csize > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast into them
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -132,9 +144,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx = L.a_bytes + P.ntile * P.chunk_elems * 2;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % P.n_tiles;
-                int m = tile / P.n_tiles;
+            const int b_rows = P.ntile / csize;
+            const uint32_t b_part = (uint32_t)b_rows * P.chunk_elems * 2;
+            for (int grp = group0; grp < total_groups; grp += group_step) {
+                const int nt = grp % P.n_tiles;
+                int m = (grp / P.n_tiles) * csize + crank;
                 const int tw = m % P.tiles_w;
                 m /= P.tiles_w;
                 const int th = m % P.tiles_h;
@@ -154,7 +168,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         const uint32_t sa = base + stage * L.stage_bytes;
                         mbar_expect_tx(full_bar(stage), tx);
                         tma_load_4d(sa, mp, full_bar(stage), tap.c0 + cc * P.chunk_elems, cw, ch, tn * P.bn);
-                        tma_load_2d(sa + L.a_bytes, &tmB, full_bar(stage), kidx * P.chunk_elems, nt * P.ntile);
+                        if (csize > 1)
+                            tma_load_2d_mc(sa + L.a_bytes + crank * b_part, &tmB, full_bar(stage), kidx * P.chunk_elems,
+                                           nt * P.ntile + crank * b_rows, cmask);
+                        else
+                            tma_load_2d(sa + L.a_bytes, &tmB, full_bar(stage), kidx * P.chunk_elems, nt * P.ntile);
                         if (++stage == P.stages) {
                             stage = 0;
                             phase ^= 1;
@@ -174,7 +192,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const uint32_t sbo = 8u * P.chunk_elems * 2;
             const uint32_t layout = (P.chunk_elems == 64) ? 2u : (P.chunk_elems == 32 ? 4u : 6u);
             const int ksteps = P.chunk_elems / 16;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int grp = group0; grp < total_groups; grp += group_step) {
                 if (!mbar_wait(tempty_bar(acc), acc_phase ^ 1)) {
                     *s_abort = 1;
                     atomicExch(P.err, 2);
@@ -198,7 +216,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         umma_bf16(d_tmem, ad, bd, idesc, accum);
                         accum = 1;
                     }
-                    umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
+                    // frees this smem stage (in every CTA that multicasts into it) once the MMAs above have read it
+                    if (csize > 1) umma_commit_mc(empty_bar(stage), cmask);
+                    else umma_commit(empty_bar(stage));
                     if (++stage == P.stages) {
                         stage = 0;
                         phase ^= 1;
@@ -226,9 +246,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t blk_counter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % P.n_tiles;
-            int m = tile / P.n_tiles;
+        for (int grp = group0; grp < total_groups; grp += group_step) {
+            const int nt = grp % P.n_tiles;
+            int m = (grp / P.n_tiles) * csize + crank;
             const int tw = m % P.tiles_w;
             m /= P.tiles_w;
             const int th = m % P.tiles_h;
@@ -248,6 +268,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 role_done:
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();  // no CTA exits while a peer may still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);

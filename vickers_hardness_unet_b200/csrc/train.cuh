@@ -410,6 +410,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             if (!e.empty()) return c.name + ": " + e;
             add_f("conv_fwd:" + c.name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
             segs.rows[0] = HL.grid;
+        } else if (u.conv != S.stem && c.k == 3 && c.stride == 1 && wconv_ok(c.cin, c.cout)) {
+            WconvLaunch WL;
+            std::string e = wconv_build(WL, in, c.cin, ctx->wpk + c.wpk, c.cout, N, u.Hin, u.Win, u.z, ep, ctx->d_err, SM);
+            if (!e.empty()) return c.name + ": " + e;
+            add_f("conv_fwd:" + c.name, [WL](cudaStream_t st) { return wconv_launch(WL, st); });
+            segs.rows[0] = WL.grid;
         } else {
             IgemmLaunch L;
             std::string e = (u.conv == S.stem)
@@ -667,6 +673,14 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                                         ep, ctx->d_err, SM);
             if (!e.empty()) return c.name + " dgrad: " + e;
             add_b(stage, "dgrad:" + c.name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
+            return "";
+        }
+        if (wconv_ok(c.cout, c.cin)) {
+            WconvLaunch WL;
+            std::string e = wconv_build(WL, u.dz, c.cout, T.wdg + T.wdg_off[u.conv], c.cin, N, u.Ho, u.Wo, out, ep,
+                                        ctx->d_err, SM);
+            if (!e.empty()) return c.name + " dgrad: " + e;
+            add_b(stage, "dgrad:" + c.name, [WL](cudaStream_t st) { return wconv_launch(WL, st); });
             return "";
         }
         IgemmLaunch L;

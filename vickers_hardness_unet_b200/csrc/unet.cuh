@@ -491,6 +491,15 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
             plan.steps.push_back({[HL](cudaStream_t st) { return hconv_launch(HL, st); }, c.name, 1});
             return "";
         }
+        if (c.k == 3 && c.stride == 1 && wconv_ok(c.cin, c.cout)) {
+            // wide layers: halo-resident operand + streamed weights (wconv.cuh); same packed weight matrix as igemm
+            WconvLaunch WL;
+            std::string e = wconv_build(WL, in, c.cin, ctx->wpk + c.wpk, c.cout, N, hin, win, out, ep, ctx->d_err,
+                                        ctx->num_sms);
+            if (!e.empty()) return c.name + ": " + e;
+            plan.steps.push_back({[WL](cudaStream_t st) { return wconv_launch(WL, st); }, c.name, 1});
+            return "";
+        }
         IgemmLaunch L;
         std::string e = build_conv(ctx, L, c, ctx->wpk + c.wpk, in, N, hin, win, out, ep);
         if (!e.empty()) return c.name + ": " + e;

@@ -277,6 +277,115 @@ static void case_stem(const char* name, int N, int H, int W) {
     cudaFree(d_x); cudaFree(d_w); cudaFree(d_xp); cudaFree(d_wpk); cudaFree(d_out);
 }
 
+// the same stem through tconv's overlapped-row (non-swizzled descriptor) mode; iters > 0: also time it
+static void case_tstem(const char* name, int N, int H, int W, bool stats, int iters = 0) {
+    std::vector<float> x((size_t)N * 3 * H * W);
+    for (auto& v : x) v = frand() * 2.f;
+    std::vector<float> w((size_t)64 * 3 * 49), wq(w.size());
+    for (auto& v : w) v = frand() * 0.08f;
+    for (size_t i = 0; i < w.size(); ++i) wq[i] = bf16r(w[i]);
+    float* d_x = to_dev_f32(x);
+    float* d_w = to_dev_f32(w);
+    const size_t out_e = (size_t)N * (H / 2) * (W / 2) * 64;
+    __nv_bfloat16 *d_xp, *d_wpk, *d_out;
+    CK(cudaMalloc(&d_xp, (size_t)N * H * (W + 8) * 4 * 2 + 128));
+    CK(cudaMemset(d_xp, 0xFF, (size_t)N * H * (W + 8) * 4 * 2 + 128));
+    CK(cudaMalloc(&d_wpk, 64 * 224 * 2));
+    CK(cudaMalloc(&d_out, out_e * 2));
+    CK(cudaMemset(d_out, 0xFF, out_e * 2));
+    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, 148), 256>>>(d_x, d_xp, N, H, W);
+    {
+        PackTable T;
+        T.add(pk_entry(PK_STEM2, 0, 0, 64 * 224));
+        CK(T.upload());
+        CK(T.launch(d_w, d_wpk, 0));
+        CK(cudaDeviceSynchronize());
+    }
+    EpilogueDesc ep;
+    ep.relu = 1;
+    float* d_stats = nullptr;
+    if (stats) {
+        CK(cudaMalloc(&d_stats, (size_t)g_ctx->num_sms * 64 * 2 * 4));
+        CK(cudaMemset(d_stats, 0, (size_t)g_ctx->num_sms * 64 * 2 * 4));
+        ep.stats = d_stats;
+    }
+    TconvLaunch L;
+    std::string e = tconv_build_stem(L, d_xp, d_wpk, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: build: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %d smem %u stages %d tiles %dx%dx%d\n", name, L.grid, L.smem, L.p.stages, L.p.tiles_w, L.p.tiles_h, N);
+    CK(tconv_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (check_err_flag(name)) return;
+    if (iters > 0) {
+        long long* d_prof;
+        CK(cudaMalloc(&d_prof, (size_t)L.grid * 16 * 8));
+        L.p.prof = d_prof;
+        const int modes[] = {0, 8, 9, 12, 13, 15};
+        for (int mode : modes) {
+            L.p.dbg = mode;
+            CK(cudaMemset(d_prof, 0, (size_t)L.grid * 16 * 8));
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            CK(tconv_launch(L, 0));
+            CK(cudaDeviceSynchronize());
+            cudaEventRecord(e0);
+            for (int i = 0; i < iters; ++i) CK(tconv_launch(L, 0));
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms /= iters;
+            const double bytes = (double)N * H * (W + 8) * 8 + out_e * 2.0;
+            const int tiles = L.p.tiles_w * L.p.tiles_h * N;
+            printf("[BENCH-S] %-30s skip[%s%s%s] %8.1f us %7.1f GB/s (min traffic) %6.0f cyc/tile/CTA\n", name,
+                   mode & 1 ? "L" : "-", mode & 2 ? "M" : "-", mode & 4 ? "E" : "-", ms * 1e3, bytes / ms * 1e-6,
+                   ms * 1e-3 * 1.965e9 / ((double)tiles / L.grid));
+            if (mode & 8) {
+                std::vector<long long> hp((size_t)L.grid * 16);
+                CK(cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost));
+                const double per = (double)tiles / L.grid;
+                const char* nm[12] = {"P:wait_empty", "P:issue", "", "", "M:wait_tempty", "M:wait_full", "M:issue", "M:commit",
+                                      "E:prefetch", "E:wait_tfull", "E:ld+arrive", "E:work"};
+                printf("          cycles/tile (CTA 0):");
+                for (int k = 0; k < 12; ++k)
+                    if (nm[k][0]) printf(" %s=%.0f", nm[k], hp[k] / per);
+                printf("\n");
+            }
+        }
+        cudaFree(d_prof);
+    } else {
+        HostT in(N, H, W, 3);
+        for (int n = 0; n < N; ++n)
+            for (int c = 0; c < 3; ++c)
+                for (int h = 0; h < H; ++h)
+                    for (int ww = 0; ww < W; ++ww) in.at(n, h, ww, c) = bf16r(x[(((size_t)n * 3 + c) * H + h) * W + ww]);
+        HostT ref = cpu_conv(in, wq, 64, 7, 2, 3);
+        for (auto& v : ref.v) v = fmaxf(v, 0.f);
+        std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+        report(name, compare(got, ref.v), 0.012, got, ref.v, 64);
+        if (stats) {
+            std::vector<float> hs((size_t)L.grid * 128);
+            CK(cudaMemcpy(hs.data(), d_stats, hs.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<float> gs(128, 0.f), rs(128, 0.f);
+            for (int b = 0; b < L.grid; ++b)
+                for (int j = 0; j < 128; ++j) gs[j] += hs[(size_t)b * 128 + j];
+            for (size_t i = 0; i < got.size(); ++i) {
+                rs[(i % 64) * 2] += got[i];
+                rs[(i % 64) * 2 + 1] += got[i] * got[i];
+            }
+            std::string nm = std::string(name) + " [stats]";
+            report(nm.c_str(), compare(gs, rs), 1e-4, gs, rs, 2);
+        }
+    }
+    cudaFree(d_x); cudaFree(d_w); cudaFree(d_xp); cudaFree(d_wpk); cudaFree(d_out);
+    if (d_stats) cudaFree(d_stats);
+}
+
 static void case_dec1(const char* name, int N, int Hl, int Wl, int cup, int cskip, int cout) {
     HostT low(N, Hl, Wl, cup);
     fill_rand_bf16(low.v, 1.0f);
@@ -949,6 +1058,12 @@ int main(int argc, char** argv) {
         case_stem("stem 7x7 s2 3->64 2x64x64", 2, 64, 64);
         case_stem("stem 7x7 s2 3->64 1x96x160", 1, 96, 160);
     }
+    if (want("tstem")) {
+        case_tstem("tstem 7x7 s2 3->64 2x64x64", 2, 64, 64, true);
+        case_tstem("tstem 7x7 s2 3->64 1x96x160", 1, 96, 160, true);
+        case_tstem("tstem 7x7 s2 3->64 3x512x512", 3, 512, 512, false);
+    }
+    if (want("sbench")) case_tstem("tstem 7x7 s2 3->64 x32 @512^2", 32, 512, 512, false, 10);
     if (want("dec1")) {
         case_dec1("dec1 up64+skip64->32 2x16x16", 2, 16, 16, 64, 64, 32);
         case_dec1("dec1 up128+skip64->64 1x16x16", 1, 16, 16, 128, 64, 64);

@@ -304,7 +304,7 @@ inline cudaError_t hconv_launch(const HconvLaunch& L, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------ tconv (TMA halo conv)
 struct TconvLaunch {
-    CUtensorMap a;
+    CUtensorMap a, d;
     TconvParams p;
     int grid = 0;
     uint32_t smem = 0;
@@ -359,11 +359,13 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     const int items = nt * (cout / 16);
     if (items > 8) return "tconv: too many accumulator column groups";
     const int acc_cols = nt * cout;
+    // cout >= 32: whole sub-tiles leave through swizzled smem staging + TMA store (see TconvParams::stage_out)
+    const uint32_t out_bytes = (!parity && cout >= 32) ? (uint32_t)nt * 128u * cout * 2u : 0u;
     L.occ = 1;
     int stages = 0;
     if (items <= 4 && 2 * acc_cols <= 256) {
         for (int st = 4; st >= 2; --st)
-            if (2 * (tconv_smem(P.w_bytes, P.stage_bytes, st).total + 1024 + 1024) <= 232448u) {
+            if (2 * (tconv_smem(P.w_bytes, P.stage_bytes, st, out_bytes).total + 1024 + 1024) <= 232448u) {
                 L.occ = 2;
                 stages = st;
                 break;
@@ -371,18 +373,30 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     }
     if (L.occ == 1)
         for (int st = 6; st >= 2; --st)
-            if (tconv_smem(P.w_bytes, P.stage_bytes, st).total + 1024 <= 232448u) {
+            if (tconv_smem(P.w_bytes, P.stage_bytes, st, out_bytes).total + 1024 <= 232448u) {
                 stages = st;
                 break;
             }
     const int groups = tc_epi_warps(L.occ) / 4;
     L.iph = (items + groups - 1) / groups;
+    const int cgs = cout / 16;
+    if (out_bytes && L.iph <= cgs && cgs % L.iph == 0 && items % groups == 0) {
+        P.stage_out = 1;
+        P.spw = (cgs / L.iph) * 128;
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2};
+        uint32_t box[4] = {(uint32_t)cout, 8, 16, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.d, out, 4, dims, str, box, es, swizzle_for_bytes(cout * 2));
+        if (!e.empty()) return "tconv D map: " + e;
+    }
     if (stages < 2) return "tconv: does not fit in shared memory";
     P.stages = stages;
     const int tmem_budget = L.occ == 2 ? 256 : 512;
     P.nacc = tmem_budget / acc_cols >= 4 ? 4 : (tmem_budget / acc_cols >= 2 ? 2 : 0);
     if (!P.nacc) return "tconv: accumulators do not fit in TMEM";
-    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, stages).total + 1024;
+    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, stages, P.stage_out ? out_bytes : 0u).total + 1024;
+    if (!P.stage_out) L.d = CUtensorMap{};
     {
         uint64_t dims[4] = {(uint64_t)cin, (uint64_t)src_w, (uint64_t)src_h, (uint64_t)N};
         uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)src_w * cin * 2, (uint64_t)src_h * src_w * cin * 2};
@@ -398,24 +412,88 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     return "";
 }
 
-inline cudaError_t tconv_launch(const TconvLaunch& L, cudaStream_t st) {
+// 7x7/s2 stem over the packed image xp[N][H][W+8][4] (H, W = INPUT extent) -> out[N, H/2, W/2, 64]; wpk = PK_STEM2 image
+inline std::string tconv_build_stem(TconvLaunch& L, const void* xp, const void* wpk, int N, int H, int W, void* out,
+                                    const EpilogueDesc& ep, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    TconvParams& P = L.p;
+    if ((H | W) & 1) return "tconv stem: H and W must be even";
+    if (ep.residual.ptr) return "tconv stem: no residual";
+    const int Ho = H / 2, Wo = W / 2, nt = 2;
+    P.H = Ho; P.W = Wo; P.N = N;
+    P.mode = 2;
+    P.nt = nt;
+    P.cin = 16;   // unused by the stem issue path except for K-step bookkeeping
+    P.cout = 64;
+    P.tiles_w = (Wo + 127) / 128;
+    P.tiles_h = (Ho + nt - 1) / nt;
+    P.halo_w = 136;                                  // 16-byte pixel pairs per staged input row (128 + 3 window overhang,
+                                                     // rounded up to 17 x 128 B: TMA rows of 128 B, not 16 B)
+    const int rows = 2 * nt + 5;
+    P.tx_bytes = (uint32_t)P.halo_w * 16 * rows;
+    P.stage_bytes = (P.tx_bytes + 1023u) & ~1023u;
+    P.w_bytes = 64 * 224 * 2;
+    P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
+    P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.stats = ep.stats;
+    P.err = err;
+    L.occ = 1;
+    L.iph = 2;                                       // 2 sub-tiles x 4 column groups over 16 epilogue warps
+    P.stages = 4;
+    P.nacc = 4;
+    P.stage_out = 1;                                 // one output row segment [64 ch x 128 px] per sub-tile through TMA
+    P.spw = 256;
+    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, P.stages, (uint32_t)nt * 128u * 128u).total + 1024;
+    {
+        uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+        uint64_t str[3] = {128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128};
+        uint32_t box[4] = {64, 128, 1, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.d, out, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!e.empty()) return "tconv stem D map: " + e;
+    }
+    {
+        // view of xp as 128-byte groups of 8 pixel pairs: [64 elements][ceil((W+8)/16) groups][H rows][N].  The last group
+        // of a row may run up to 120 B past the row end (into the next row; for the very last row into the 128 B of slack
+        // every xp allocation carries): those pairs only feed output columns >= Wo, which are masked.
+        uint64_t dims[4] = {64, (uint64_t)(W + 8 + 15) / 16, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {128, (uint64_t)(W + 8) * 8, (uint64_t)H * (W + 8) * 8};
+        uint32_t box[4] = {64, 17, (uint32_t)rows, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.a, xp, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (!e.empty()) return "tconv stem A map: " + e;
+    }
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    const int waves = (total_tiles + num_sms - 1) / num_sms;
+    L.grid = (total_tiles + waves - 1) / waves;
+    return "";
+}
+
+template <int kOcc, int kIph, bool kStage>
+inline cudaError_t tconv_launch_t(const TconvLaunch& L, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tconv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
+        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<kOcc, kIph, kStage>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kOcc == 2 ? 115200 : 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (L.occ == 2) {
-        if (L.iph == 1) tconv_kernel<2, 1><<<L.grid, tc_threads(2), L.smem, st>>>(L.a, L.p);
-        else tconv_kernel<2, 2><<<L.grid, tc_threads(2), L.smem, st>>>(L.a, L.p);
-    } else {
-        if (L.iph == 1) tconv_kernel<1, 1><<<L.grid, tc_threads(1), L.smem, st>>>(L.a, L.p);
-        else tconv_kernel<1, 2><<<L.grid, tc_threads(1), L.smem, st>>>(L.a, L.p);
-    }
+    tconv_kernel<kOcc, kIph, kStage><<<L.grid, tc_threads(kOcc), L.smem, st>>>(L.a, L.d, L.p);
     return cudaGetLastError();
+}
+inline cudaError_t tconv_launch(const TconvLaunch& L, cudaStream_t st) {
+    const int key = (L.occ == 2 ? 4 : 0) | (L.iph == 2 ? 2 : 0) | (L.p.stage_out ? 1 : 0);
+    switch (key) {
+        case 0: return tconv_launch_t<1, 1, false>(L, st);
+        case 1: return tconv_launch_t<1, 1, true>(L, st);
+        case 2: return tconv_launch_t<1, 2, false>(L, st);
+        case 3: return tconv_launch_t<1, 2, true>(L, st);
+        case 4: return tconv_launch_t<2, 1, false>(L, st);
+        case 5: return tconv_launch_t<2, 1, true>(L, st);
+        case 6: return tconv_launch_t<2, 2, false>(L, st);
+        default: return tconv_launch_t<2, 2, true>(L, st);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ wconv (wide halo conv)

@@ -8,7 +8,7 @@
 
 namespace ub {
 
-enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5, PK_HPAR = 6 };
+enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5, PK_HPAR = 6, PK_STEM2 = 7 };
 
 struct PackEntry {
     int type;
@@ -77,6 +77,12 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int rs = int((E.taps >> (4 * t)) & 0xF), r = rs >> 2, s = rs & 3;
             dst = (long long)ci * E.d + E.pad + t * E.cout + co;
             return w[(((long long)co * E.a + E.b + ci) * R + r) * S + s];
+        }
+        case PK_STEM2: {  // tconv stem operand: [K chunk j = r*4 + q][cout group g][co % 8][8 elements], element e of chunk
+            // (r, q) = input pixel px = 2q + e/4 (kernel column px - 1; px 0 is padding), channel e % 4 (3 is padding)
+            const int e8 = int(i % 8), co8 = int((i / 8) % 8), g = int((i / 64) % 8), j = int(i / 512);
+            const int r = j >> 2, q = j & 3, px = 2 * q + (e8 >> 2), ch = e8 & 3, co = g * 8 + co8;
+            return (ch < 3 && px >= 1) ? w[((co * 3 + ch) * 7 + r) * 7 + (px - 1)] : 0.f;
         }
         case PK_HPAR: {  // tconv parity operand: cout = rows, cin = cup (<= 64), a = cin_total of the OIHW tensor.
             // logical [parity][a*2+b][co][c] = sum of the 3x3 taps that land on low-res neighbour (a, b) for output

@@ -30,7 +30,8 @@ constexpr int kTcHaloH = 18;        // 16 output rows + 2
 
 struct TconvParams {
     int H, W, N;                    // OUTPUT extent
-    int mode;                       // 0: plain 3x3 over src[N,H,W,cin]; 1: parity (src = low-res [N,H/2,W/2,cin], 2x2 taps)
+    int mode;                       // 0: plain 3x3 over src[N,H,W,cin]; 1: parity (src = low-res [N,H/2,W/2,cin], 2x2 taps);
+                                    // 2: 7x7/s2 stem over the packed image xp[N][2H][2W+8][4] (see tc_issue_stem)
     int nt;                         // accumulators (sub-tiles) per pipeline step
     int tiles_w, tiles_h;           // tile grid per image (plain: 8*nt x 16 output px; parity: 8 x 16 low-res px)
     int cin, cout;
@@ -45,22 +46,29 @@ struct TconvParams {
     __nv_bfloat16* out;             // [N, H, W, cout]
     const __nv_bfloat16* residual;  // same shape or nullptr
     float* stats;                   // [gridDim.x][cout][2] or nullptr
+    int stage_out;                  // 1: the epilogue transposes through swizzled smem and stores whole sub-tiles with TMA
+                                    // (cout >= 32: a register store of 16 channels per pixel touches 32 different 128-byte
+                                    // lines per warp instruction and the LSU serialises them: measured 2100 of 5900
+                                    // cycles per tile on the stem); 0: straight from registers (cout = 16, parity mode)
+    int spw;                        // epilogue threads per sub-tile (named-barrier population), stage_out only
     int* err;
     long long* prof;                // selftest only: [grid][16] cycle counters per role phase (dbg & 8)
     int dbg;                        // selftest only: 1 = skip halo loads, 2 = skip MMA issue, 4 = skip epilogue math + stores
 };
 
 struct TconvSmem {
-    uint32_t ss_off, cstat_off, bar_off, w_off, halo_off, total;
+    uint32_t ss_off, cstat_off, bar_off, w_off, halo_off, out_off, total;
 };
-__host__ __device__ inline TconvSmem tconv_smem(uint32_t w_bytes, uint32_t stage_bytes, int stages) {
+// out_bytes: epilogue staging (nt sub-tiles x 128 pixels x cout x 2 B) or 0
+__host__ __device__ inline TconvSmem tconv_smem(uint32_t w_bytes, uint32_t stage_bytes, int stages, uint32_t out_bytes = 0) {
     TconvSmem s;
     s.ss_off = 0;                                  // scale[64], shift[64]
     s.cstat_off = 512;                             // [<= 16 epilogue warps][64 ch][2]
     s.bar_off = s.cstat_off + 16 * 128 * 4;        // 8704
     s.w_off = 9216;
     s.halo_off = (s.w_off + w_bytes + 1023u) & ~1023u;
-    s.total = s.halo_off + stages * stage_bytes;
+    s.out_off = s.halo_off + stages * stage_bytes;
+    s.total = s.out_off + out_bytes;
     return s;
 }
 
@@ -111,16 +119,44 @@ __device__ __forceinline__ void tc_issue_parity(uint32_t d_tmem, uint64_t a_base
     }
 }
 
+// Stem mode (encoder.conv1, 7x7 stride 2, 3(+1 zero) input channels): out(ho, wo) = sum_r sum_{px<8} xp[2ho+r-3][2wo+px][4ch]
+// * w[r][px][ch] — 7 row taps with K = 32 each.  The operand row of output pixel wo is the 64 contiguous bytes of input
+// row 2ho+r-3 starting at byte 16*wo: consecutive rows OVERLAP (pitch 16 B, length 64 B).  The non-swizzled K-major
+// descriptor expresses exactly that: a core matrix (8 rows x 16 B) is 128 contiguous bytes, core matrices adjacent in K
+// are LBO = 16 B apart, adjacent in M SBO = 128 B apart — so the raw input rows in shared memory ARE the im2col matrix
+// and nothing is expanded.  Sub-tile s = output row, 128 consecutive wo.  Weights: [K chunk of 8][cout group of 8][8][8]
+// (LBO = 1024 B between K chunks, SBO = 128 B between groups of 8 output channels), PK_STEM2.
+__device__ __forceinline__ void tc_issue_stem(uint32_t d_tmem, uint32_t stage_addr, uint32_t w_addr, uint32_t row_pitch,
+                                              uint32_t idesc, int nt) {
+    const uint64_t a_base = umma_desc(stage_addr, 16, 128, 0u);
+    const uint64_t b_base = umma_desc(w_addr, 1024, 128, 0u);
+    for (int s = 0; s < nt; ++s) {
+        const uint32_t d = d_tmem + s * 64;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            const uint64_t a_r = a_base + (((uint32_t)(2 * s + r) * row_pitch) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t ad = a_r + (uint32_t)(kk * 2);
+                const uint64_t bd = b_base + (uint32_t)(((r * 4 + kk * 2) * 1024) >> 4);
+                if (r == 0 && kk == 0) umma_bf16_c<false>(d, ad, bd, idesc);
+                else umma_bf16_c<true>(d, ad, bd, idesc);
+            }
+        }
+    }
+}
+
 // kIph = accumulator column groups (16 channels of one sub-tile) each epilogue thread handles per pipeline step
-template <int kOcc, int kIph>
+template <int kOcc, int kIph, bool kStage>
 __global__ void __launch_bounds__(tc_threads(kOcc), kOcc)
-tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ TconvParams P) {
+tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
+             const __grid_constant__ TconvParams P) {
     constexpr int kEw = tc_epi_warps(kOcc), kTcThreads = tc_threads(kOcc);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
-    const TconvSmem L = tconv_smem(P.w_bytes, P.stage_bytes, P.stages);
+    const TconvSmem L = tconv_smem(P.w_bytes, P.stage_bytes, P.stages, kStage ? (uint32_t)P.nt * 128u * P.cout * 2u : 0u);
     const uint32_t bar0 = base + L.bar_off;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (P.stages + s); };
@@ -136,6 +172,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
+        if (kStage) tma_prefetch_desc(&tmD);
         for (int s = 0; s < P.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -189,7 +226,11 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
                     break;
                 }
                 UB_TC_TICK(t_wait)
-                const int x0 = (P.mode ? it.tw * 8 : it.tw * 8 * P.nt) - 1, y0 = it.th * 16 - 1;
+                int x0 = (P.mode ? it.tw * 8 : it.tw * 8 * P.nt) - 1, y0 = it.th * 16 - 1;
+                if (P.mode == 2) {  // 128-byte groups of 8 pixel pairs of the packed image: output column wo <-> pair wo
+                    x0 = it.tw * 16;
+                    y0 = 2 * it.th * P.nt - 3;
+                }
                 if (P.dbg & 1) {
                     mbar_arrive(full_bar(stage));
                 } else {
@@ -233,7 +274,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
                 const uint64_t a_base = a_base0 + (uint64_t)((stage * P.stage_bytes) >> 4);
                 const uint32_t d_tmem = tmem_base + acc * acc_cols;
                 if (!(P.dbg & 2)) {
-                    if (P.mode) {
+                    if (P.mode == 2) {
+                        tc_issue_stem(d_tmem, base + L.halo_off + stage * P.stage_bytes, base + L.w_off,
+                                      (uint32_t)P.halo_w * 16u, idesc, P.nt);
+                    } else if (P.mode) {
                         switch (ks) {
                             case 1: tc_issue_parity<1>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
                             case 2: tc_issue_parity<2>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
@@ -286,7 +330,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
             const int i = i0 + k < items ? i0 + k : items - 1;
             it_s[k] = i / cgs;
             it_c0[k] = (i - it_s[k] * cgs) * 16;
-            if (P.mode) {
+            if (P.mode == 2) {
+                it_dh[k] = it_s[k];
+                it_dw[k] = row;
+            } else if (P.mode) {
                 it_dh[k] = 2 * hl + (it_s[k] >> 1);
                 it_dw[k] = 2 * wl + (it_s[k] & 1);
             } else {
@@ -295,22 +342,26 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
             }
         }
         const int n_mine = items - i0 < kIph ? (items - i0 > 0 ? items - i0 : 0) : kIph;
-        const int th_px = P.mode ? 32 : 16, tw_px = P.mode ? 16 : 8 * P.nt;
+        // staged stores: all items of a thread belong to ONE sub-tile (host guarantees kIph divides cout/16)
+        const int my_sub = it_s[0];
+        const uint32_t out_row_bytes = (uint32_t)P.cout * 2u, out_swz = out_row_bytes / 16u - 1u;
+        const bool store_issuer = kStage && n_mine > 0 && q == 0 && lane == 0 && (i0 % cgs) == 0;
+        const int th_px = P.mode == 2 ? P.nt : (P.mode ? 32 : 16), tw_px = P.mode == 2 ? 128 : (P.mode ? 16 : 8 * P.nt);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (HcTileIter it(P.tiles_w, P.tiles_h, total_tiles); it.valid(); it.next()) {
             const int h0 = it.th * th_px, w0 = it.tw * tw_px;
-            size_t off[kIph];
+            const int pix0 = (it.tn * P.H + h0) * P.W + w0;      // pixel index of the tile origin (fits 32 bits)
             bool valid[kIph];
             uint4 rv[kIph][2];
 #pragma unroll
             for (int k = 0; k < kIph; ++k) {
-                const int ph = h0 + it_dh[k], pw = w0 + it_dw[k];
-                valid[k] = k < n_mine && ph < P.H && pw < P.W;
-                off[k] = (((size_t)it.tn * P.H + ph) * P.W + pw) * P.cout + it_c0[k];
+                valid[k] = k < n_mine && h0 + it_dh[k] < P.H && w0 + it_dw[k] < P.W;
                 if (P.residual && valid[k]) {  // issued before the accumulator wait: the loads overlap the tile's MMAs
-                    rv[k][0] = __ldg(reinterpret_cast<const uint4*>(P.residual + off[k]));
-                    rv[k][1] = __ldg(reinterpret_cast<const uint4*>(P.residual + off[k]) + 1);
+                    const uint4* rp = reinterpret_cast<const uint4*>(
+                        P.residual + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + it_c0[k]);
+                    rv[k][0] = __ldg(rp);
+                    rv[k][1] = __ldg(rp + 1);
                 }
             }
             UB_TC_TICK(t_a)
@@ -320,28 +371,34 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
             }
             tc_fence_after();
             UB_TC_TICK(t_wait)
-            uint32_t r[kIph][16];
+            if (kStage && n_mine > 0) {
+                // the previous tile's TMA store has finished READING this sub-tile's staging before anyone rewrites it
+                if (store_issuer) tma_wait_read<0>();
+                named_bar_sync(2 + 2 * my_sub, P.spw);
+            }
+            UB_TC_TICK(t_b)
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * acc_cols;
 #pragma unroll
-            for (int k = 0; k < kIph; ++k) tmem_ld16(taddr + it_s[k] * P.cout + it_c0[k], r[k]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: hand it back to the MMA warp
-            UB_TC_TICK(t_b)
-#pragma unroll
             for (int k = 0; k < kIph; ++k) {
-                if (k >= n_mine || (P.dbg & 4)) break;
+                uint32_t r[16];
+                tmem_ld16(taddr + it_s[k] * P.cout + it_c0[k], r);
+                tmem_ld_wait();
+                if (k == kIph - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                if (k >= n_mine || (P.dbg & 4)) continue;
                 const int c0 = it_c0[k];
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + 4 * j);
                     const float4 sh = *reinterpret_cast<const float4*>(ss + 64 + c0 + 4 * j);
-                    v[4 * j + 0] = __uint_as_float(r[k][4 * j + 0]) * sc.x + sh.x;
-                    v[4 * j + 1] = __uint_as_float(r[k][4 * j + 1]) * sc.y + sh.y;
-                    v[4 * j + 2] = __uint_as_float(r[k][4 * j + 2]) * sc.z + sh.z;
-                    v[4 * j + 3] = __uint_as_float(r[k][4 * j + 3]) * sc.w + sh.w;
+                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) * sc.x + sh.x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) * sc.y + sh.y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) * sc.z + sh.z;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) * sc.w + sh.w;
                 }
                 if (P.residual && valid[k]) {
 #pragma unroll
@@ -364,9 +421,17 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
                     o[j].z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
                     o[j].w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
                 }
-                if (valid[k]) {
-                    reinterpret_cast<uint4*>(P.out + off[k])[0] = o[0];
-                    reinterpret_cast<uint4*>(P.out + off[k])[1] = o[1];
+                if (kStage) {
+                    // row = TMEM lane = pixel in TMA box order; 16-byte chunks XOR-swizzled like the output tensor map
+                    uint32_t so = (uint32_t)row * out_row_bytes + (uint32_t)c0 * 2u;
+                    uint8_t* sp = sm + L.out_off + it_s[k] * 128u * out_row_bytes;
+                    *reinterpret_cast<uint4*>(sp + (so ^ (((so >> 7) & out_swz) << 4))) = o[0];
+                    so += 16;
+                    *reinterpret_cast<uint4*>(sp + (so ^ (((so >> 7) & out_swz) << 4))) = o[1];
+                } else if (valid[k]) {
+                    uint4* op = reinterpret_cast<uint4*>(P.out + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + c0);
+                    op[0] = o[0];
+                    op[1] = o[1];
                 }
                 if (P.stats) {
                     // statistics of the bf16 values just stored (masked pixels contribute 0); fixed summation order
@@ -388,12 +453,23 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Tc
                     }
                 }
             }
+            if (kStage && n_mine > 0 && !(P.dbg & 4)) {
+                fence_async_smem();                       // staging writes -> visible to the TMA store (async proxy)
+                named_bar_sync(3 + 2 * my_sub, P.spw);
+                if (store_issuer) {
+                    const uint32_t src = base + L.out_off + my_sub * 128u * out_row_bytes;
+                    if (P.mode == 2) tma_store_4d(&tmD, src, 0, w0, h0 + my_sub, it.tn);
+                    else tma_store_4d(&tmD, src, 0, w0 + 8 * my_sub, h0, it.tn);   // partial tiles are clipped by the TMA
+                    tma_commit();
+                }
+            }
             UB_TC_TICK(t_work)
             if (++acc == P.nacc) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        if (kStage && store_issuer) tma_wait_all<0>();  // all output stores complete before the CTA exits
         if (prof && threadIdx.x == 64) {
             P.prof[blockIdx.x * 16 + 8] = t_a;
             P.prof[blockIdx.x * 16 + 9] = t_wait;

@@ -381,7 +381,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     };
 
     // ---------------------------------------------------------------- forward graph
-    plan.xp = A.take((long long)N * H * (W + 8) * 4);
+    plan.xp = A.take((long long)N * H * (W + 8) * 4 + 64);
     struct BlockRec { int u1, u2, ud; __nv_bfloat16* x_in; __nv_bfloat16* g; int layer; };
     std::vector<BlockRec> blocks;
     struct DecRec { int u1, u2; __nv_bfloat16* low; __nv_bfloat16* skip; __nv_bfloat16* d_skip; int Hl, Wl; };
@@ -396,7 +396,13 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         StatSegs segs;
         memset(&segs, 0, sizeof(segs));
         segs.n = 1; segs.ptr[0] = plan.stat_part;
-        if (c.tc == 1 && u.conv != S.stem) {
+        if (u.conv == S.stem) {
+            TconvLaunch TL;
+            std::string e = tconv_build_stem(TL, in, ctx->wpk + c.wpk, N, H, W, u.z, ep, ctx->d_err, SM);
+            if (!e.empty()) return c.name + ": " + e;
+            add_f("conv_fwd:" + c.name, [TL](cudaStream_t st) { return tconv_launch(TL, st); });
+            segs.rows[0] = TL.grid;
+        } else if (c.tc == 1) {
             TconvLaunch TL;
             std::string e = tconv_build(TL, in, c.cin, false, ctx->wpk + c.wpk, c.cout, N, u.Hin, u.Win, u.z, ep, ctx->d_err,
                                         SM);

@@ -295,7 +295,7 @@ inline std::string ctx_build_pack_tables(Ctx* ctx) {
             e = pk_entry(PK_HCONV, c.w, c.wpk, 9ll * c.cin * c.cout);
             e.cout = c.cout; e.cin = c.cin; e.a = c.cin; e.b = 0; e.c = 0;
         } else if ((int)i == S.stem) {
-            e = pk_entry(PK_STEM, c.w, c.wpk, 64 * 224);
+            e = pk_entry(PK_STEM2, c.w, c.wpk, 64 * 224);
         } else {
             const NetSpec::Dec* dd = nullptr;
             for (auto& d : S.dec) if (d.c1 == (int)i) dd = &d;
@@ -507,13 +507,14 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         return "";
     };
 
-    plan.xp = A.take((long long)N * H * (W + 8) * 4);
+    plan.xp = A.take((long long)N * H * (W + 8) * 4 + 64);  // + 128 B of slack: see tconv_build_stem
     __nv_bfloat16* f1 = A.take((long long)N * (H / 2) * (W / 2) * 64);
     if (!dry) {
-        IgemmLaunch L;
-        err = build_stem(ctx, L, ctx->wpk + S.convs[S.stem].wpk, plan.xp, N, H, W, f1, fold(S.convs[S.stem].bn, 1));
+        TconvLaunch TL;
+        err = tconv_build_stem(TL, plan.xp, ctx->wpk + S.convs[S.stem].wpk, N, H, W, f1, fold(S.convs[S.stem].bn, 1),
+                               ctx->d_err, ctx->num_sms);
         if (!err.empty()) return "stem: " + err;
-        add_igemm(L, "encoder.conv1");
+        plan.steps.push_back({[TL](cudaStream_t st) { return tconv_launch(TL, st); }, "encoder.conv1", 1});
     }
     int h = H / 4, w = W / 4;
     __nv_bfloat16* cur = A.take((long long)N * h * w * 64);

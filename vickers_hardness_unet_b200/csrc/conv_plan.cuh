@@ -482,6 +482,22 @@ inline cudaError_t tconv_launch_t(const TconvLaunch& L, cudaStream_t st) {
     tconv_kernel<kOcc, kIph, kStage><<<L.grid, tc_threads(kOcc), L.smem, st>>>(L.a, L.d, L.p);
     return cudaGetLastError();
 }
+// seg head: plain 16 -> 16 launch (PK_HEAD weights) whose epilogue writes logits / prob / mask; outputs are set per call
+inline cudaError_t tconv_launch_head(const TconvLaunch& L, float* logits, float* prob, uint8_t* mask, float thresh_logit,
+                                     cudaStream_t st) {
+    if (L.occ != 2 || L.iph != 2 || L.p.stage_out) return cudaErrorInvalidValue;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    TconvParams p = L.p;
+    p.logits = logits; p.prob = prob; p.mask = mask; p.thresh_logit = thresh_logit;
+    tconv_kernel<2, 2, false, true><<<L.grid, tc_threads(2), L.smem, st>>>(L.a, L.d, p);
+    return cudaGetLastError();
+}
+
 inline cudaError_t tconv_launch(const TconvLaunch& L, cudaStream_t st) {
     const int key = (L.occ == 2 ? 4 : 0) | (L.iph == 2 ? 2 : 0) | (L.p.stage_out ? 1 : 0);
     switch (key) {

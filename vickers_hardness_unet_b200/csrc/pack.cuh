@@ -8,7 +8,7 @@
 
 namespace ub {
 
-enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5, PK_HPAR = 6, PK_STEM2 = 7 };
+enum PackType { PK_CONV = 0, PK_STEM = 1, PK_DEC1 = 2, PK_DLOW = 3, PK_TAPS = 4, PK_HCONV = 5, PK_HPAR = 6, PK_STEM2 = 7, PK_HEAD = 8 };
 
 struct PackEntry {
     int type;
@@ -83,6 +83,17 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int e8 = int(i % 8), co8 = int((i / 8) % 8), g = int((i / 64) % 8), j = int(i / 512);
             const int r = j >> 2, q = j & 3, px = 2 * q + (e8 >> 2), ch = e8 & 3, co = g * 8 + co8;
             return (ch < 3 && px >= 1) ? w[((co * 3 + ch) * 7 + r) * 7 + (px - 1)] : 0.f;
+        }
+        case PK_HEAD: {  // seg head [1][16][3][3] as a 16 -> 16 tconv operand [tap][co][ci]: row 0 = bf16(w), row 1 = the
+            // bf16 of the rounding residual w - bf16(w) (the epilogue adds the two accumulator columns: fp32-accurate
+            // weights on the bf16 tensor core), rows 2..15 = 0; 32-byte rows, SWIZZLE_32B like PK_HCONV
+            const int ci = int(i % 16), co = int((i / 16) % 16), tap = int(i / 256);
+            const unsigned off = (unsigned)(i * 2);
+            dst = (off ^ (((off >> 7) & 1u) << 4)) / 2;
+            if (co > 1) return 0.f;
+            const float wv = w[ci * 9 + tap];
+            const float hi = __bfloat162float(__float2bfloat16(wv));
+            return co == 0 ? hi : wv - hi;
         }
         case PK_HPAR: {  // tconv parity operand: cout = rows, cin = cup (<= 64), a = cin_total of the OIHW tensor.
             // logical [parity][a*2+b][co][c] = sum of the 3x3 taps that land on low-res neighbour (a, b) for output

@@ -51,6 +51,13 @@ struct TconvParams {
                                     // lines per warp instruction and the LSU serialises them: measured 2100 of 5900
                                     // cycles per tile on the stem); 0: straight from registers (cout = 16, parity mode)
     int spw;                        // epilogue threads per sub-tile (named-barrier population), stage_out only
+    // segmentation-head epilogue (kHead kernels: Conv2d(16,1,3,padding=1) + bias, the conv has cout = 16 accumulator
+    // columns of which column 0 holds the bf16 high part and column 1 the bf16 low part of the fp32 weights)
+    const float* head_bias;         // [1]
+    float* logits;                  // fp32 [N,1,H,W] or nullptr
+    float* prob;                    // sigmoid(logits) or nullptr
+    uint8_t* mask;                  // {0,255} = logits >= thresh_logit, or nullptr
+    float thresh_logit;
     int* err;
     long long* prof;                // selftest only: [grid][16] cycle counters per role phase (dbg & 8)
     int dbg;                        // selftest only: 1 = skip halo loads, 2 = skip MMA issue, 4 = skip epilogue math + stores
@@ -147,7 +154,7 @@ __device__ __forceinline__ void tc_issue_stem(uint32_t d_tmem, uint32_t stage_ad
 }
 
 // kIph = accumulator column groups (16 channels of one sub-tile) each epilogue thread handles per pipeline step
-template <int kOcc, int kIph, bool kStage>
+template <int kOcc, int kIph, bool kStage, bool kHead = false>
 __global__ void __launch_bounds__(tc_threads(kOcc), kOcc)
 tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ TconvParams P) {
@@ -342,6 +349,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
         const int n_mine = items - i0 < kIph ? (items - i0 > 0 ? items - i0 : 0) : kIph;
+        const float head_bias = kHead ? __ldg(P.head_bias) : 0.f;
         // staged stores: all items of a thread belong to ONE sub-tile (host guarantees kIph divides cout/16)
         const int my_sub = it_s[0];
         const uint32_t out_row_bytes = (uint32_t)P.cout * 2u, out_swz = out_row_bytes / 16u - 1u;
@@ -389,6 +397,17 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
                 if (k >= n_mine || (P.dbg & 4)) continue;
+                if (kHead) {
+                    // fp32 logit = (w_hi + w_lo) . x + bias; sigmoid(x) >= t  <=>  x >= logit(t)
+                    if (valid[k]) {
+                        const float lg = __uint_as_float(r[0]) + __uint_as_float(r[1]) + head_bias;
+                        const size_t o = (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]);
+                        if (P.logits) P.logits[o] = lg;
+                        if (P.prob) P.prob[o] = 1.f / (1.f + __expf(-lg));
+                        if (P.mask) P.mask[o] = lg >= P.thresh_logit ? 255 : 0;
+                    }
+                    continue;
+                }
                 const int c0 = it_c0[k];
                 float v[16];
 #pragma unroll

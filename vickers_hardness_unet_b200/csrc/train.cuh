@@ -49,6 +49,7 @@ struct TrainPlan {
     __nv_bfloat16* xp = nullptr;
     __nv_bfloat16* head_in = nullptr;   // activation feeding the seg head
     __nv_bfloat16* d_head_in = nullptr; // its gradient
+    TconvLaunch head_fwd;               // seg head forward on the tensor core (logits pointer patched per call)
     std::vector<Unit> units;
     std::vector<LaunchFn> fwd;          // after input pack, before head
     std::vector<LaunchFn> bwd[4];       // stage 0: decoder, 1: layer4, 2: layer3, 3: layer2 + layer1 + stem
@@ -532,6 +533,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         decs.push_back(r);
     }
     plan.head_in = cur;
+    if (!dry) {
+        err = tconv_build(plan.head_fwd, cur, 16, false, ctx->wpk + S.convs[S.head].wpk, 16, N, H, W, nullptr,
+                          EpilogueDesc(), ctx->d_err, SM);
+        if (!err.empty()) return "segmentation_head: " + err;
+        plan.head_fwd.p.head_bias = ctx->head_w + 144;
+    }
     plan.d_head_in = A.take((long long)N * H * W * 16);
     // gradient buffers w.r.t. unit outputs `a` (dA): one per unit
     std::vector<__nv_bfloat16*> dA(plan.units.size(), nullptr);
@@ -1023,10 +1030,7 @@ inline int ctx_train_forward(Ctx* ctx, const float* x, float* logits, const floa
         UB_CUDA(P->fwd[i](st));
     }
     ctx->prof_mark("head_fwd:segmentation_head", st);
-    dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
-    head_conv_kernel<<<grid, 256, 0, st>>>(P->head_in, ctx->head_w, ctx->head_w + 144, logits, nullptr, nullptr, 0.f, N, H,
-                                           W);
-    UB_CUDA(cudaGetLastError());
+    UB_CUDA(tconv_launch_head(P->head_fwd, logits, nullptr, nullptr, 0.f, st));
     ctx->prof_mark("end:forward", st);
     return 0;
 }

@@ -137,7 +137,12 @@ struct NetSpec {
         // packed bf16 weight arena (forward operands)
         for (size_t i = 0; i < convs.size(); ++i) {
             ConvRef& c = convs[i];
-            if ((int)i == head) continue;
+            if ((int)i == head) {  // 16 -> 16 tconv operand, rows 0 / 1 = bf16 high / low parts of the fp32 weights (PK_HEAD)
+                c.wpk = wpk_total;
+                c.wpk_elems = 9 * 16 * 16;
+                wpk_total += c.wpk_elems;
+                continue;
+            }
             long long n;
             if ((int)i == stem) n = 64 * 224;
             else n = (long long)c.cout * c.cin * c.k * c.k;
@@ -186,6 +191,7 @@ struct Ctx {
         int N = 0;
         __nv_bfloat16* xp = nullptr;
         __nv_bfloat16* head_in = nullptr;
+        TconvLaunch head;   // seg head on the tensor core (outputs patched per call)
         struct Step {
             std::function<cudaError_t(cudaStream_t)> fn;
             std::string name;
@@ -286,8 +292,11 @@ inline std::string ctx_build_pack_tables(Ctx* ctx) {
     PackTable& T = ctx->fwd_pack;
     for (size_t i = 0; i < S.convs.size(); ++i) {
         const ConvRef& c = S.convs[i];
-        if ((int)i == S.head) continue;
         PackEntry e;
+        if ((int)i == S.head) {
+            T.add(pk_entry(PK_HEAD, c.w, c.wpk, 9 * 16 * 16));
+            continue;
+        }
         if (c.tc == 2) {
             e = pk_entry(PK_HPAR, c.w, c.wpk, tconv_w_elems(c.cin, c.cout, true));
             e.cout = c.cout; e.cin = c.cin; e.a = c.cin; e.b = 0; e.c = 0;
@@ -592,6 +601,12 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         w *= 2;
     }
     plan.head_in = cur;
+    if (!dry) {
+        err = tconv_build(plan.head, cur, 16, false, ctx->wpk + S.convs[S.head].wpk, 16, N, h, w, nullptr, EpilogueDesc(),
+                          ctx->d_err, ctx->num_sms);
+        if (!err.empty()) return "segmentation_head: " + err;
+        plan.head.p.head_bias = ctx->head_w + 144;
+    }
     plan.launches = (int)plan.steps.size() + 2;  // + input pack + head
     if (arena_needed) *arena_needed = A.off;
     return "";
@@ -639,9 +654,7 @@ inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* pro
     if (thresh <= 0.f) tl = -INFINITY;
     else if (thresh >= 1.f) tl = INFINITY;
     else tl = logf(thresh / (1.f - thresh));
-    dim3 grid((W + kHeadTile - 1) / kHeadTile, (H + kHeadTile - 1) / kHeadTile, N);
-    head_conv_kernel<<<grid, 256, 0, st>>>(P.head_in, ctx->head_w, ctx->head_w + 144, logits, prob, mask, tl, N, H, W);
-    UB_CUDA(cudaGetLastError());
+    UB_CUDA(tconv_launch_head(P.head, logits, prob, mask, tl, st));
     mark();
     UB_CUDA(cudaEventRecord(ctx->arena_event, st));
     ctx->arena_stream = st;

@@ -38,8 +38,10 @@ def _r(t: torch.Tensor) -> torch.Tensor:
     return _RoundSTE.apply(t)
 
 
-def _dec_conv1_parity(x_low, skip, w, cup):
-    """cat(nearest2x(x_low), skip) (*) w, computed as the CUDA path does: 4 output parities, summed 2x2 weights."""
+def _dec_conv1_parity(x_low, skip, w, cup, round_up_part=False):
+    """cat(nearest2x(x_low), skip) (*) w, computed as the CUDA path does: 4 output parities, summed 2x2 weights.
+    round_up_part: the contribution of the up-sampled channels is stored in bf16 before the skip part is added (decoder
+    block 3: two tconv launches, csrc/unet.cuh tc == 3)."""
     N, _, Hl, Wl = x_low.shape
     cout = w.shape[0]
     w_up, w_sk = w[:, :cup], w[:, cup:]
@@ -55,6 +57,8 @@ def _dec_conv1_parity(x_low, skip, w, cup):
             # low-res taps at offsets (a-1+ph, b-1+pw): pad so that a 2x2 VALID conv lines up
             xp = F.pad(x_low, (1 - pw, pw, 1 - ph, ph))
             acc = F.conv2d(xp, weff)
+            if round_up_part:
+                acc = _r(acc)
             if full is not None:
                 acc = acc + full[:, :, ph::2, pw::2]
             cols.append(acc)
@@ -62,9 +66,9 @@ def _dec_conv1_parity(x_low, skip, w, cup):
     return torch.stack(rows, -2).reshape(N, cout, 2 * Hl, 2 * Wl)              # interleave the two row parities
 
 
-# decoder blocks whose conv1 runs on the halo-resident kernel (plain bf16 3x3 weights over cat(up(x), skip), csrc/hconv.cuh);
-# the others use the parity-folded 2x2 weights on the low-res tensor (csrc/unet.cuh::build_dec1)
-HCONV_DECODER_BLOCKS = (3, 4)
+# every decoder conv1 uses the parity-folded 2x2 weights on the low-res tensor for its up-sampled channels (tap-table
+# kernel for blocks 0-2, tconv parity mode for blocks 3-4); block 3 additionally stores that part in bf16 (two launches)
+SPLIT_DECODER_BLOCKS = (3,)
 
 
 def emulated_forward(o, x, train: bool):
@@ -97,12 +101,7 @@ def emulated_forward(o, x, train: bool):
     skips = [feats[3], feats[2], feats[1], feats[0], None]
     cups = [512, 256, 128, 64, 32]
     for i, blk in enumerate(o.decoder.blocks):
-        if i in HCONV_DECODER_BLOCKS:
-            up = t.repeat_interleave(2, 2).repeat_interleave(2, 3)
-            cat = torch.cat([up, skips[i]], 1) if skips[i] is not None else up
-            z = F.conv2d(cat, _r(blk.conv1[0].weight), None, 1, 1)
-        else:
-            z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i])
+        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i], round_up_part=i in SPLIT_DECODER_BLOCKS)
         u = _r(F.relu(bn(z, blk.conv1[1])))
         t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
     head = o.segmentation_head[0]

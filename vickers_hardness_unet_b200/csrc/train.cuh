@@ -489,11 +489,28 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         // unit 1: output at 2h x 2w; Hin/Win recorded as the OUTPUT resolution (stride-1 bookkeeping)
         r.u1 = new_unit(d.c1, 2 * h, 2 * w);
         r.u2 = new_unit(d.c2, 2 * h, 2 * w);
+        __nv_bfloat16* zup = S.convs[d.c1].tc == 3 ? A.take((long long)N * (2 * h) * (2 * w) * d.cout) : nullptr;
         if (!dry) {
             const Unit u1 = plan.units[r.u1];
             StatSegs segs;
             memset(&segs, 0, sizeof(segs));
-            if (S.convs[d.c1].tc == 2) {
+            if (S.convs[d.c1].tc == 3) {
+                // launch 1: conv over the up-sampled channels (parity folding on the low-res tensor) -> zup (bf16);
+                // launch 2: z = conv over the skip channels + zup, batch statistics of z in its epilogue
+                const ConvRef& cc = S.convs[d.c1];
+                EpilogueDesc e1, e2;
+                e2.stats = plan.stat_part;
+                e2.residual = nhwc_view(zup, N, 2 * h, 2 * w, d.cout);
+                TconvLaunch T1, T2;
+                err = tconv_build(T1, cur, d.cup, true, ctx->wpk + cc.wpk, d.cout, N, 2 * h, 2 * w, zup, e1, ctx->d_err, SM);
+                if (err.empty())
+                    err = tconv_build(T2, skips[i], d.cskip, false, ctx->wpk + cc.wpk2, d.cout, N, 2 * h, 2 * w, u1.z, e2,
+                                      ctx->d_err, SM);
+                if (!err.empty()) return cc.name + ": " + err;
+                add_f("conv_fwd:" + cc.name + "[up]", [T1](cudaStream_t st) { return tconv_launch(T1, st); });
+                add_f("conv_fwd:" + cc.name + "[skip]", [T2](cudaStream_t st) { return tconv_launch(T2, st); });
+                segs.n = 1; segs.ptr[0] = e2.stats; segs.rows[0] = T2.grid;
+            } else if (S.convs[d.c1].tc == 2) {
                 // nearest-2x upsample folded into four parity convolutions on the low-res tensor (tconv.cuh)
                 EpilogueDesc ep;
                 ep.stats = plan.stat_part;

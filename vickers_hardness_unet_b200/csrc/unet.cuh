@@ -43,7 +43,10 @@ struct ConvRef {
     long long wpk_elems = 0;
     int hc = 0;           // > 0: runs on the halo-resident kernel (hconv.cuh) with this many pipeline stages
     int hc_cup = 0;       // hconv: channels taken from the nearest-2x up-sampled low-res source (decoder conv1)
-    int tc = 0;           // 1: runs on the TMA halo kernel (tconv.cuh), 2: its parity mode (up-sampled input, no skip)
+    int tc = 0;           // 1: runs on the TMA halo kernel (tconv.cuh), 2: its parity mode (up-sampled input, no skip),
+                          // 3: decoder conv1 split into two tconv launches: parity mode over the up-sampled channels
+                          //    (scaled, bf16) then plain mode over the skip channels with that as the residual
+    long long wpk2 = -1;  // tc == 3: offset of the second (skip-channel) operand
 };
 
 struct NetSpec {
@@ -159,10 +162,15 @@ struct NetSpec {
                     c.tc = 2;
                     if (tconv_w_elems(c.cin, c.cout, true) > n) n = tconv_w_elems(c.cin, c.cout, true);
                 }
+                if (c.hc && cup > 0 && cup < c.cin && tconv_ok(cup, c.cout, true) && tconv_ok(c.cin - cup, c.cout, false)) {
+                    c.tc = 3;
+                    n = tconv_w_elems(cup, c.cout, true) + tconv_w_elems(c.cin - cup, c.cout, false);
+                }
             }
             (void)is_dec1;
             c.wpk = wpk_total;
             c.wpk_elems = n;
+            if (c.tc == 3) c.wpk2 = c.wpk + tconv_w_elems(c.hc_cup, c.cout, true);
             wpk_total += (n + 63) & ~63ll;  // keep every matrix 128 B aligned
         }
     }
@@ -297,7 +305,14 @@ inline std::string ctx_build_pack_tables(Ctx* ctx) {
             T.add(pk_entry(PK_HEAD, c.w, c.wpk, 9 * 16 * 16));
             continue;
         }
-        if (c.tc == 2) {
+        if (c.tc == 3) {
+            const int cup = c.hc_cup, cskip = c.cin - cup;
+            e = pk_entry(PK_HPAR, c.w, c.wpk, tconv_w_elems(cup, c.cout, true));
+            e.cout = c.cout; e.cin = cup; e.a = c.cin;
+            T.add(e);
+            e = pk_entry(PK_HCONV, c.w, c.wpk2, tconv_w_elems(cskip, c.cout, false));
+            e.cout = c.cout; e.cin = cskip; e.a = c.cin; e.b = cup; e.c = 0;
+        } else if (c.tc == 2) {
             e = pk_entry(PK_HPAR, c.w, c.wpk, tconv_w_elems(c.cin, c.cout, true));
             e.cout = c.cout; e.cin = c.cin; e.a = c.cin; e.b = 0; e.c = 0;
         } else if (c.hc) {
@@ -571,8 +586,24 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         const ConvRef& c2 = S.convs[d.c2];
         __nv_bfloat16* t = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         __nv_bfloat16* o = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
+        __nv_bfloat16* r = c1.tc == 3 ? A.take((long long)N * (2 * h) * (2 * w) * d.cout) : nullptr;
         if (!dry) {
-            if (c1.tc == 2) {
+            if (c1.tc == 3) {
+                // launch 1: scale * conv(up-sampled channels) by parity folding on the low-res tensor -> r (bf16);
+                // launch 2: relu(scale * conv(skip channels) + shift + r).  Nothing up-sampled or concatenated exists.
+                EpilogueDesc e1, e2 = fold(c1.bn, 1);
+                e1.scale = e2.scale;
+                e2.residual = nhwc_view(r, N, 2 * h, 2 * w, d.cout);
+                TconvLaunch T1, T2;
+                err = tconv_build(T1, cur, d.cup, true, ctx->wpk + c1.wpk, d.cout, N, 2 * h, 2 * w, r, e1, ctx->d_err,
+                                  ctx->num_sms);
+                if (err.empty())
+                    err = tconv_build(T2, skips[i], d.cskip, false, ctx->wpk + c1.wpk2, d.cout, N, 2 * h, 2 * w, t, e2,
+                                      ctx->d_err, ctx->num_sms);
+                if (!err.empty()) return c1.name + ": " + err;
+                plan.steps.push_back({[T1](cudaStream_t st) { return tconv_launch(T1, st); }, c1.name + "[up]", 1});
+                plan.steps.push_back({[T2](cudaStream_t st) { return tconv_launch(T2, st); }, c1.name + "[skip]", 1});
+            } else if (c1.tc == 2) {
                 // nearest-2x upsample folded into four 2x2-tap parity convolutions on the low-res tensor: ONE launch
                 TconvLaunch TL;
                 err = tconv_build(TL, cur, d.cup, true, ctx->wpk + c1.wpk, d.cout, N, 2 * h, 2 * w, t, fold(c1.bn, 1),

@@ -381,7 +381,7 @@ def main():
             conv_ms = prof["igemm_ms"]
             conv_tf = gflop * B / (conv_ms * 1e-3) / 1e3
             roof.update({"achieved": conv_tf, "frac": conv_tf / pk["bf16_tflops_sustained"],
-                         "kernel": "ub::igemm_kernel (all conv launches of one step, algorithmic FLOPs)",
+                         "kernel": "conv stack = all ub::wconv_kernel / tconv_kernel / igemm_kernel launches of one step (algorithmic FLOPs)",
                          "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / prof["total_ms"],
                          "launches_per_step": prof["n_igemm"]})
             if a.profile_out:

@@ -277,6 +277,82 @@ static void case_stem(const char* name, int N, int H, int W) {
     cudaFree(d_x); cudaFree(d_w); cudaFree(d_xp); cudaFree(d_wpk); cudaFree(d_out);
 }
 
+// wide decoder conv1 as two halo-resident launches: wpconv (parity-folded up-sampled channels -> bf16 partial) and wconv
+// over the skip channels with that partial as the residual; same reference as case_dec1.  iters > 0: time both.
+static void case_dec1_split(const char* name, int N, int Hl, int Wl, int cup, int cskip, int cout, int iters = 0) {
+    HostT low(N, Hl, Wl, cup);
+    fill_rand_bf16(low.v, 1.0f);
+    HostT skip(N, 2 * Hl, 2 * Wl, cskip);
+    fill_rand_bf16(skip.v, 1.0f);
+    const int cin = cup + cskip;
+    std::vector<float> w((size_t)cout * cin * 9);
+    const float ws = 1.0f / sqrtf((float)cin * 9);
+    for (auto& x : w) x = frand() * ws;
+    __nv_bfloat16* d_low = to_dev_bf16(low.v);
+    __nv_bfloat16* d_skip = to_dev_bf16(skip.v);
+    float* d_w = to_dev_f32(w);
+    const long long kt = 9 * cskip + 4 * cup;
+    const size_t out_e = (size_t)N * 4 * Hl * Wl * cout;
+    __nv_bfloat16 *d_wpk, *d_part, *d_out;
+    CK(cudaMalloc(&d_wpk, 4 * cout * kt * 2));
+    CK(cudaMalloc(&d_part, out_e * 2));
+    CK(cudaMalloc(&d_out, out_e * 2));
+    CK(cudaMemset(d_part, 0xFF, out_e * 2));
+    CK(cudaMemset(d_out, 0xFF, out_e * 2));
+    pack_dec1_w_kernel<<<64, 256>>>(d_w, d_wpk, cout, cup, cskip);
+    WpconvLaunch L1;
+    std::string e = wpconv_build(L1, d_low, cup, d_wpk, (int)kt, 9 * cskip, cout, N, Hl, Wl, d_part, nullptr, g_ctx->d_err,
+                                 g_ctx->num_sms);
+    EpilogueDesc ep;
+    ep.relu = 1;
+    ep.residual = nhwc_view(d_part, N, 2 * Hl, 2 * Wl, cout);
+    WconvLaunch L2;
+    if (e.empty())
+        e = wconv_build(L2, d_skip, cskip, d_wpk, cout, N, 2 * Hl, 2 * Wl, d_out, ep, g_ctx->d_err, g_ctx->num_sms, kt);
+    if (!e.empty()) {
+        printf("[FAIL] %s: build: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: wpconv grid %d bstages %d tiles %dx%dx%d n_tiles %d | wconv grid %d\n", name, L1.grid, L1.p.bstages,
+           L1.p.tiles_w, L1.p.tiles_h, N, L1.p.n_tiles, L2.grid);
+    CK(wpconv_launch(L1, 0));
+    CK(wconv_launch(L2, 0));
+    CK(cudaDeviceSynchronize());
+    if (check_err_flag(name)) return;
+    if (iters > 0) {
+        cudaEvent_t e0, e1, e2;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        float m1 = 0, m2 = 0;
+        for (int i = 0; i < iters; ++i) {
+            cudaEventRecord(e0);
+            CK(wpconv_launch(L1, 0));
+            cudaEventRecord(e1);
+            CK(wconv_launch(L2, 0));
+            cudaEventRecord(e2);
+            CK(cudaDeviceSynchronize());
+            float a, b;
+            cudaEventElapsedTime(&a, e0, e1);
+            cudaEventElapsedTime(&b, e1, e2);
+            m1 += a; m2 += b;
+        }
+        printf("[BENCH-D] %-34s wpconv %7.1f us + wconv(skip,+res) %7.1f us\n", name, m1 / iters * 1e3, m2 / iters * 1e3);
+    } else {
+        HostT cat(N, 2 * Hl, 2 * Wl, cin);
+        for (int n = 0; n < N; ++n)
+            for (int h = 0; h < 2 * Hl; ++h)
+                for (int ww = 0; ww < 2 * Wl; ++ww) {
+                    for (int c = 0; c < cup; ++c) cat.at(n, h, ww, c) = low.get(n, h / 2, ww / 2, c);
+                    for (int c = 0; c < cskip; ++c) cat.at(n, h, ww, cup + c) = skip.get(n, h, ww, c);
+                }
+        HostT ref = cpu_conv(cat, w, cout, 3, 1, 1);
+        for (auto& v : ref.v) v = fmaxf(v, 0.f);
+        std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
+        report(name, compare(got, ref.v), 0.02, got, ref.v, cout);
+    }
+    cudaFree(d_low); cudaFree(d_skip); cudaFree(d_w); cudaFree(d_wpk); cudaFree(d_part); cudaFree(d_out);
+}
+
 // the same stem through tconv's overlapped-row (non-swizzled descriptor) mode; iters > 0: also time it
 static void case_tstem(const char* name, int N, int H, int W, bool stats, int iters = 0) {
     std::vector<float> x((size_t)N * 3 * H * W);
@@ -1090,6 +1166,15 @@ int main(int argc, char** argv) {
         case_tconv("tconv parity up32->16 2x32x64", 2, 32, 64, 32, 16, true, false, true, true, true);
         case_tconv("tconv parity up32->16 7x96x80 (multi-tile, partial)", 7, 96, 80, 32, 16, true, false, true, true, true);
         case_tconv("tconv parity up64->32 1x32x32", 1, 32, 32, 64, 32, true, false, true, true, false);
+    }
+    if (want("split")) {
+        case_dec1_split("split up128+skip128->128 1x8x8", 1, 8, 8, 128, 128, 128);
+        case_dec1_split("split up512+skip256->256 2x16x16", 2, 16, 16, 512, 256, 256);
+        case_dec1_split("split up256+skip128->128 3x24x40 (partial tiles)", 3, 24, 40, 256, 128, 128);
+    }
+    if (want("dbench")) {
+        case_dec1_split("D0c1 up512+skip256->256 @32^2 x32", 32, 16, 16, 512, 256, 256, 10);
+        case_dec1_split("D1c1 up256+skip128->128 @64^2 x32", 32, 32, 32, 256, 128, 128, 10);
     }
     if (want("wide")) {
         case_wconv("wide 128->128 1x16x16", 1, 16, 16, 128, 128, false, true, true, true);

@@ -223,8 +223,8 @@ int unetb200_profile_infer(unetb200_ctx* h, const float* x_dev, float* logits_de
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
         ms_out[i] = ms;
-        // launch 0 = input pack, last = head, others = plan steps
-        is_igemm_out[i] = (i >= 1 && i <= (int)plan.steps.size()) ? plan.steps[i - 1].is_igemm : 0;
+        // launch 0 = input pack, last = seg head (a tensor-core conv launch), others = plan steps
+        is_igemm_out[i] = (i >= 1 && i <= (int)plan.steps.size()) ? plan.steps[i - 1].is_igemm : (i == n - 1 ? 1 : 0);
     }
     for (auto e : ev) cudaEventDestroy(e);
     if (n_out) *n_out = n;

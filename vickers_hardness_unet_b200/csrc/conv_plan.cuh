@@ -522,8 +522,10 @@ struct WconvLaunch {
 inline bool wconv_ok(int cin, int cout) { return cin >= 64 && cin % 64 == 0 && cout >= 128 && cout % 128 == 0 && cout <= 512; }
 
 // 3x3/s1/p1 conv src[N,H,W,cin] -> out[N,H,W,cout]; wpk = K-major packed weights [cout][(r*3+s)*cin + ci] (pack_conv_w)
+// ldb: row pitch (elements) of the packed weight matrix when it is wider than 9*cin (a decoder conv1's PK_DEC1 matrix,
+// whose first 9*cskip columns are exactly the skip-channel operand); 0 = dense.
 inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const void* wpk, int cout, int N, int H, int W,
-                               void* out, const EpilogueDesc& ep, int* err, int num_sms) {
+                               void* out, const EpilogueDesc& ep, int* err, int num_sms, long long ldb = 0) {
     memset(&L.p, 0, sizeof(L.p));
     WconvParams& P = L.p;
     if (!wconv_ok(cin, cout)) return "wconv: unsupported channel configuration";
@@ -554,7 +556,7 @@ inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const v
     }
     {
         uint64_t dims[2] = {(uint64_t)9 * cin, (uint64_t)cout};
-        uint64_t str[1] = {(uint64_t)9 * cin * 2};
+        uint64_t str[1] = {(uint64_t)(ldb ? ldb : 9ll * cin) * 2};
         uint32_t box[2] = {64, (uint32_t)kWcN};
         uint32_t es[2] = {1, 1};
         std::string e = make_tmap_bf16(&L.b, wpk, 2, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -573,6 +575,66 @@ inline cudaError_t wconv_launch(const WconvLaunch& L, cudaStream_t st) {
         attr_set = true;
     }
     wconv_kernel<<<L.grid, kWcThreads, L.smem, st>>>(L.a, L.b, L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ wpconv (wide parity conv)
+struct WpconvLaunch {
+    CUtensorMap a, b;
+    WpconvParams p;
+    int grid = 0;
+    uint32_t smem = 0;
+};
+inline bool wpconv_ok(int cup, int cout) { return cup >= 64 && cup % 64 == 0 && cout >= 64 && cout % 64 == 0 && cout <= 512; }
+
+// out[N, 2Hl, 2Wl, cout] = scale * conv3x3(nearest2x(low[N,Hl,Wl,cup])) by parity folding.  wpk_dec1 = the PK_DEC1 matrix
+// [4 parities][cout][kt], kt = 9*cskip + 4*cup (low taps start at column koff = 9*cskip).
+inline std::string wpconv_build(WpconvLaunch& L, const void* low, int cup, const void* wpk_dec1, int kt, int koff, int cout,
+                                int N, int Hl, int Wl, void* out, const float* scale, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    WpconvParams& P = L.p;
+    if (!wpconv_ok(cup, cout)) return "wpconv: unsupported channel configuration";
+    P.Hl = Hl; P.Wl = Wl; P.N = N;
+    P.tiles_w = (Wl + 15) / 16;
+    P.tiles_h = (Hl + 15) / 16;
+    P.n_tiles = cout / 64;
+    P.cup = cup; P.cout = cout; P.koff = koff;
+    P.scale = scale;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.err = err;
+    int bst = 16;
+    while (bst > 2 && wpconv_smem(bst).total + 1024 > 232448u) --bst;
+    P.bstages = bst;
+    L.smem = wpconv_smem(bst).total + 1024;
+    {
+        uint64_t dims[4] = {(uint64_t)cup, (uint64_t)Wl, (uint64_t)Hl, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cup * 2, (uint64_t)Wl * cup * 2, (uint64_t)Hl * Wl * cup * 2};
+        uint32_t box[4] = {64, 18, 18, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.a, low, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!e.empty()) return "wpconv A map: " + e;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)kt, (uint64_t)4 * cout};
+        uint64_t str[1] = {(uint64_t)kt * 2};
+        uint32_t box[2] = {64, 64};
+        uint32_t es[2] = {1, 1};
+        std::string e = make_tmap_bf16(&L.b, wpk_dec1, 2, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!e.empty()) return "wpconv B map: " + e;
+    }
+    const int total = P.tiles_w * P.tiles_h * N * P.n_tiles;
+    const int waves = (total + num_sms - 1) / num_sms;
+    L.grid = (total + waves - 1) / waves;
+    return "";
+}
+inline cudaError_t wpconv_launch(const WpconvLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wpconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    wpconv_kernel<<<L.grid, kWcThreads, L.smem, st>>>(L.a, L.b, L.p);
     return cudaGetLastError();
 }
 

@@ -323,4 +323,249 @@ done:
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ wpconv (parity mode)
+// The up-sampled half of a wide decoder conv1 (decoder.blocks.0-2): out = scale * conv3x3(nearest2x(low)) computed on the
+// LOW-RES tensor as four 2x2-tap parity convolutions (weights summed per parity: the PK_DEC1 packed matrix the tap-table
+// kernel uses, columns [koff, koff + 4*cup)), written as a bf16 partial that the skip-channel conv (wconv / tconv) then
+// adds through its residual path — nothing up-sampled or concatenated ever exists in memory, and the 4 parity launches
+// + two-source tap table of the igemm path (23 % of the inference step) become two halo-resident launches.
+// Per 64-channel K chunk: ONE TMA halo box [64 ch, 18, 18, 1] of a 16 x 16 low-res tile (two 128-pixel sub-tiles) and
+// sixteen [64 cout x 64 ch] weight tiles (parity x tap), each used by both sub-tiles.  Accumulators: 4 parities x 2
+// sub-tiles x 64 columns = all 512 TMEM columns (single buffered: the epilogue of an item is ~10 % of its MMA time).
+struct WpconvParams {
+    int Hl, Wl, N;                     // LOW-RES extent; the output is [N, 2*Hl, 2*Wl, cout]
+    int tiles_w, tiles_h, n_tiles;     // 16 x 16 low-res tiles per image; cout / 64
+    int cup, cout, koff;               // K chunks = cup / 64; koff = first low-tap column of the packed weight matrix
+    int bstages;
+    const float* scale;                // [cout] or nullptr
+    __nv_bfloat16* out;
+    int* err;
+};
+constexpr uint32_t kWpBStage = 64 * 128;   // 8 KB
+
+struct WpconvSmem {
+    uint32_t ss_off, bar_off, halo_off, b_off, total;
+};
+__host__ __device__ inline WpconvSmem wpconv_smem(int bstages) {
+    WpconvSmem s;
+    s.ss_off = 0;                      // scale[512]
+    s.bar_off = 2048;
+    s.halo_off = 3072;
+    s.b_off = s.halo_off + kWcHaloStages * kWcHaloStage;
+    s.total = s.b_off + bstages * kWpBStage;
+    return s;
+}
+
+__global__ void __launch_bounds__(kWcThreads, 1)
+wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ WpconvParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw_addr);
+    const WpconvSmem L = wpconv_smem(P.bstages);
+    const uint32_t bar0 = base + L.bar_off;
+    auto hfull = [&](int s) { return bar0 + 8u * s; };
+    auto hempty = [&](int s) { return bar0 + 8u * (2 + s); };
+    const uint32_t tfull = bar0 + 8u * 4, tempty = bar0 + 8u * 5;
+    auto bfull = [&](int s) { return bar0 + 8u * (6 + s); };
+    auto bempty = [&](int s) { return bar0 + 8u * (6 + P.bstages + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bar_off + (6 + 2 * P.bstages) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_items = P.tiles_w * P.tiles_h * P.N * P.n_tiles;
+    const int chunks = P.cup >> 6;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(hfull(s), 1);
+            mbar_init(hempty(s), 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 16);
+        for (int s = 0; s < P.bstages; ++s) {
+            mbar_init(bfull(s), 1);
+            mbar_init(bempty(s), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+        tmem_relinquish();
+    }
+    {
+        float* ss = reinterpret_cast<float*>(sm + L.ss_off);
+        for (int c = threadIdx.x; c < 512; c += kWcThreads) ss[c] = (P.scale && c < P.cout) ? P.scale[c] : 1.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto decode = [&](int item, int& nt, int& tw, int& th, int& tn) {
+        nt = item % P.n_tiles;
+        int t = item / P.n_tiles;
+        tw = t % P.tiles_w;
+        t /= P.tiles_w;
+        th = t % P.tiles_h;
+        tn = t / P.tiles_h;
+    };
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one thread)
+        if (lane == 0) {
+            int hs = 0, bs = 0;
+            uint32_t hph = 0, bph = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                int nt, tw, th, tn;
+                decode(item, nt, tw, th, tn);
+                for (int c = 0; c < chunks; ++c) {
+                    if (!mbar_wait(hempty(hs), hph ^ 1)) {
+                        atomicExch(P.err, 51);
+                        goto done;
+                    }
+                    mbar_expect_tx(hfull(hs), kWcHaloBytes);
+                    tma_load_4d(base + L.halo_off + hs * kWcHaloStage, &tmA, hfull(hs), c * 64, tw * 16 - 1, th * 16 - 1, tn);
+                    if (++hs == kWcHaloStages) {
+                        hs = 0;
+                        hph ^= 1;
+                    }
+                    for (int pt = 0; pt < 16; ++pt) {  // parity (pt >> 2) x low-res neighbour (pt & 3)
+                        if (!mbar_wait(bempty(bs), bph ^ 1)) {
+                            atomicExch(P.err, 52);
+                            goto done;
+                        }
+                        mbar_expect_tx(bfull(bs), kWpBStage);
+                        tma_load_2d(base + L.b_off + bs * kWpBStage, &tmB, bfull(bs), P.koff + (pt & 3) * P.cup + c * 64,
+                                    (pt >> 2) * P.cout + nt * 64);
+                        if (++bs == P.bstages) {
+                            bs = 0;
+                            bph ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one thread)
+        if (lane == 0) {
+            int hs = 0, bs = 0;
+            uint32_t hph = 0, bph = 0, aph = 0;
+            const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+            const uint64_t a_desc0 = umma_desc(base + L.halo_off, 16, 18 * 128, 2u);
+            const uint64_t b_desc0 = umma_desc(base + L.b_off, 16, 8 * 128, 2u);
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                if (!mbar_wait(tempty, aph ^ 1)) {
+                    atomicExch(P.err, 53);
+                    goto done;
+                }
+                tc_fence_after();
+                for (int c = 0; c < chunks; ++c) {
+                    if (!mbar_wait(hfull(hs), hph)) {
+                        atomicExch(P.err, 54);
+                        goto done;
+                    }
+                    tc_fence_after();
+                    const uint64_t a_base = a_desc0 + (uint64_t)((hs * kWcHaloStage) >> 4);
+#pragma unroll
+                    for (int pt = 0; pt < 16; ++pt) {
+                        if (!mbar_wait(bfull(bs), bph)) {
+                            atomicExch(P.err, 55);
+                            goto done;
+                        }
+                        tc_fence_after();
+                        const int par = pt >> 2, ab = pt & 3;
+                        const uint64_t bd = b_desc0 + (uint64_t)((bs * kWpBStage) >> 4);
+                        // low-res neighbour (a, b) of output parity (ph, pw) sits at halo pixel (a + ph, b + pw)
+                        const uint64_t ad = a_base + (uint32_t)(((((ab >> 1) + (par >> 1)) * 18 + (ab & 1) + (par & 1)) * 128) >> 4);
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint64_t a = ad + (uint32_t)((s * 8 * 128 + kk * 32) >> 4);
+                                const uint64_t b = bd + (uint32_t)((kk * 32) >> 4);
+                                const uint32_t d = tmem_base + (par * 2 + s) * 64;
+                                if (ab == 0 && kk == 0) umma_bf16(d, a, b, idesc, c > 0 ? 1u : 0u);
+                                else umma_bf16_c<true>(d, a, b, idesc);
+                            }
+                        }
+                        umma_commit(bempty(bs));
+                        if (++bs == P.bstages) {
+                            bs = 0;
+                            bph ^= 1;
+                        }
+                    }
+                    umma_commit(hempty(hs));
+                    if (++hs == kWcHaloStages) {
+                        hs = 0;
+                        hph ^= 1;
+                    }
+                }
+                umma_commit(tfull);
+                aph ^= 1;
+            }
+        }
+    } else {
+        // ================================================================= epilogue (16 warps): warp group g = output parity
+        const int e = warp - 2;
+        const int q = warp & 3;
+        const int par = e >> 2, ph = par >> 1, pw = par & 1;
+        const int row = q * 32 + lane;
+        const int wl = row & 7, hl = row >> 3;
+        const float* ss = reinterpret_cast<const float*>(sm + L.ss_off);
+        const int Ho = 2 * P.Hl, Wo = 2 * P.Wl;
+        uint32_t aph = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            int nt, tw, th, tn;
+            decode(item, nt, tw, th, tn);
+            if (!mbar_wait_warp(tfull, aph, lane)) {
+                atomicExch(P.err, 56);
+                goto done;
+            }
+            tc_fence_after();
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int lh = th * 16 + hl, lw = tw * 16 + s * 8 + wl;
+                const bool valid = lh < P.Hl && lw < P.Wl;
+                __nv_bfloat16* op = P.out + (((size_t)tn * Ho + 2 * lh + ph) * Wo + 2 * lw + pw) * P.cout + nt * 64;
+                const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (par * 2 + s) * 64;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + half * 32, r);
+                    tmem_ld_wait();
+                    if (s == 1 && half == 1) {  // last TMEM read of this item: hand the accumulators back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = nt * 64 + half * 32 + j * 8;
+                        const float4 sc0 = *reinterpret_cast<const float4*>(ss + c);
+                        const float4 sc1 = *reinterpret_cast<const float4*>(ss + c + 4);
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(r[j * 8 + 0]) * sc0.x, __uint_as_float(r[j * 8 + 1]) * sc0.y);
+                        o.y = pack_bf16(__uint_as_float(r[j * 8 + 2]) * sc0.z, __uint_as_float(r[j * 8 + 3]) * sc0.w);
+                        o.z = pack_bf16(__uint_as_float(r[j * 8 + 4]) * sc1.x, __uint_as_float(r[j * 8 + 5]) * sc1.y);
+                        o.w = pack_bf16(__uint_as_float(r[j * 8 + 6]) * sc1.z, __uint_as_float(r[j * 8 + 7]) * sc1.w);
+                        if (valid) *reinterpret_cast<uint4*>(op + half * 32 + j * 8) = o;
+                    }
+                }
+            }
+            aph ^= 1;
+        }
+    }
+done:
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 }  // namespace ub

@@ -542,8 +542,8 @@ inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const v
     P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
     P.stats = ep.stats;
     P.err = err;
-    int bst = 8;
-    while (bst > 2 && wconv_smem(bst).total + 1024 > 232448u) --bst;
+    int bst = 9;   // multiple of 3: the producer waits once per group of 3 weight tiles
+    while (bst > 3 && wconv_smem(bst).total + 1024 > 232448u) bst -= 3;
     P.bstages = bst;
     L.smem = wconv_smem(bst).total + 1024;
     {
@@ -602,8 +602,8 @@ inline std::string wpconv_build(WpconvLaunch& L, const void* low, int cup, const
     P.scale = scale;
     P.out = reinterpret_cast<__nv_bfloat16*>(out);
     P.err = err;
-    int bst = 16;
-    while (bst > 2 && wpconv_smem(bst).total + 1024 > 232448u) --bst;
+    int bst = 16;  // multiple of 4: the producer waits once per group of 4 weight tiles
+    while (bst > 4 && wpconv_smem(bst).total + 1024 > 232448u) bst -= 4;
     P.bstages = bst;
     L.smem = wpconv_smem(bst).total + 1024;
     {

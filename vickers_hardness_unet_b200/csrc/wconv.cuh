@@ -139,7 +139,11 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         hph ^= 1;
                     }
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (!mbar_wait(bempty(bs), bph ^ 1)) {
+                        // one wait per 3 weight tiles: ring slots free in order, so the LAST slot of the group being free
+                        // implies the first two are (bstages is a multiple of 3: a group never straddles the wrap).  A
+                        // wait + expect_tx + TMA issue per tile made the single producer thread the bottleneck
+                        // (~900 cycles per tile whatever its size).
+                        if (tap % 3 == 0 && !mbar_wait(bempty(bs + 2), bph ^ 1)) {
                             atomicExch(P.err, 42);
                             goto done;
                         }
@@ -434,7 +438,8 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         hph ^= 1;
                     }
                     for (int pt = 0; pt < 16; ++pt) {  // parity (pt >> 2) x low-res neighbour (pt & 3)
-                        if (!mbar_wait(bempty(bs), bph ^ 1)) {
+                        // one wait per 4 weight tiles (see wconv_kernel; bstages is a multiple of 4)
+                        if ((pt & 3) == 0 && !mbar_wait(bempty(bs + 3), bph ^ 1)) {
                             atomicExch(P.err, 52);
                             goto done;
                         }

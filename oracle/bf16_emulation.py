@@ -66,9 +66,11 @@ def _dec_conv1_parity(x_low, skip, w, cup, round_up_part=False):
     return torch.stack(rows, -2).reshape(N, cout, 2 * Hl, 2 * Wl)              # interleave the two row parities
 
 
-# every decoder conv1 uses the parity-folded 2x2 weights on the low-res tensor for its up-sampled channels (tap-table
-# kernel for blocks 0-2, tconv parity mode for blocks 3-4); block 3 additionally stores that part in bf16 (two launches)
+# every decoder conv1 uses the parity-folded 2x2 weights on the low-res tensor for its up-sampled channels; block 3
+# (and, in inference only, blocks 0-2: csrc/unet.cuh tc == 4) stores that part in bf16 and adds it to the skip-channel
+# conv through the residual path (two launches); block 4 has no skip
 SPLIT_DECODER_BLOCKS = (3,)
+SPLIT_DECODER_BLOCKS_EVAL = (0, 1, 2, 3)
 
 
 def emulated_forward(o, x, train: bool):
@@ -101,7 +103,7 @@ def emulated_forward(o, x, train: bool):
     skips = [feats[3], feats[2], feats[1], feats[0], None]
     cups = [512, 256, 128, 64, 32]
     for i, blk in enumerate(o.decoder.blocks):
-        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i], round_up_part=i in SPLIT_DECODER_BLOCKS)
+        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i], round_up_part=i in (SPLIT_DECODER_BLOCKS if train else SPLIT_DECODER_BLOCKS_EVAL))
         u = _r(F.relu(bn(z, blk.conv1[1])))
         t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
     head = o.segmentation_head[0]

@@ -489,12 +489,47 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         // unit 1: output at 2h x 2w; Hin/Win recorded as the OUTPUT resolution (stride-1 bookkeeping)
         r.u1 = new_unit(d.c1, 2 * h, 2 * w);
         r.u2 = new_unit(d.c2, 2 * h, 2 * w);
-        __nv_bfloat16* zup = S.convs[d.c1].tc == 3 ? A.take((long long)N * (2 * h) * (2 * w) * d.cout) : nullptr;
+        // The wide blocks' split (tc == 4: wpconv + wconv) is used by inference only: its extra bf16 rounding of the
+        // up-sampled partial moved the 10-step training loss from 7e-4 to 1.04e-3 relative (north_star asks 1e-3), so
+        // the train forward keeps the four parity launches of the tap-table kernel for decoder.blocks.0-2.conv1.
+        constexpr bool kTrainWideSplit = false;
+        const bool wide_split = kTrainWideSplit && S.convs[d.c1].tc == 4;
+        __nv_bfloat16* zup = (S.convs[d.c1].tc == 3 || wide_split) ? A.take((long long)N * (2 * h) * (2 * w) * d.cout)
+                                                                   : nullptr;
         if (!dry) {
             const Unit u1 = plan.units[r.u1];
             StatSegs segs;
             memset(&segs, 0, sizeof(segs));
-            if (S.convs[d.c1].tc == 3) {
+            if (wide_split) {
+                // wide blocks: wpconv over the up-sampled channels -> zup, then wconv / tconv over the skip channels + zup
+                const ConvRef& cc = S.convs[d.c1];
+                const int kt = 9 * d.cskip + 4 * d.cup;
+                EpilogueDesc e2;
+                e2.stats = plan.stat_part;
+                e2.residual = nhwc_view(zup, N, 2 * h, 2 * w, d.cout);
+                WpconvLaunch WP;
+                err = wpconv_build(WP, cur, d.cup, ctx->wpk + cc.wpk, kt, 9 * d.cskip, d.cout, N, h, w, zup, nullptr,
+                                   ctx->d_err, SM);
+                if (!err.empty()) return cc.name + ": " + err;
+                add_f("conv_fwd:" + cc.name + "[up]", [WP](cudaStream_t st) { return wpconv_launch(WP, st); });
+                int rows = 0;
+                if (wconv_ok(d.cskip, d.cout)) {
+                    WconvLaunch WL;
+                    err = wconv_build(WL, skips[i], d.cskip, ctx->wpk + cc.wpk, d.cout, N, 2 * h, 2 * w, u1.z, e2, ctx->d_err,
+                                      SM, kt);
+                    if (!err.empty()) return cc.name + ": " + err;
+                    add_f("conv_fwd:" + cc.name + "[skip]", [WL](cudaStream_t st) { return wconv_launch(WL, st); });
+                    rows = WL.grid;
+                } else {
+                    TconvLaunch TL;
+                    err = tconv_build(TL, skips[i], d.cskip, false, ctx->wpk + cc.wpk2, d.cout, N, 2 * h, 2 * w, u1.z, e2,
+                                      ctx->d_err, SM);
+                    if (!err.empty()) return cc.name + ": " + err;
+                    add_f("conv_fwd:" + cc.name + "[skip]", [TL](cudaStream_t st) { return tconv_launch(TL, st); });
+                    rows = TL.grid;
+                }
+                segs.n = 1; segs.ptr[0] = e2.stats; segs.rows[0] = rows;
+            } else if (S.convs[d.c1].tc == 3) {
                 // launch 1: conv over the up-sampled channels (parity folding on the low-res tensor) -> zup (bf16);
                 // launch 2: z = conv over the skip channels + zup, batch statistics of z in its epilogue
                 const ConvRef& cc = S.convs[d.c1];
@@ -531,8 +566,9 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                 add_f("conv_fwd:" + S.convs[d.c1].name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
                 segs.n = 1; segs.ptr[0] = ep.stats; segs.rows[0] = HL.grid;
             }
-            segs.n = S.convs[d.c1].hc ? 1 : 4;
-            for (int par = 0; par < (S.convs[d.c1].hc ? 0 : 4); ++par) {
+            const bool one_stat_seg = S.convs[d.c1].hc || wide_split;
+            segs.n = one_stat_seg ? 1 : 4;
+            for (int par = 0; par < (one_stat_seg ? 0 : 4); ++par) {
                 EpilogueDesc ep;
                 ep.stats = plan.stat_part + (size_t)par * SM * 512 * 2;
                 IgemmLaunch L;

@@ -46,6 +46,7 @@ struct ConvRef {
     int tc = 0;           // 1: runs on the TMA halo kernel (tconv.cuh), 2: its parity mode (up-sampled input, no skip),
                           // 3: decoder conv1 split into two tconv launches: parity mode over the up-sampled channels
                           //    (scaled, bf16) then plain mode over the skip channels with that as the residual
+                          // 4: the same split for the wide blocks: wpconv (parity, PK_DEC1 matrix) + wconv or tconv
     long long wpk2 = -1;  // tc == 3: offset of the second (skip-channel) operand
 };
 
@@ -167,10 +168,23 @@ struct NetSpec {
                     n = tconv_w_elems(cup, c.cout, true) + tconv_w_elems(c.cin - cup, c.cout, false);
                 }
             }
-            (void)is_dec1;
+            if (is_dec1 && !c.hc) {
+                int cup = 0;
+                for (auto& d : dec) if (d.c1 == (int)i) cup = d.cup;
+                const int cskip = c.cin - cup;
+                if (cskip > 0 && wpconv_ok(cup, c.cout) && (wconv_ok(cskip, c.cout) || tconv_ok(cskip, c.cout, false))) {
+                    c.tc = 4;
+                    c.hc_cup = cup;
+                    if (!wconv_ok(cskip, c.cout)) {
+                        c.wpk2 = n;  // relative for now: the skip-slice tconv operand follows the PK_DEC1 matrix
+                        n += tconv_w_elems(cskip, c.cout, false);
+                    }
+                }
+            }
             c.wpk = wpk_total;
             c.wpk_elems = n;
             if (c.tc == 3) c.wpk2 = c.wpk + tconv_w_elems(c.hc_cup, c.cout, true);
+            if (c.tc == 4 && c.wpk2 >= 0) c.wpk2 += c.wpk;
             wpk_total += (n + 63) & ~63ll;  // keep every matrix 128 B aligned
         }
     }
@@ -326,6 +340,11 @@ inline std::string ctx_build_pack_tables(Ctx* ctx) {
             if (dd) {
                 e = pk_entry(PK_DEC1, c.w, c.wpk, 4ll * dd->cout * (9 * dd->cskip + 4 * dd->cup));
                 e.cout = dd->cout; e.cin = dd->cup; e.a = dd->cskip;
+                if (c.tc == 4 && c.wpk2 >= 0) {  // + the skip-channel slice as a tconv operand
+                    T.add(e);
+                    e = pk_entry(PK_HCONV, c.w, c.wpk2, tconv_w_elems(dd->cskip, dd->cout, false));
+                    e.cout = dd->cout; e.cin = dd->cskip; e.a = c.cin; e.b = dd->cup; e.c = 0;
+                }
             } else {
                 e = pk_entry(PK_CONV, c.w, c.wpk, (long long)c.cout * c.cin * c.k * c.k);
                 e.cout = c.cout; e.cin = c.cin; e.a = c.k; e.b = c.k; e.c = 0;
@@ -586,9 +605,33 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         const ConvRef& c2 = S.convs[d.c2];
         __nv_bfloat16* t = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         __nv_bfloat16* o = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
-        __nv_bfloat16* r = c1.tc == 3 ? A.take((long long)N * (2 * h) * (2 * w) * d.cout) : nullptr;
+        __nv_bfloat16* r = (c1.tc == 3 || c1.tc == 4) ? A.take((long long)N * (2 * h) * (2 * w) * d.cout) : nullptr;
         if (!dry) {
-            if (c1.tc == 3) {
+            if (c1.tc == 4) {
+                // wide blocks: launch 1 = wpconv (scale * parity-folded conv of the up-sampled channels on the low-res
+                // tensor -> r), launch 2 = wconv / tconv over the skip channels with r as the residual
+                const int kt = 9 * d.cskip + 4 * d.cup;
+                EpilogueDesc e2 = fold(c1.bn, 1);
+                e2.residual = nhwc_view(r, N, 2 * h, 2 * w, d.cout);
+                WpconvLaunch WP;
+                err = wpconv_build(WP, cur, d.cup, ctx->wpk + c1.wpk, kt, 9 * d.cskip, d.cout, N, h, w, r, e2.scale,
+                                   ctx->d_err, ctx->num_sms);
+                if (!err.empty()) return c1.name + ": " + err;
+                plan.steps.push_back({[WP](cudaStream_t st) { return wpconv_launch(WP, st); }, c1.name + "[up]", 1});
+                if (wconv_ok(d.cskip, d.cout)) {
+                    WconvLaunch WL;
+                    err = wconv_build(WL, skips[i], d.cskip, ctx->wpk + c1.wpk, d.cout, N, 2 * h, 2 * w, t, e2, ctx->d_err,
+                                      ctx->num_sms, kt);
+                    if (!err.empty()) return c1.name + ": " + err;
+                    plan.steps.push_back({[WL](cudaStream_t st) { return wconv_launch(WL, st); }, c1.name + "[skip]", 1});
+                } else {
+                    TconvLaunch TL;
+                    err = tconv_build(TL, skips[i], d.cskip, false, ctx->wpk + c1.wpk2, d.cout, N, 2 * h, 2 * w, t, e2,
+                                      ctx->d_err, ctx->num_sms);
+                    if (!err.empty()) return c1.name + ": " + err;
+                    plan.steps.push_back({[TL](cudaStream_t st) { return tconv_launch(TL, st); }, c1.name + "[skip]", 1});
+                }
+            } else if (c1.tc == 3) {
                 // launch 1: scale * conv(up-sampled channels) by parity folding on the low-res tensor -> r (bf16);
                 // launch 2: relu(scale * conv(skip channels) + shift + r).  Nothing up-sampled or concatenated exists.
                 EpilogueDesc e1, e2 = fold(c1.bn, 1);

@@ -805,7 +805,7 @@ static void bench_tconv(const char* name, int N, int H, int W, int cin, int cout
 
 // wconv: wide halo conv with streamed weights vs the CPU conv
 static void case_wconv(const char* name, int N, int H, int W, int cin, int cout, bool residual, bool relu, bool scale_shift,
-                       bool stats) {
+                       bool stats, bool pair = false) {
     HostT src(N, H, W, cin);
     fill_rand_bf16(src.v, 1.0f);
     std::vector<float> w((size_t)cout * cin * 9);
@@ -844,15 +844,24 @@ static void case_wconv(const char* name, int N, int H, int W, int cin, int cout,
         ep.stats = d_stats;
     }
     WconvLaunch L;
-    std::string e = wconv_build(L, d_src, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    Wconv2Launch L2;
+    std::string e = pair ? wconv2_build(L2, d_src, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms)
+                         : wconv_build(L, d_src, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
     if (!e.empty()) {
         printf("[FAIL] %s: %s\n", name, e.c_str());
         g_fail++;
         return;
     }
-    printf("       %s: grid %d smem %u bstages %d tiles %dx%dx%d n_tiles %d\n", name, L.grid, L.smem, L.p.bstages,
-           L.p.tiles_w, L.p.tiles_h, N, L.p.n_tiles);
-    CK(wconv_launch(L, 0));
+    if (pair) {
+        L.grid = L2.grid;
+        printf("       %s: PAIR grid %d smem %u bstages %d kN %d tiles %dx%dx%d n_tiles %d\n", name, L2.grid, L2.smem,
+               L2.p.bstages, L2.kn, L2.p.tiles_w, L2.p.tiles_h, N, L2.p.n_tiles);
+        CK(wconv2_launch(L2, 0));
+    } else {
+        printf("       %s: grid %d smem %u bstages %d tiles %dx%dx%d n_tiles %d\n", name, L.grid, L.smem, L.p.bstages,
+               L.p.tiles_w, L.p.tiles_h, N, L.p.n_tiles);
+        CK(wconv_launch(L, 0));
+    }
     CK(cudaDeviceSynchronize());
     if (!check_err_flag(name)) {
         std::vector<float> got = from_dev_bf16(d_out, ref.v.size());
@@ -876,7 +885,7 @@ static void case_wconv(const char* name, int N, int H, int W, int cin, int cout,
     if (d_stats) cudaFree(d_stats);
 }
 
-static void bench_wconv(const char* name, int N, int H, int W, int cin, int cout, int iters) {
+static void bench_wconv(const char* name, int N, int H, int W, int cin, int cout, int iters, bool pair = false) {
     const size_t in_e = (size_t)N * H * W * cin, out_e = (size_t)N * H * W * cout;
     __nv_bfloat16 *d_in, *d_out, *d_wpk;
     CK(cudaMalloc(&d_in, in_e * 2));
@@ -887,18 +896,23 @@ static void bench_wconv(const char* name, int N, int H, int W, int cin, int cout
     EpilogueDesc ep;
     ep.relu = 1;
     WconvLaunch L;
-    std::string e = wconv_build(L, d_in, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
+    Wconv2Launch L2;
+    std::string e = pair ? wconv2_build(L2, d_in, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms)
+                         : wconv_build(L, d_in, cin, d_wpk, cout, N, H, W, d_out, ep, g_ctx->d_err, g_ctx->num_sms);
     if (!e.empty()) {
         printf("[FAIL] bench %s: %s\n", name, e.c_str());
         return;
     }
+    if (pair) { L.grid = L2.grid; L.p.bstages = L2.p.bstages; }
+    auto go = [&]() { return pair ? wconv2_launch(L2, 0) : wconv_launch(L, 0); };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    for (int i = 0; i < 3; ++i) CK(wconv_launch(L, 0));
+    for (int i = 0; i < 3; ++i) CK(go());
     CK(cudaDeviceSynchronize());
+    if (check_err_flag(name)) return;
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) CK(wconv_launch(L, 0));
+    for (int i = 0; i < iters; ++i) CK(go());
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -1182,6 +1196,20 @@ int main(int argc, char** argv) {
         case_wconv("wide 256->256 +res 3x32x32 (multi-item/CTA)", 3, 32, 32, 256, 256, true, true, true, true);
         case_wconv("wide 256->512 raw 40x16x16 (multi-item/CTA)", 40, 16, 16, 256, 512, false, false, false, true);
         case_wconv("wide 512->128 (dgrad shape) 2x16x16", 2, 16, 16, 512, 128, false, false, false, false);
+    }
+    if (want("pair")) {
+        case_wconv("pair 128->128 1x16x16", 1, 16, 16, 128, 128, false, true, true, true, true);
+        case_wconv("pair 64->128 2x24x40 (partial tiles)", 2, 24, 40, 64, 128, true, true, true, true, true);
+        case_wconv("pair 256->256 +res 3x32x32 (multi-item)", 3, 32, 32, 256, 256, true, true, true, true, true);
+        case_wconv("pair 256->512 raw 40x16x16 (multi-item)", 40, 16, 16, 256, 512, false, false, false, true, true);
+        case_wconv("pair 512->128 (dgrad shape) 2x16x16", 2, 16, 16, 512, 128, false, false, false, false, true);
+    }
+    if (want("pbench")) {
+        bench_wconv("PAIR L2 3x3 128->128 @64^2 x32", 32, 64, 64, 128, 128, 20, true);
+        bench_wconv("PAIR L3 3x3 256->256 @32^2 x32", 32, 32, 32, 256, 256, 20, true);
+        bench_wconv("PAIR L4 3x3 512->512 @16^2 x32", 32, 16, 16, 512, 512, 20, true);
+        bench_wconv("PAIR L3 3x3 256->256 @32^2 x16", 16, 32, 32, 256, 256, 20, true);
+        bench_wconv("PAIR L4 3x3 512->512 @16^2 x16", 16, 16, 16, 512, 512, 20, true);
     }
     if (want("xbench")) {
         bench_wconv("L2 3x3 128->128 @64^2 x32", 32, 64, 64, 128, 128, 20);

@@ -171,14 +171,14 @@ wconv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint64_t a_desc0 = umma_desc(base + L.halo_off, 16, 10 * 128, 2u);
             const uint64_t b_desc0 = umma_desc(base + L.b_off, 16, 8 * 128, 2u);
             for (int item = pair0; item < total_items; item += pair_step) {
-                if (!mbar_wait_cluster(tempty(acc), aph ^ 1)) {
+                if (!mbar_wait(tempty(acc), aph ^ 1)) {
                     atomicExch(P.err, 63);
                     goto done;
                 }
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + acc * kN;
                 for (int c = 0; c < chunks; ++c) {
-                    if (!mbar_wait(hfull(hs), hph) || !mbar_wait_cluster(phfull(hs), hph)) {
+                    if (!mbar_wait(hfull(hs), hph) || !mbar_wait(phfull(hs), hph)) {
                         atomicExch(P.err, 64);
                         goto done;
                     }
@@ -186,7 +186,7 @@ wconv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const uint64_t a_base = a_desc0 + (uint64_t)((hs * kW2HaloStage) >> 4);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        if (!mbar_wait(bfull(bs), bph) || !mbar_wait_cluster(pbfull(bs), bph)) {
+                        if (!mbar_wait(bfull(bs), bph) || !mbar_wait(pbfull(bs), bph)) {
                             atomicExch(P.err, 65);
                             goto done;
                         }

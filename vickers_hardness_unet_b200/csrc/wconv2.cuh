@@ -197,7 +197,11 @@ wconv2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         for (int kk = 0; kk < 4; ++kk)
                             umma2_bf16(d0, ad + (uint32_t)((kk * 32) >> 4), bd + (uint32_t)((kk * 32) >> 4), idesc,
                                        (c > 0 || tap > 0 || kk > 0) ? 1u : 0u);
-                        umma2_commit(bempty(bs));       // frees this weight stage in BOTH CTAs
+                        if (tap % 3 == 2) {             // frees the row's three weight stages in BOTH CTAs (bstages % 3 == 0)
+                            umma2_commit(bempty(bs - 2));
+                            umma2_commit(bempty(bs - 1));
+                            umma2_commit(bempty(bs));
+                        }
                         if (++bs == P.bstages) {
                             bs = 0;
                             bph ^= 1;

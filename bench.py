@@ -106,7 +106,7 @@ def cpu_oracle_rate(size: int, batch: int, budget_s: float, threads: int):
         t0 = time.perf_counter()
         m(x)
         one = time.perf_counter() - t0
-        n = max(2, min(20, int(budget_s / max(one, 1e-3))))
+        n = max(3, min(1000, int(budget_s / max(one, 1e-3))))  # ~budget_s seconds of CPU work
         ts = []
         for _ in range(n):
             t0 = time.perf_counter()
@@ -362,7 +362,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         thr = os.cpu_count() or 1
-        rate, n, med = cpu_oracle_rate(S, 1, 15.0, thr)
+        rate, n, med = cpu_oracle_rate(S, 1, 12.0, thr)
         cpu = {"value": rate, "unit": "images/s", "cores": thr, "kind": "port",
                "sample": f"fp32 oracle forward, batch 1 @ {S}x{S}, median of {n} runs ({med * 1e3:.0f} ms each), "
                          f"{thr} torch threads on {os.cpu_count()} host cores"}

@@ -147,6 +147,14 @@ int unetb200_loss_bce_dice_backward(const float* logits_dev, const float* target
                                     const float* g_bce_dev, const float* g_dice_dev, float gscale, float eps,
                                     float* dlogits_dev, long long n, void* stream);
 
+/* ---- validation metrics (/root/reference/train.py:230-281 dice_coef / iou_coef, called at train.py:518-522) ----------- */
+/* pred_dev: fp32 [N,1,H,W] probabilities (thresh 0.5) or logits (thresh 0: sigmoid(x) > 0.5 <=> x > 0); target_dev: fp32
+ * {0,1} masks of the same shape; hw = H*W.  out2_dev[0] = batch mean of the per-image Dice, out2_dev[1] = of the IoU,
+ * with the reference's eps placement.  scratch_dev: unetb200_seg_metrics_scratch_floats(N) floats.  Deterministic. */
+int unetb200_seg_metrics_scratch_floats(int N);
+int unetb200_seg_metrics(const float* pred_dev, const float* target_dev, int N, long long hw, float thresh, float eps,
+                         float* scratch_dev, float* out2_dev, void* stream);
+
 /* torch.optim.AdamW(...).step() (train.py:606,444,449) fused over the flat arrays: decoupled weight decay on every
  * element, bias-corrected moments (step >= 1).  grad_scale multiplies the gradient first (1/world_size, 1/loss_scale);
  * zero_grad != 0 clears grads_dev afterwards (optimizer.zero_grad, train.py:428). */

@@ -213,3 +213,30 @@ def test_gradient_accumulation_without_zero_grad():
     worst = float((m.flat_grads - 2 * g1).abs().max())
     print(f"\n[accumulation] rel-L2 {rel:.2e} max-abs {worst:.2e} (fp32 reduction order differs between the two backwards)")
     assert rel <= 1e-4
+
+
+def test_device_metrics_equal_reference_formulas():
+    """vb.metrics.dice_iou == dice_coef / iou_coef of /root/reference/train.py:230-281 (threshold 0.5 on the probability,
+    per-image ratios with the reference's eps placement, batch mean), incl. an all-background image and a target-only one."""
+    import vickers_hardness_unet_b200 as vb
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(5, 1, 96, 160, generator=g) * 2
+    target = (torch.rand(5, 1, 96, 160, generator=g) < 0.2).float()
+    logits[1] = -3.0          # nothing predicted ...
+    target[1] = 0.0           # ... and nothing to find: 0/0 -> eps/eps = 1
+    logits[2] = -3.0          # nothing predicted but a target present -> ~0
+    prob = torch.sigmoid(logits)
+
+    def ref(prob, target, eps=1e-7):  # train.py:246-256, 277-281
+        pred = (prob > 0.5).float()
+        inter = (pred * target).sum(dim=(1, 2, 3))
+        u = pred.sum(dim=(1, 2, 3)) + target.sum(dim=(1, 2, 3))
+        return ((2 * inter + eps) / (u + eps)).mean().item(), ((inter + eps) / (u - inter + eps)).mean().item()
+
+    want = ref(prob, target)
+    got = vb.metrics.dice_iou(prob.cuda(), target.cuda()).cpu()
+    got_l = vb.metrics.dice_iou(logits.cuda(), target.cuda(), from_logits=True).cpu()
+    for k in range(2):
+        assert abs(float(got[k]) - want[k]) <= 1e-6 and abs(float(got_l[k]) - want[k]) <= 1e-6, (got, got_l, want)
+    assert abs(vb.metrics.dice_coef(prob.cuda(), target.cuda()) - want[0]) <= 1e-6
+    assert abs(vb.metrics.iou_coef(prob.cuda(), target.cuda()) - want[1]) <= 1e-6

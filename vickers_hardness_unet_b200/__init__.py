@@ -6,6 +6,7 @@ from ._lib import UnetB200Error, LIB_PATH  # noqa: F401
 from .unet import Unet  # noqa: F401
 from . import losses  # noqa: F401
 from . import distributed  # noqa: F401
+from . import metrics  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 
-__all__ = ["Unet", "losses", "distributed", "FusedAdamW", "UnetB200Error"]
+__all__ = ["Unet", "losses", "distributed", "metrics", "FusedAdamW", "UnetB200Error"]

@@ -55,6 +55,8 @@ def _proto(lib):
         "unetb200_loss_scratch_floats": (i32, []),
         "unetb200_loss_bce_dice_forward": (i32, [vp, vp, i64, f32, vp, vp, vp]),
         "unetb200_loss_bce_dice_backward": (i32, [vp, vp, vp, vp, vp, f32, f32, vp, i64, vp]),
+        "unetb200_seg_metrics_scratch_floats": (i32, [i32]),
+        "unetb200_seg_metrics": (i32, [vp, vp, i32, i64, f32, f32, vp, vp, vp]),
         "unetb200_adamw_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, i32, vp]),
     }
     for name, (res, args) in sigs.items():

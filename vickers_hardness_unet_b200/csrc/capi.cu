@@ -402,6 +402,18 @@ int unetb200_loss_bce_dice_backward(const float* logits_dev, const float* target
     return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
 }
 
+int unetb200_seg_metrics_scratch_floats(int N) { return N > 0 ? N * kMetricBlocks * 3 : 0; }
+
+int unetb200_seg_metrics(const float* pred_dev, const float* target_dev, int N, long long hw, float thresh, float eps,
+                         float* scratch_dev, float* out2_dev, void* stream) {
+    if (!pred_dev || !target_dev || !scratch_dev || !out2_dev || N < 1 || hw < 1) return loss_fail("seg_metrics: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    seg_metrics_partial_kernel<<<dim3(kMetricBlocks, N), 256, 0, st>>>(pred_dev, target_dev, hw, thresh, scratch_dev);
+    seg_metrics_finalize_kernel<<<1, 256, 0, st>>>(scratch_dev, N, eps, out2_dev);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
+}
+
 int unetb200_adamw_step(unetb200_ctx* h, float* params_dev, float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
                         long long n, float lr, float beta1, float beta2, float eps, float weight_decay, long long step,
                         float grad_scale, int zero_grad, void* stream) {

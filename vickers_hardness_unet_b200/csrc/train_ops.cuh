@@ -497,6 +497,62 @@ __global__ void loss_bwd_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------ validation metrics
+// dice_coef / iou_coef of /root/reference/train.py:230-281 on the device: pred = [p > thresh] (thresh 0.5 for
+// probabilities, 0 for logits since sigmoid(x) > 0.5 <=> x > 0); per image inter = sum pred*t, sp = sum pred, st = sum t;
+// dice_n = (2*inter + eps) / (sp + st + eps); iou_n = (inter + eps) / (sp + st - inter + eps); mean over the batch.
+constexpr int kMetricBlocks = 64;   // blocks per image (fixed: deterministic partial layout [N][64][3])
+__global__ void __launch_bounds__(256)
+seg_metrics_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, long long hw, float thresh,
+                           float* __restrict__ partial) {
+    const int n = blockIdx.y;
+    const float* pn = p + (long long)n * hw;
+    const float* tn = t + (long long)n * hw;
+    float inter = 0.f, sp = 0.f, st = 0.f;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < hw; i += 256ll * kMetricBlocks) {
+        const float pred = __ldg(pn + i) > thresh ? 1.f : 0.f;
+        const float tv = __ldg(tn + i);
+        inter += pred * tv;
+        sp += pred;
+        st += tv;
+    }
+    __shared__ float red[8][3];
+    inter = warp_sum(inter); sp = warp_sum(sp); st = warp_sum(st);
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5][0] = inter; red[threadIdx.x >> 5][1] = sp; red[threadIdx.x >> 5][2] = st;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float a = 0.f;
+        for (int w = 0; w < 8; ++w) a += red[w][threadIdx.x];
+        partial[((long long)n * kMetricBlocks + blockIdx.x) * 3 + threadIdx.x] = a;
+    }
+}
+// one block: thread n < N finishes image n (fp64), then the batch mean -> out[0] = dice, out[1] = iou
+__global__ void __launch_bounds__(256)
+seg_metrics_finalize_kernel(const float* __restrict__ partial, int N, float eps, float* __restrict__ out) {
+    double dsum = 0, isum = 0;
+    for (int n = threadIdx.x; n < N; n += 256) {
+        double inter = 0, sp = 0, st = 0;
+        for (int b = 0; b < kMetricBlocks; ++b) {
+            const float* q = partial + ((long long)n * kMetricBlocks + b) * 3;
+            inter += q[0]; sp += q[1]; st += q[2];
+        }
+        dsum += (2 * inter + eps) / (sp + st + eps);
+        isum += (inter + eps) / (sp + st - inter + eps);
+    }
+    __shared__ double rd[8], ri[8];
+    dsum = warp_sum_d(dsum); isum = warp_sum_d(isum);
+    if ((threadIdx.x & 31) == 0) { rd[threadIdx.x >> 5] = dsum; ri[threadIdx.x >> 5] = isum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) { a += rd[w]; b += ri[w]; }
+        out[0] = (float)(a / N);
+        out[1] = (float)(b / N);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ fused AdamW
 // torch.optim.AdamW semantics (/root/reference/train.py:606): decoupled decay on every tensor, bias-corrected moments.
 // Optionally scales the gradient (1/world_size, 1/loss_scale) and zeroes it afterwards.

@@ -387,6 +387,13 @@ def main():
             if a.profile_out:
                 with open(a.profile_out, "w") as f:
                     f.write(prof["table"])
+        # DRAM traffic of the conv stack per step from the committed ncu capture (same workload only)
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "infer_dram_traffic_b32_512.json")
+        if B == 32 and S == 512 and os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            roof["traffic"] = tj["conv_stack_dram_bytes_per_step"]
+            roof["traffic_note"] = "bytes per step (sum over the conv launches), ncu dram__bytes_read+write: " + tj["source"]
         out = {
             "metric": "images_per_sec_infer_512", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,

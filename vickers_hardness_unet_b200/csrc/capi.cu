@@ -254,7 +254,7 @@ int unetb200_conv_nhwc(unetb200_ctx* h, const void* in, const float* w, const fl
     const size_t wn = (size_t)cout * cin * k * k;
     __nv_bfloat16* wpk = nullptr;
     UB_CUDA(cudaMallocAsync(&wpk, wn * 2, st));
-    pack_conv_w_kernel<<<ew_grid(wn, 256, ctx->num_sms), 256, 0, st>>>(w, wpk, cout, cin, k, k, 0);
+    launch_k(pack_conv_w_kernel, ew_grid(wn, 256, ctx->num_sms), 256, 0, st, w, wpk, cout, cin, k, k, 0);
     EpilogueDesc ep;
     ep.scale = scale; ep.shift = shift; ep.relu = relu;
     const int Ho = H / stride, Wo = W / stride;
@@ -269,7 +269,7 @@ int unetb200_conv_nhwc(unetb200_ctx* h, const void* in, const float* w, const fl
     if (!e.empty()) return ctx_fail(ctx, "conv_nhwc: " + e);
     UB_CUDA(igemm_launch(L, st));
     if (stats) {
-        reduce_partials_kernel<<<(cout * 2 + 127) / 128, 128, 0, st>>>(part, stats, L.grid, cout * 2);
+        launch_k(reduce_partials_kernel, (cout * 2 + 127) / 128, 128, 0, st, part, stats, L.grid, cout * 2);
         UB_CUDA(cudaGetLastError());
         UB_CUDA(cudaFreeAsync(part, st));
     }
@@ -384,8 +384,8 @@ int unetb200_loss_bce_dice_forward(const float* logits_dev, const float* target_
     cudaStream_t st = (cudaStream_t)stream;
     long long nb = (n + 1023) / 1024;
     if (nb > 1024) nb = 1024;
-    loss_partial_kernel<<<(int)nb, 256, 0, st>>>(logits_dev, target_dev, scratch_dev, n);
-    loss_finalize_kernel<<<1, 32, 0, st>>>(scratch_dev, (int)nb, (double)n, eps, result_dev);
+    launch_k(loss_partial_kernel, (int)nb, 256, 0, st, logits_dev, target_dev, scratch_dev, n);
+    launch_k(loss_finalize_kernel, 1, 32, 0, st, scratch_dev, (int)nb, (double)n, eps, result_dev);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
 }
@@ -396,7 +396,7 @@ int unetb200_loss_bce_dice_backward(const float* logits_dev, const float* target
     if (!logits_dev || !target_dev || !result_dev || !dlogits_dev || n < 1) return loss_fail("loss_backward: bad argument");
     long long nb = (n + 1023) / 1024;
     if (nb > 148 * 16) nb = 148 * 16;
-    loss_bwd_kernel<<<(int)nb, 256, 0, (cudaStream_t)stream>>>(logits_dev, target_dev, result_dev, g_bce_dev, g_dice_dev,
+    launch_k(loss_bwd_kernel, (int)nb, 256, 0, (cudaStream_t)stream, logits_dev, target_dev, result_dev, g_bce_dev, g_dice_dev,
                                                                gscale, eps, dlogits_dev, n);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
@@ -408,8 +408,8 @@ int unetb200_seg_metrics(const float* pred_dev, const float* target_dev, int N, 
                          float* scratch_dev, float* out2_dev, void* stream) {
     if (!pred_dev || !target_dev || !scratch_dev || !out2_dev || N < 1 || hw < 1) return loss_fail("seg_metrics: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    seg_metrics_partial_kernel<<<dim3(kMetricBlocks, N), 256, 0, st>>>(pred_dev, target_dev, hw, thresh, scratch_dev);
-    seg_metrics_finalize_kernel<<<1, 256, 0, st>>>(scratch_dev, N, eps, out2_dev);
+    launch_k(seg_metrics_partial_kernel, dim3(kMetricBlocks, N), 256, 0, st, pred_dev, target_dev, hw, thresh, scratch_dev);
+    launch_k(seg_metrics_finalize_kernel, 1, 256, 0, st, scratch_dev, N, eps, out2_dev);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : loss_fail(cudaGetErrorString(e));
 }
@@ -423,7 +423,7 @@ int unetb200_adamw_step(unetb200_ctx* h, float* params_dev, float* grads_dev, fl
     UB_CUDA(cudaSetDevice(ctx->device));
     const float bc1 = 1.f - (float)pow((double)beta1, (double)step);
     const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-    adamw_kernel<<<ew_grid(n / 4 + 4, 256, ctx->num_sms), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(adamw_kernel, ew_grid(n / 4 + 4, 256, ctx->num_sms), 256, 0, (cudaStream_t)stream, 
         params_dev, grads_dev, exp_avg_dev, exp_avg_sq_dev, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, grad_scale,
         zero_grad);
     UB_CUDA(cudaGetLastError());

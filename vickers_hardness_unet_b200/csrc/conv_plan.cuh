@@ -208,7 +208,7 @@ inline cudaError_t igemm_launch(const IgemmLaunch& L, cudaStream_t st) {
     cudaError_t e = igemm_set_attr();
     if (e != cudaSuccess) return e;
     if (L.p.csize == 1) {
-        igemm_kernel<<<L.grid, kIgemmThreads, L.smem, st>>>(L.a0, L.a1, L.b, L.d, L.p);
+        launch_k(igemm_kernel, L.grid, kIgemmThreads, L.smem, st, L.a0, L.a1, L.b, L.d, L.p);
         return cudaGetLastError();
     }
     cudaLaunchConfig_t cfg;
@@ -298,8 +298,8 @@ inline cudaError_t hconv_launch(const HconvLaunch& L, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    if (L.occ == 2) hconv_kernel<2><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
-    else hconv_kernel<1><<<L.grid, kHcThreads, L.smem, st>>>(L.p);
+    if (L.occ == 2) launch_k(hconv_kernel<2>, L.grid, kHcThreads, L.smem, st, L.p);
+    else launch_k(hconv_kernel<1>, L.grid, kHcThreads, L.smem, st, L.p);
     return cudaGetLastError();
 }
 
@@ -480,7 +480,7 @@ inline cudaError_t tconv_launch_t(const TconvLaunch& L, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    tconv_kernel<kOcc, kIph, kStage><<<L.grid, tc_threads(kOcc), L.smem, st>>>(L.a, L.d, L.p);
+    launch_k(tconv_kernel<kOcc, kIph, kStage>, L.grid, tc_threads(kOcc), L.smem, st, L.a, L.d, L.p);
     return cudaGetLastError();
 }
 // seg head: plain 16 -> 16 launch (PK_HEAD weights) whose epilogue writes logits / prob / mask; outputs are set per call
@@ -495,7 +495,7 @@ inline cudaError_t tconv_launch_head(const TconvLaunch& L, float* logits, float*
     }
     TconvParams p = L.p;
     p.logits = logits; p.prob = prob; p.mask = mask; p.thresh_logit = thresh_logit;
-    tconv_kernel<2, 2, false, true><<<L.grid, tc_threads(2), L.smem, st>>>(L.a, L.d, p);
+    launch_k(tconv_kernel<2, 2, false, true>, L.grid, tc_threads(2), L.smem, st, L.a, L.d, p);
     return cudaGetLastError();
 }
 
@@ -575,7 +575,7 @@ inline cudaError_t wconv_launch(const WconvLaunch& L, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    wconv_kernel<<<L.grid, kWcThreads, L.smem, st>>>(L.a, L.b, L.p);
+    launch_k(wconv_kernel, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
     return cudaGetLastError();
 }
 
@@ -718,7 +718,7 @@ inline cudaError_t wpconv_launch(const WpconvLaunch& L, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    wpconv_kernel<<<L.grid, kWcThreads, L.smem, st>>>(L.a, L.b, L.p);
+    launch_k(wpconv_kernel, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
     return cudaGetLastError();
 }
 
@@ -775,7 +775,7 @@ inline cudaError_t hwgrad_launch(const HwgradLaunch& L, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    hwgrad_kernel<<<L.grid, kHcThreads, L.smem, st>>>(L.p);
+    launch_k(hwgrad_kernel, L.grid, kHcThreads, L.smem, st, L.p);
     return cudaGetLastError();
 }
 

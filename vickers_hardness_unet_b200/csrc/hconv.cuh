@@ -157,6 +157,7 @@ template <int kOcc>
 __global__ void __launch_bounds__(kHcThreads, kOcc)
 hconv_kernel(const __grid_constant__ HconvParams P) {
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -189,6 +190,7 @@ hconv_kernel(const __grid_constant__ HconvParams P) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);
         float* cst = reinterpret_cast<float*>(sm + L.cstat_off);

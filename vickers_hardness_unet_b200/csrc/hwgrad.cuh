@@ -48,6 +48,7 @@ __host__ __device__ inline HwgradSmem hwgrad_smem(int cw, int cout, int stages) 
 __global__ void __launch_bounds__(kHcThreads, 1)
 hwgrad_kernel(const __grid_constant__ HwgradParams P) {
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -87,6 +88,7 @@ hwgrad_kernel(const __grid_constant__ HwgradParams P) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -75,6 +75,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ IgemmParams P) {
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -121,6 +122,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     // per-channel scale/shift -> smem (identity when absent)
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);

@@ -10,6 +10,8 @@ namespace ub {
 // The stem reads 8-pixel x 4-channel windows (64 B) starting at padded pixel 2*ow, so every window start is
 // 16 B aligned and no window leaves the row (SURVEY.md section 7 "7x7 stem with Cin=3").
 __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int N, int H, int W) {
+    griddep_launch();
+    griddep_wait();
     const int Wp = W + 8;
     const long long total = (long long)N * H * (Wp / 2);  // two pixels (16 B) per thread
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -45,6 +47,8 @@ struct NormParams {
 };
 __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ xp, int N, int H, int W,
                                      int bgr, NormParams np) {
+    griddep_launch();
+    griddep_wait();
     const int Wp = W + 8;
     const long long total = (long long)N * H * (Wp / 2);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -77,6 +81,8 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloa
 // roles of co/ci (the dgrad operand: [ci][( (R-1-r)*S + (S-1-s) )*cout + co]).
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
                                    int R, int S, int flip) {
+    griddep_launch();
+    griddep_wait();
     const long long total = (long long)cout * cin * R * S;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -105,6 +111,8 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // K runs over the conv's output channels and the taps are mirrored:  value = w[c][ci0 + co][2-r][2-s].
 __global__ void pack_hconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int ctot,
                                     int dim1_total, int ci0, int transposed) {
+    griddep_launch();
+    griddep_wait();
     const long long total = 9ll * ctot * cout;
     const int cpr = ctot < 64 ? ctot : 64;          // channels per row
     const int nblk = ctot > 64 ? ctot / 64 : 1;
@@ -131,6 +139,8 @@ __global__ void pack_hconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* 
 
 // Stem: [64][3][7][7] -> [64][r*32 + px*4 + ch], px 0..7 <-> kernel column s = px-1 (px 0 and ch 3 are zero).
 __global__ void pack_stem_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+    griddep_launch();
+    griddep_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 64 * 224) return;
     const int ch = i % 4, px = (i / 4) % 8, r = (i / 32) % 7, co = i / 224;
@@ -146,6 +156,8 @@ __global__ void pack_stem_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 //   row sets: ph=0: a=0<-{r=0}, a=1<-{1,2};  ph=1: a=0<-{0,1}, a=1<-{2}   (same for columns).
 __global__ void pack_dec1_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cup,
                                    int cskip) {
+    griddep_launch();
+    griddep_wait();
     const int kt = 9 * cskip + 4 * cup;
     const long long total = 4ll * cout * kt;
     const int cin = cup + cskip;
@@ -178,6 +190,8 @@ __global__ void pack_dec1_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                float* __restrict__ scale, float* __restrict__ shift, int C) {
+    griddep_launch();
+    griddep_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float s = gamma[c] * rsqrtf(var[c] + eps);
@@ -192,6 +206,8 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 }
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
                                     int H, int W, int C) {
+    griddep_launch();
+    griddep_wait();
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
     const long long total = (long long)N * Ho * Wo * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -231,6 +247,8 @@ __global__ void __launch_bounds__(256)
 head_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w /*[16][3][3]*/,
                  const float* __restrict__ bias, float* __restrict__ logits, float* __restrict__ prob,
                  uint8_t* __restrict__ mask, float thresh_logit, int N, int H, int W) {
+    griddep_launch();
+    griddep_wait();
     __shared__ uint4 tile[(kHeadTile + 2) * (kHeadTile + 2) * 2];  // [18][18][16 ch bf16 = 2 x uint4]
     __shared__ float sw[9 * 16];
     const int tx = threadIdx.x % kHeadTile, ty = threadIdx.x / kHeadTile;
@@ -273,6 +291,8 @@ head_conv_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
 
 // out[j] = sum_t part[t][j]  (deterministic second stage of the per-tile statistics reduction)
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int ntiles, int width) {
+    griddep_launch();
+    griddep_wait();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= width) return;
     float s = 0.f;
@@ -284,6 +304,20 @@ inline int ew_grid(long long total, int block, int num_sms) {
     long long g = (total + block - 1) / block;
     const long long cap = (long long)num_sms * 16;
     return int(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// grid for kernels that process two elements per loop iteration and whose threads keep a fixed channel group:
+// half the blocks of ew_grid for small tensors, and blockDim * grid stays a multiple of the channel-group count c8.
+inline int ew_grid2(long long total, int block, int num_sms, int c8) {
+    long long g = (total + 2LL * block - 1) / (2LL * block);
+    const long long cap = (long long)num_sms * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    if (c8 > block) {   // blockDim * g must be a multiple of c8
+        const long long m = c8 / block;
+        g = (g + m - 1) / m * m;
+    }
+    return int(g);
 }
 
 }  // namespace ub

@@ -135,6 +135,8 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
 __global__ void __launch_bounds__(256)
 pack_table_kernel(const PackEntry* __restrict__ tab, int n, const float* __restrict__ params,
                   __nv_bfloat16* __restrict__ dst_base) {
+    griddep_launch();
+    griddep_wait();
     int lo = 0, hi = n - 1;  // last entry whose block_begin <= blockIdx.x
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -173,7 +175,7 @@ struct PackTable {
     }
     cudaError_t launch(const float* params, __nv_bfloat16* dst_base, cudaStream_t st) const {
         if (!nblocks) return cudaSuccess;
-        pack_table_kernel<<<nblocks, 256, 0, st>>>(dev, (int)host.size(), params, dst_base);
+        launch_k(pack_table_kernel, nblocks, 256, 0, st, dev, (int)host.size(), params, dst_base);
         return cudaGetLastError();
     }
     ~PackTable() { cudaFree(dev); }

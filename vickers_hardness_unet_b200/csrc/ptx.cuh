@@ -74,6 +74,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ----------------------------------------------------------------------------------------------- TMA
+// Programmatic dependent launch (PDL).  Every kernel of the library calls griddep_launch() first (the next kernel of
+// the stream may start its prologue: barrier init, TMEM allocation, descriptor prefetch, as soon as SM resources free
+// up) and griddep_wait() before its first access to global memory (returns when the preceding kernel has COMPLETED and
+// its writes are visible).  Both are no-ops in a kernel launched without the stream-serialization attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -308,5 +315,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// Host side of PDL: every launch of the library goes through launch_k, which sets the programmatic stream
+// serialization attribute (UNETB200_PDL=0 in the environment turns it off for A/B measurements).
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("UNETB200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace ub

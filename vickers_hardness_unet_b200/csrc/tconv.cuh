@@ -160,6 +160,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ TconvParams P) {
     constexpr int kEw = tc_epi_warps(kOcc), kTcThreads = tc_threads(kOcc);
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -194,6 +195,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);
         float* cst = reinterpret_cast<float*>(sm + L.cstat_off);

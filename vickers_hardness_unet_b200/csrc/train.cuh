@@ -26,7 +26,7 @@ inline cudaError_t wg_launch(const WgLaunch& L, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    wgrad_kernel<<<L.grid, kWgThreads, L.smem, st>>>(L.z, L.x, L.p, L.max_ncin);
+    launch_k(wgrad_kernel, L.grid, kWgThreads, L.smem, st, L.z, L.x, L.p, L.max_ncin);
     return cudaGetLastError();
 }
 
@@ -370,12 +370,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const float* bt = params + b.beta;
         const int C = c.cout;
         add_f("bn_finalize:" + c.name, [=](cudaStream_t st) {
-            bn_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(segs, C, count, gm, bt, rm, rv, cnt, 0.1f, 1e-5f,
+            launch_k(bn_finalize_kernel, (C + 7) / 8, 256, 0, st, segs, C, count, gm, bt, rm, rv, cnt, 0.1f, 1e-5f,
                                                                u.scale, u.shift, u.mean, u.invstd);
             return cudaGetLastError();
         });
         add_f("bn_apply:" + c.name, [=](cudaStream_t st) {
-            bn_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(u.z, u.scale, u.shift, residual, relu, u.a,
+            launch_k(bn_apply_kernel, ew_grid2(npix * (C / 8), 256, SM, C / 8), 256, 0, st, u.z, u.scale, u.shift, residual, relu, u.a,
                                                                              npix, C);
             return cudaGetLastError();
         });
@@ -446,7 +446,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     if (!dry) {
         const int Hh = H / 2, Wh = W / 2;
         add_f("maxpool:encoder.maxpool", [=](cudaStream_t st) {
-            maxpool3x3s2_idx_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, SM), 256, 0, st>>>(
+            launch_k(maxpool3x3s2_idx_kernel, ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, SM), 256, 0, st, 
                 f1, p1, pool_idx, N, Hh, Wh, 64);
             return cudaGetLastError();
         });
@@ -643,8 +643,9 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const long long npix = (long long)N * u.Ho * u.Wo;
         const int C = c.cout;
         const int ppb = 256 / (C / 8);
-        long long nb = (npix + ppb - 1) / ppb;
+        long long nb = (npix + ppb - 1) / ppb / 8;   // >= 8 block iterations (2 pixels each 4): few partial rows
         if (nb > 6 * SM) nb = 6 * SM;
+        if (nb < 1) nb = 1;
         const int nblocks = (int)nb;
         float* part = plan.red_part;
         // ReLU mask: units with a residual input (g_out != nullptr) read the stored activation; the others recompute
@@ -656,17 +657,17 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         float* dgm = grads + b.gamma;
         float* dbt = grads + b.beta;
         add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
-            bn_bwd_reduce_kernel<<<nblocks, 256, 0, st>>>(dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
+            launch_k(bn_bwd_reduce_kernel, nblocks, 256, 0, st, dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
             return cudaGetLastError();
         });
         add_b(stage, "bn_bwd_finalize:" + c.name, [=](cudaStream_t st) {
-            bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, nblocks, C, (double)npix, gm, u.invstd, dgm,
-                                                                   dbt, u.coef);
+            launch_k(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, st, part, nblocks, C, (double)npix, gm, u.mean, u.invstd,
+                                                                   dgm, dbt, u.coef);
             return cudaGetLastError();
         });
         add_b(stage, "bn_bwd_apply:" + c.name, [=](cudaStream_t st) {
-            bn_bwd_apply_kernel<<<ew_grid(npix * (C / 8), 256, SM), 256, 0, st>>>(dA_in, mask, msc, msh, u.z, u.mean,
-                                                                                 u.invstd, u.coef, u.dz, g_out, npix, C);
+            launch_k(bn_bwd_apply_kernel, ew_grid2(npix * (C / 8), 256, SM, C / 8), 256, 0, st, dA_in, mask, msc, msh, u.z,
+                                                                                         u.coef, u.dz, g_out, npix, C);
             return cudaGetLastError();
         });
     };
@@ -940,7 +941,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const __nv_bfloat16* dsk = d_skips[3];
         __nv_bfloat16* dF1 = dA[u_stem];
         add_b(3, "maxpool_bwd:encoder.maxpool", [=](cudaStream_t st) {
-            maxpool_bwd_kernel<<<ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st>>>(d_p1, pool_idx, dsk, dF1, N, Hh,
+            launch_k(maxpool_bwd_kernel, ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st, d_p1, pool_idx, dsk, dF1, N, Hh,
                                                                                             Wh, 64);
             return cudaGetLastError();
         });
@@ -990,7 +991,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         }
         const float* gpk = T.gpk;
         add_b(stage, "unpack_grads:stage" + std::to_string(stage), [=](cudaStream_t st) {
-            unpack_grads_kernel<<<nblocks, 256, 0, st>>>(UT, gpk, grads);
+            launch_k(unpack_grads_kernel, nblocks, 256, 0, st, UT, gpk, grads);
             return cudaGetLastError();
         });
     }
@@ -1076,7 +1077,7 @@ inline int ctx_train_forward(Ctx* ctx, const float* x, float* logits, const floa
     if (ctx_train_prepare(ctx, N, params, buffers, counters, grads, &P)) return 1;
     const int H = ctx->H, W = ctx->W;
     ctx->prof_mark("pack_input:x", st);
-    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P->xp, N, H, W);
+    launch_k(pack_input_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x, P->xp, N, H, W);
     UB_CUDA(cudaGetLastError());
     for (size_t i = 0; i < P->fwd.size(); ++i) {
         ctx->prof_mark(P->fwd_names[i], st);
@@ -1111,10 +1112,10 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             ctx->prof_mark("head_bwd:segmentation_head", st);
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
-            head_bwd_data_kernel<<<ew_grid(npx, 256, SM), 256, 0, st>>>(dlogits, ctx->head_w, P.d_head_in, N, H, W);
+            launch_k(head_bwd_data_kernel, ew_grid(npx, 256, SM), 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W);
             const int nb = 8 * SM;
-            head_bwd_weight_kernel<<<nb, 288, 0, st>>>(P.head_in, dlogits, P.red_part, N, H, W);
-            sum_rows_kernel<<<(145 + 7) / 8, 256, 0, st>>>(P.red_part, nb, 145, P.grads + hc.w);
+            launch_k(head_bwd_weight_kernel, nb, 288, 0, st, P.head_in, dlogits, P.red_part, N, H, W);
+            launch_k(sum_rows_kernel, (145 + 7) / 8, 256, 0, st, P.red_part, nb, 145, P.grads + hc.w);
             UB_CUDA(cudaGetLastError());
         }
         for (size_t i = 0; i < P.bwd[stage].size(); ++i) {

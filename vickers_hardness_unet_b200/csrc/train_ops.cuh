@@ -42,6 +42,8 @@ bn_finalize_kernel(StatSegs segs, int C, double count, const float* __restrict__
                    float* __restrict__ running_var, long long* __restrict__ counter, float momentum,
                    float eps, float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+    griddep_launch();
+    griddep_wait();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (blockIdx.x == 0 && threadIdx.x == 0 && counter) *counter += 1;
@@ -78,21 +80,25 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
                 __nv_bfloat16* __restrict__ out, long long npix, int C) {
+    griddep_launch();
+    griddep_wait();
     const int C8 = C / 8;
     const long long total = npix * C8;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int c0 = int(i0 % C8) * 8;
     float sc[8], sh[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        sc[k] = __ldg(scale + c0 + k);
-        sh[k] = __ldg(shift + c0 + k);
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(scale + c0)), b = __ldg(reinterpret_cast<const float4*>(scale + c0) + 1);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(shift + c0)), d = __ldg(reinterpret_cast<const float4*>(shift + c0) + 1);
+        sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+        sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
     }
-    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), v);
-        float r[8];
-        if (residual) unpack8(__ldg(reinterpret_cast<const uint4*>(residual) + i), r);
+    const uint4* z4 = reinterpret_cast<const uint4*>(z);
+    const uint4* r4 = reinterpret_cast<const uint4*>(residual);
+    auto one = [&](const uint4& zv, const uint4& rv) {
+        float v[8], r[8];
+        unpack8(zv, v);
+        if (residual) unpack8(rv, r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float y = v[k] * sc[k] + sh[k];
@@ -100,7 +106,26 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ s
             if (relu) y = fmaxf(y, 0.f);
             v[k] = y;
         }
-        reinterpret_cast<uint4*>(out)[i] = pack8(v);
+        return pack8(v);
+    };
+    const long long step = (long long)gridDim.x * blockDim.x;
+    long long i = i0;
+    for (; i + step < total; i += 2 * step) {   // two independent elements in flight per thread
+        const long long j = i + step;
+        const uint4 za = __ldg(z4 + i), zb = __ldg(z4 + j);
+        uint4 ra = za, rb = zb;
+        if (residual) {
+            ra = __ldg(r4 + i);
+            rb = __ldg(r4 + j);
+        }
+        reinterpret_cast<uint4*>(out)[i] = one(za, ra);
+        reinterpret_cast<uint4*>(out)[j] = one(zb, rb);
+    }
+    if (i < total) {
+        const uint4 za = __ldg(z4 + i);
+        uint4 ra = za;
+        if (residual) ra = __ldg(r4 + i);
+        reinterpret_cast<uint4*>(out)[i] = one(za, ra);
     }
 }
 
@@ -108,13 +133,29 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ s
 // g = dA * [a > 0] ; partial sums per block of (sum g, sum g*zhat), zhat = (z - mean) * invstd.
 // The ReLU mask comes from the stored activation `a_mask` (units with a residual input) or, when a_mask == nullptr and
 // scale != nullptr, is recomputed from z (a = relu(z*scale + shift) > 0  <=>  z*scale + shift > 0): one tensor less to read.
-// blockDim = 256; thread t owns channel group t % C8 for the pixels t / C8 + k * (256 / C8).
+// blockDim = 256; thread t owns channel group t % C8 for the pixels t / C8 + k * (256 / C8).  Two pixels per loop
+// iteration keep 4-6 independent 16-byte loads in flight per thread; the host sizes the grid so that a block runs
+// >= 8 iterations (few partial rows for the small, wide tensors of layer3/4: the row traffic was as large as the tensor).
+__device__ __forceinline__ void bn_bwd_mask8(float (&g)[8], const float (&zz)[8], const uint4* a_mask, long long idx,
+                                             const float (&sc)[8], const float (&sh)[8]) {
+    if (a_mask) {
+        float m[8];
+        unpack8(__ldg(a_mask + idx), m);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
+    }
+}
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                      const float* __restrict__ invstd, float* __restrict__ partial, long long npix, int C) {
-    __shared__ float red[256 * 16];
+    griddep_launch();
+    griddep_wait();
+    __shared__ float red[256 * 17];
     const int C8 = C / 8;
     const int cg = threadIdx.x % C8;
     const int lane_p = threadIdx.x / C8;
@@ -128,21 +169,37 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
         sc[k] = scale ? scale[cg * 8 + k] : 0.f;
         sh[k] = scale ? shift[cg * 8 + k] : 1.f;   // no mask: 0*z + 1 > 0 always
     }
+    const uint4* dA4 = reinterpret_cast<const uint4*>(dA);
+    const uint4* z4 = reinterpret_cast<const uint4*>(z);
+    const uint4* m4 = reinterpret_cast<const uint4*>(a_mask);
     if (lane_p < ppb) {
-        for (long long p = (long long)blockIdx.x * ppb + lane_p; p < npix; p += (long long)gridDim.x * ppb) {
+        const long long step = (long long)gridDim.x * ppb;
+        long long p = (long long)blockIdx.x * ppb + lane_p;
+        for (; p + step < npix; p += 2 * step) {
+            const long long i0 = p * C8 + cg, i1 = (p + step) * C8 + cg;
+            const uint4 ga = __ldg(dA4 + i0), gb = __ldg(dA4 + i1);
+            const uint4 za = __ldg(z4 + i0), zb = __ldg(z4 + i1);
+            float g[8], zz[8], h[8], zy[8];
+            unpack8(ga, g);
+            unpack8(za, zz);
+            unpack8(gb, h);
+            unpack8(zb, zy);
+            bn_bwd_mask8(g, zz, m4, i0, sc, sh);
+            bn_bwd_mask8(h, zy, m4, i1, sc, sh);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                s1[k] += g[k];
+                s2[k] += g[k] * (zz[k] - mu[k]) * is[k];
+                s1[k] += h[k];
+                s2[k] += h[k] * (zy[k] - mu[k]) * is[k];
+            }
+        }
+        if (p < npix) {
             const long long idx = p * C8 + cg;
             float g[8], zz[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(dA) + idx), g);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(z) + idx), zz);
-            if (a_mask) {
-                float m[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(a_mask) + idx), m);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) g[k] = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
-            }
+            unpack8(__ldg(dA4 + idx), g);
+            unpack8(__ldg(z4 + idx), zz);
+            bn_bwd_mask8(g, zz, m4, idx, sc, sh);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 s1[k] += g[k];
@@ -151,9 +208,9 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
         }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        red[threadIdx.x * 16 + k] = s1[k];
-        red[threadIdx.x * 16 + 8 + k] = s2[k];
+    for (int k = 0; k < 8; ++k) {   // row pitch 17 words: conflict-free column walks below
+        red[threadIdx.x * 17 + k] = s1[k];
+        red[threadIdx.x * 17 + 8 + k] = s2[k];
     }
     __syncthreads();
     // thread t < C*2 sums its (channel, which) over the ppb pixel lanes
@@ -161,17 +218,23 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
         const int c = j >> 1, which = j & 1;
         const int g8 = c / 8, k = c % 8;
         float acc = 0.f;
-        for (int l = 0; l < ppb; ++l) acc += red[(l * C8 + g8) * 16 + which * 8 + k];
+        for (int l = 0; l < ppb; ++l) acc += red[(l * C8 + g8) * 17 + which * 8 + k];
         partial[((size_t)blockIdx.x * C + c) * 2 + which] = acc;
     }
 }
 
-// sums the per-block partials; writes dgamma / dbeta and the apply coefficients k1 = gamma*invstd, k2 = s1/n, k3 = s2/n
+// sums the per-block partials; writes dgamma / dbeta and the affine apply coefficients
+//   dz = k1 * (g - s1/n - zhat * s2/n),  zhat = (z - mean) * invstd,  k1 = gamma * invstd
+//      = cA * g + cB * z + cC   with  cA = k1,  cB = -k1 * invstd * s2/n,  cC = -k1 * s1/n - cB * mean
+// stored as coef[0..C) = cA, coef[C..2C) = cB, coef[2C..3C) = cC (16-byte loads in the apply pass).
 // one WARP per channel (blockDim = 256 -> 8 channels per block)
 __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, double count,
-                       const float* __restrict__ gamma, const float* __restrict__ invstd,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       float* __restrict__ coef) {
+    griddep_launch();
+    griddep_wait();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -186,53 +249,77 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int C, do
     if (lane) return;
     dbeta[c] = (float)s1;
     dgamma[c] = (float)s2;
-    coef[c * 3 + 0] = gamma[c] * invstd[c];
-    coef[c * 3 + 1] = (float)(s1 / count);
-    coef[c * 3 + 2] = (float)(s2 / count);
+    const double k1 = (double)gamma[c] * (double)invstd[c];
+    const double cB = -k1 * (double)invstd[c] * (s2 / count);
+    coef[c] = (float)k1;
+    coef[C + c] = (float)cB;
+    coef[2 * C + c] = (float)(-k1 * (s1 / count) - cB * (double)mean[c]);
 }
 
-// dz = k1 * (g - k2 - zhat*k3);  optionally also writes g (the masked gradient, for the residual identity path).
-// Mask as in bn_bwd_reduce_kernel; per-thread channel constants are loop invariant (see bn_apply_kernel).
+// dz = cA * g + cB * z + cC;  optionally also writes g (the masked gradient, for the residual identity path).
+// Mask as in bn_bwd_reduce_kernel; per-thread channel constants are loop invariant (see bn_apply_kernel) and arrive as
+// 16-byte loads (56 scalar loads per thread were the larger part of this kernel on the <= 16 MB tensors).
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
                     const float* __restrict__ scale, const float* __restrict__ shift,
-                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
-                    const float* __restrict__ invstd, const float* __restrict__ coef,
+                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ coef,
                     __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ g_out, long long npix, int C) {
+    griddep_launch();
+    griddep_wait();
     const int C8 = C / 8;
     const long long total = npix * C8;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int c0 = int(i0 % C8) * 8;
-    float mu[8], is[8], k1[8], k2[8], k3[8], sc[8], sh[8];
+    float cA[8], cB[8], cC[8], sc[8], sh[8];
+    auto ld8 = [](const float* p, float (&o)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    };
+    ld8(coef + c0, cA);
+    ld8(coef + C + c0, cB);
+    ld8(coef + 2 * C + c0, cC);
+    if (scale) {
+        ld8(scale + c0, sc);
+        ld8(shift + c0, sh);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        mu[k] = __ldg(mean + c);
-        is[k] = __ldg(invstd + c);
-        k1[k] = __ldg(coef + c * 3);
-        k2[k] = __ldg(coef + c * 3 + 1);
-        k3[k] = __ldg(coef + c * 3 + 2);
-        sc[k] = scale ? __ldg(scale + c) : 0.f;
-        sh[k] = scale ? __ldg(shift + c) : 1.f;
+        for (int k = 0; k < 8; ++k) sc[k] = 0.f, sh[k] = 1.f;
     }
-    for (long long i = i0; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float g[8], zz[8], o[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dA) + i), g);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(z) + i), zz);
-        if (a_mask) {
-            float m[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(a_mask) + i), m);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = m[k] > 0.f ? g[k] : 0.f;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
-        }
+    const uint4* dA4 = reinterpret_cast<const uint4*>(dA);
+    const uint4* z4 = reinterpret_cast<const uint4*>(z);
+    const uint4* m4 = reinterpret_cast<const uint4*>(a_mask);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    long long i = i0;
+    for (; i + step < total; i += 2 * step) {
+        const long long j = i + step;
+        const uint4 ga = __ldg(dA4 + i), gb = __ldg(dA4 + j);
+        const uint4 za = __ldg(z4 + i), zb = __ldg(z4 + j);
+        float g[8], zz[8], h[8], zy[8], o[8], q[8];
+        unpack8(ga, g);
+        unpack8(za, zz);
+        unpack8(gb, h);
+        unpack8(zb, zy);
+        bn_bwd_mask8(g, zz, m4, i, sc, sh);
+        bn_bwd_mask8(h, zy, m4, j, sc, sh);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float zh = (zz[k] - mu[k]) * is[k];
-            o[k] = k1[k] * (g[k] - k2[k] - zh * k3[k]);
+            o[k] = cA[k] * g[k] + (cB[k] * zz[k] + cC[k]);
+            q[k] = cA[k] * h[k] + (cB[k] * zy[k] + cC[k]);
         }
+        reinterpret_cast<uint4*>(dz)[i] = pack8(o);
+        reinterpret_cast<uint4*>(dz)[j] = pack8(q);
+        if (g_out) {
+            reinterpret_cast<uint4*>(g_out)[i] = pack8(g);
+            reinterpret_cast<uint4*>(g_out)[j] = pack8(h);
+        }
+    }
+    if (i < total) {
+        float g[8], zz[8], o[8];
+        unpack8(__ldg(dA4 + i), g);
+        unpack8(__ldg(z4 + i), zz);
+        bn_bwd_mask8(g, zz, m4, i, sc, sh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = cA[k] * g[k] + (cB[k] * zz[k] + cC[k]);
         reinterpret_cast<uint4*>(dz)[i] = pack8(o);
         if (g_out) reinterpret_cast<uint4*>(g_out)[i] = pack8(g);
     }
@@ -243,6 +330,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* _
 // the element PyTorch's max_pool2d backward picks) won; the backward is then a pure gather.
 __global__ void maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                         uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+    griddep_launch();
+    griddep_wait();
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
     const long long total = (long long)N * Ho * Wo * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -290,6 +379,8 @@ __global__ void maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ in, __
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
                                    int H, int W, int C) {
+    griddep_launch();
+    griddep_wait();
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -335,6 +426,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const u
 // dA[n,h,w,c] = sum_{r,s} dL[n, h+1-r, w+1-s] * w[c][r][s]   (bf16 out, 16 channels per pixel)
 __global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
                                      __nv_bfloat16* __restrict__ dA, int N, int H, int W) {
+    griddep_launch();
+    griddep_wait();
     __shared__ float sw[144];
     if (threadIdx.x < 144) sw[threadIdx.x] = w[threadIdx.x];  // [c][r][s]
     __syncthreads();
@@ -377,6 +470,8 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* 
 __global__ void __launch_bounds__(288)
 head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ dL, float* __restrict__ partial,
                        int N, int H, int W) {
+    griddep_launch();
+    griddep_wait();
     const int tap = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = tap / 3, s = tap - 3 * r;
     float acc[16], bsum = 0.f;
@@ -416,6 +511,8 @@ head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ A, const float* __restr
 // out[j] = sum_b partial[b][j]; one WARP per column j (blockDim = 256 -> 8 columns per block)
 __global__ void __launch_bounds__(256)
 sum_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* __restrict__ out) {
+    griddep_launch();
+    griddep_wait();
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= width) return;
@@ -431,6 +528,8 @@ sum_rows_kernel(const float* __restrict__ partial, int nrows, int width, float* 
 __global__ void __launch_bounds__(256)
 loss_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ partial,
                     long long n) {
+    griddep_launch();
+    griddep_wait();
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
@@ -460,6 +559,8 @@ loss_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, fl
 // result[0..2] = bce, dice, bce+dice ; result[3..5] = I, P, T (saved for backward); single thread
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n, float eps,
                                      float* __restrict__ result) {
+    griddep_launch();
+    griddep_wait();
     if (threadIdx.x || blockIdx.x) return;
     double s[4] = {0, 0, 0, 0};
     for (int b = 0; b < nblocks; ++b)
@@ -480,6 +581,8 @@ __global__ void loss_bwd_kernel(const float* __restrict__ x, const float* __rest
                                 const float* __restrict__ result, const float* __restrict__ g_bce,
                                 const float* __restrict__ g_dice, float gscale, float eps, float* __restrict__ dx,
                                 long long n) {
+    griddep_launch();
+    griddep_wait();
     const float I = result[3], P = result[4], T = result[5];
     const float gb = (g_bce ? *g_bce : 0.f) * gscale / (float)n;
     float gd = (g_dice ? *g_dice : 0.f) * gscale;
@@ -505,6 +608,8 @@ constexpr int kMetricBlocks = 64;   // blocks per image (fixed: deterministic pa
 __global__ void __launch_bounds__(256)
 seg_metrics_partial_kernel(const float* __restrict__ p, const float* __restrict__ t, long long hw, float thresh,
                            float* __restrict__ partial) {
+    griddep_launch();
+    griddep_wait();
     const int n = blockIdx.y;
     const float* pn = p + (long long)n * hw;
     const float* tn = t + (long long)n * hw;
@@ -531,6 +636,8 @@ seg_metrics_partial_kernel(const float* __restrict__ p, const float* __restrict_
 // one block: thread n < N finishes image n (fp64), then the batch mean -> out[0] = dice, out[1] = iou
 __global__ void __launch_bounds__(256)
 seg_metrics_finalize_kernel(const float* __restrict__ partial, int N, float eps, float* __restrict__ out) {
+    griddep_launch();
+    griddep_wait();
     double dsum = 0, isum = 0;
     for (int n = threadIdx.x; n < N; n += 256) {
         double inter = 0, sp = 0, st = 0;
@@ -559,6 +666,8 @@ seg_metrics_finalize_kernel(const float* __restrict__ partial, int N, float eps,
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
                              float gscale, int zero_grad) {
+    griddep_launch();
+    griddep_wait();
     const long long n4 = n / 4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4 + (n & 3);
          i += (long long)gridDim.x * blockDim.x) {
@@ -606,6 +715,8 @@ struct UnpackTable {
 };
 __global__ void __launch_bounds__(256)
 unpack_grads_kernel(UnpackTable T, const float* __restrict__ gpk, float* __restrict__ grads) {
+    griddep_launch();
+    griddep_wait();
     int k = 0;
     while (k + 1 < T.n && (int)blockIdx.x >= T.e[k + 1].block_begin) ++k;
     const UnpackEntry E = T.e[k];
@@ -629,6 +740,8 @@ struct TapList {
 };
 __global__ void pack_dgrad_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
                                     int cin_total, int ci0, int cin, int R, int S, int ld, int col0, TapList taps) {
+    griddep_launch();
+    griddep_wait();
     const long long total = (long long)cin * taps.n * cout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -643,6 +756,8 @@ __global__ void pack_dgrad_w_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // tap index t = ((ph*2 + a)*2 + pw)*2 + b
 __global__ void pack_dec1_dlow_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cup,
                                         int cin_total) {
+    griddep_launch();
+    griddep_wait();
     const long long total = (long long)cup * 16 * cout;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {

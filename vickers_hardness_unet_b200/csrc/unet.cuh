@@ -299,6 +299,8 @@ inline int ctx_fail(Ctx* ctx, const std::string& msg) {
 __global__ void bn_fold_all_kernel(const int* __restrict__ tab, int nbn, const float* __restrict__ params,
                                    const float* __restrict__ buffers, float eps, float* __restrict__ scale,
                                    float* __restrict__ shift) {
+    griddep_launch();
+    griddep_wait();
     const int b = blockIdx.x;
     if (b >= nbn) return;
     const int* t = tab + b * 6;
@@ -372,7 +374,7 @@ inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers,
     UB_CUDA(cudaMemcpyAsync(ctx->head_w, params + hc.w, 145 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // weight + bias
     UB_CUDA(ctx->fwd_pack.launch(params, ctx->wpk, st));
     if (fold_bn) {
-        bn_fold_all_kernel<<<(int)S.bns.size(), 128, 0, st>>>(ctx->fold_tab, (int)S.bns.size(), params, buffers, 1e-5f,
+        launch_k(bn_fold_all_kernel, (int)S.bns.size(), 128, 0, st, ctx->fold_tab, (int)S.bns.size(), params, buffers, 1e-5f,
                                                               ctx->fold_scale, ctx->fold_shift);
         UB_CUDA(cudaGetLastError());
     }
@@ -565,7 +567,7 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         const int num_sms = ctx->num_sms;
         const int Hh = H / 2, Wh = W / 2;
         plan.steps.push_back({[=](cudaStream_t st) {
-            maxpool3x3s2_kernel<<<ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, num_sms), 256, 0, st>>>(
+            launch_k(maxpool3x3s2_kernel, ew_grid((long long)N * (Hh / 2) * (Wh / 2) * 8, 256, num_sms), 256, 0, st, 
                 f1, cur, N, Hh, Wh, 64);
             return cudaGetLastError();
         }, "encoder.maxpool", 0});
@@ -714,10 +716,10 @@ inline int ctx_forward_infer(Ctx* ctx, const float* x, float* logits, float* pro
     if (ctx->arena_used && ctx->arena_stream != st) UB_CUDA(cudaStreamWaitEvent(st, ctx->arena_event, 0));
     mark();
     if (x8)
-        pack_input_u8_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x8, P.xp, N, H,
+        launch_k(pack_input_u8_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x8, P.xp, N, H,
                                                                                                           W, bgr, *norm);
     else
-        pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st>>>(x, P.xp, N, H, W);
+        launch_k(pack_input_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x, P.xp, N, H, W);
     UB_CUDA(cudaGetLastError());
     for (auto& s : P.steps) {
         mark();

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kWcThreads, 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ WconvParams P) {
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -95,6 +96,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);
         float* cst = reinterpret_cast<float*>(sm + L.cstat_off);
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(kWcThreads, 1)
 wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ WpconvParams P) {
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -400,6 +403,7 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);
         for (int c = threadIdx.x; c < 512; c += kWcThreads) ss[c] = (P.scale && c < P.cout) ? P.scale[c] : 1.f;

@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX,
              const __grid_constant__ WgParams P, const int max_ncin) {
     extern __shared__ uint8_t smem_raw[];
+    griddep_launch();
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw_addr);
@@ -96,6 +97,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CU
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
         tmem_relinquish();
     }
+    griddep_wait();   // PDL: nothing above touches global memory
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -976,6 +976,79 @@ static void case_hwgrad(const char* name, int N, int H, int W, int cup, int cski
     }
     cudaFree(d_low); cudaFree(d_src); cudaFree(d_dz); cudaFree(d_g);
 }
+// xwgrad: dW of a 3x3 s1 conv given dZ and X (TMA halo boxes, all taps per pass), written into columns [dci0, dci0+cin)
+// of a packed [co][9][ctot] gradient (the other columns must stay untouched)
+static void case_xwgrad(const char* name, int N, int H, int W, int cin, int cout, int cextra) {
+    const int ctot = cextra + cin, dci0 = cextra;
+    HostT src(N, H, W, cin), dz(N, H, W, cout);
+    fill_rand_bf16(src.v, 1.0f);
+    fill_rand_bf16(dz.v, 1.0f);
+    std::vector<float> ref((size_t)cout * 9 * ctot, 0.f);
+#pragma omp parallel for collapse(2)
+    for (int co = 0; co < cout; ++co)
+        for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            for (int ci = 0; ci < cin; ++ci) {
+                double acc = 0;
+                for (int n = 0; n < N; ++n)
+                    for (int h = 0; h < H; ++h)
+                        for (int w = 0; w < W; ++w) acc += (double)dz.at(n, h, w, co) * src.get(n, h + r - 1, w + s - 1, ci);
+                ref[((size_t)co * 9 + tap) * ctot + dci0 + ci] = (float)acc;
+            }
+        }
+    __nv_bfloat16* d_src = to_dev_bf16(src.v);
+    __nv_bfloat16* d_dz = to_dev_bf16(dz.v);
+    float* d_g;
+    CK(cudaMalloc(&d_g, ref.size() * 4));
+    CK(cudaMemset(d_g, 0, ref.size() * 4));
+    XwgradLaunch L;
+    std::string e = xwgrad_build(L, d_src, cin, d_dz, cout, N, H, W, d_g, ctot, dci0, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %dx%d smem %u stages %d th %d co_blk %d cw %d wide %d\n", name, L.grid.x, L.grid.y, L.smem,
+           L.p.stages, L.p.th, L.p.co_blk, L.p.cw, L.p.wide);
+    CK(xwgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> got(ref.size());
+        CK(cudaMemcpy(got.data(), d_g, got.size() * 4, cudaMemcpyDeviceToHost));
+        report(name, compare(got, ref), 2e-3, got, ref, ctot);
+    }
+    cudaFree(d_src); cudaFree(d_dz); cudaFree(d_g);
+}
+static void bench_xwgrad(const char* name, int N, int H, int W, int cin, int cout, int iters) {
+    __nv_bfloat16 *d_src, *d_dz;
+    float* d_g;
+    CK(cudaMalloc(&d_src, (size_t)N * H * W * cin * 2));
+    CK(cudaMalloc(&d_dz, (size_t)N * H * W * cout * 2));
+    CK(cudaMalloc(&d_g, (size_t)cout * 9 * cin * 4));
+    CK(cudaMemset(d_src, 0x3C, (size_t)N * H * W * cin * 2));
+    CK(cudaMemset(d_dz, 0x3C, (size_t)N * H * W * cout * 2));
+    XwgradLaunch L;
+    std::string e = xwgrad_build(L, d_src, cin, d_dz, cout, N, H, W, d_g, cin, 0, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) { printf("[FAIL] bench %s: %s\n", name, e.c_str()); return; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) CK(xwgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) CK(xwgrad_launch(L, 0));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double flops = 2.0 * N * H * W * (double)cout * cin * 9;
+    const double bytes = 2.0 * N * H * W * (double)(cout + cin);
+    printf("[BENCH-XW] %-30s %8.1f us %7.1f TFLOP/s %6.2f TB/s  grid %dx%d stages %d th %d smem %u\n", name, ms * 1e3,
+           flops / ms * 1e-9, bytes / ms * 1e-9, L.grid.x, L.grid.y, L.p.stages, L.p.th, L.smem);
+    check_err_flag(name);
+    cudaFree(d_src); cudaFree(d_dz); cudaFree(d_g);
+}
 static void bench_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout, int iters) {
     const int ctot = cup + cskip;
     __nv_bfloat16 *d_low, *d_src, *d_dz;
@@ -1246,6 +1319,27 @@ int main(int argc, char** argv) {
         case_hwgrad("hwgrad up32->16 2x32x64", 2, 32, 64, 32, 0, 16);
         case_hwgrad("hwgrad up64+skip64->32 2x32x32 (4 groups)", 2, 32, 32, 64, 64, 32);
         case_hwgrad("hwgrad 64->64 5x64x64 (multi-tile/CTA)", 5, 64, 64, 0, 64, 64);
+    }
+    if (want("xwgrad")) {
+        case_xwgrad("xwgrad 16->16 2x32x32", 2, 32, 32, 16, 16, 0);
+        case_xwgrad("xwgrad 32->32 1x48x40 (th 16)", 1, 48, 40, 32, 32, 0);
+        case_xwgrad("xwgrad 64->64 3x24x24 (th 8, 2 co groups)", 3, 24, 24, 64, 64, 0);
+        case_xwgrad("xwgrad 16->32 1x32x16", 1, 32, 16, 16, 32, 0);
+        case_xwgrad("xwgrad 64->32 2x20x16 (partial tile rows, column offset 64 of 128)", 2, 20, 16, 64, 32, 64);
+        case_xwgrad("xwgrad 64->64 5x64x64 (multi-tile/CTA)", 5, 64, 64, 64, 64, 0);
+        case_xwgrad("xwgrad wide 128->128 2x16x16", 2, 16, 16, 128, 128, 0);
+        case_xwgrad("xwgrad wide 256->256 3x32x32", 3, 32, 32, 256, 256, 0);
+        case_xwgrad("xwgrad wide 64->128 1x64x64 (column offset 128)", 1, 64, 64, 64, 128, 128);
+        case_xwgrad("xwgrad wide 512->512 2x16x16", 2, 16, 16, 512, 512, 0);
+    }
+    if (want("xbench")) {
+        bench_xwgrad("D4c2 16->16 @512^2 x16", 16, 512, 512, 16, 16, 5);
+        bench_xwgrad("D3c2 32->32 @256^2 x16", 16, 256, 256, 32, 32, 5);
+        bench_xwgrad("L1 64->64 @128^2 x16", 16, 128, 128, 64, 64, 10);
+        bench_xwgrad("D3c1 skip64->32 @256^2 x16", 16, 256, 256, 64, 32, 5);
+        bench_xwgrad("L2 128->128 @64^2 x16", 16, 64, 64, 128, 128, 10);
+        bench_xwgrad("L3 256->256 @32^2 x16", 16, 32, 32, 256, 256, 10);
+        bench_xwgrad("L4 512->512 @16^2 x16", 16, 16, 16, 512, 512, 10);
     }
     if (want("wbench")) {
         bench_hwgrad("D4c2 16->16 @512^2 x16", 16, 512, 512, 0, 16, 16, 5);

@@ -11,6 +11,7 @@
 #include "tconv.cuh"
 #include "wconv.cuh"
 #include "wconv2.cuh"
+#include "xwgrad.cuh"
 #include "tmap.cuh"
 
 namespace ub {
@@ -736,7 +737,7 @@ inline bool hwgrad_ok(int cup, int cskip, int cout) {
     return true;
 }
 inline std::string hwgrad_build(HwgradLaunch& L, const void* low, int cup, const void* src, int cskip, const void* dz,
-                                int cout, int N, int H, int W, float* gpk, int* err, int num_sms) {
+                                int cout, int N, int H, int W, float* gpk, int* err, int num_sms, int gtot = 0) {
     memset(&L.p, 0, sizeof(L.p));
     if (!hwgrad_ok(cup, cskip, cout)) return "hwgrad: unsupported channel configuration";
     if (cup && ((H | W) & 1)) return "hwgrad: up-sampled source needs even H, W";
@@ -753,6 +754,7 @@ inline std::string hwgrad_build(HwgradLaunch& L, const void* low, int cup, const
     P.cw = ctot < 64 ? ctot : 64;
     P.ndh_max = 9 * P.cw <= 512 ? 3 : (6 * P.cw <= 512 ? 2 : 1);
     P.gpk = gpk;
+    P.gtot = gtot ? gtot : ctot;
     P.err = err;
     int stages = 4;
     for (; stages >= 2; --stages)
@@ -776,6 +778,80 @@ inline cudaError_t hwgrad_launch(const HwgradLaunch& L, cudaStream_t st) {
         attr_set = true;
     }
     launch_k(hwgrad_kernel, L.grid, kHcThreads, L.smem, st, L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ xwgrad (TMA halo wgrad)
+struct XwgradLaunch {
+    CUtensorMap z, x;
+    XwgradParams p;
+    dim3 grid;
+    uint32_t smem = 0;
+};
+// dZ [N,H,W,cout] x X [N,H,W,cin] (both dense NHWC bf16) -> gpk[cout][9][ctot] columns [dci0, dci0 + cin)
+inline bool xwgrad_ok(int cin, int cout, int H, int W) {
+    if (!(cin == 16 || cin == 32 || cin % 64 == 0)) return false;
+    if (!(cout == 16 || cout == 32 || cout == 64 || cout % 128 == 0)) return false;
+    if (getenv("UNETB200_NO_XWGRAD")) return false;
+    return W % kXwTileW == 0 && H % 2 == 0 && H >= 8;
+}
+inline std::string xwgrad_build(XwgradLaunch& L, const void* x, int cin, const void* dz, int cout, int N, int H, int W,
+                                float* gpk, int ctot, int dci0, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    if (!xwgrad_ok(cin, cout, H, W)) return "xwgrad: unsupported configuration";
+    XwgradParams& P = L.p;
+    P.H = H; P.W = W; P.N = N;
+    P.wide = cout >= 128;
+    P.co_blk = P.wide ? 128 : (cout < 32 ? cout : 32);
+    P.zc_box = P.co_blk < 64 ? P.co_blk : 64;
+    P.n_zbox = P.co_blk / P.zc_box;
+    P.cw = P.wide ? (cin < 32 ? cin : 32) : (cin < 64 ? cin : 64);
+    P.th = (H % 32 == 0) ? 32 : (H % 16 == 0 ? 16 : 8);
+    P.tiles_w = W / kXwTileW;
+    P.tiles_h = (H + P.th - 1) / P.th;
+    P.cout = cout; P.cin = cin;
+    P.ctot = ctot; P.dci0 = dci0;
+    P.gpk = gpk;
+    P.err = err;
+    if ((P.wide ? 3 : 1) * 3 * P.cw > 512) return "xwgrad: accumulators do not fit in TMEM";
+    int stages = 6;
+    for (; stages >= 2; --stages)
+        if (xwgrad_smem(P.th, P.zc_box, P.n_zbox, P.cw, stages).total + 1024 <= 232448u) break;
+    if (stages < 2) return "xwgrad: does not fit in shared memory";
+    P.stages = stages;
+    L.smem = xwgrad_smem(P.th, P.zc_box, P.n_zbox, P.cw, stages).total + 1024;
+    {
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2};
+        uint32_t box[4] = {(uint32_t)P.zc_box, (uint32_t)kXwTileW, (uint32_t)(P.th + 2), 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.z, dz, 4, dims, str, box, es, swizzle_for_bytes(P.zc_box * 2));
+        if (!e.empty()) return "xwgrad dZ map: " + e;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+        uint32_t box[4] = {(uint32_t)P.cw, (uint32_t)(kXwTileW + 2), (uint32_t)P.th, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.x, x, 4, dims, str, box, es, swizzle_for_bytes(P.cw * 2));
+        if (!e.empty()) return "xwgrad X map: " + e;
+    }
+    const int ngroups = (cout / P.co_blk) * (cin / P.cw);
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    int gx = num_sms / ngroups;
+    if (gx < 1) gx = 1;
+    if (gx > total_tiles) gx = total_tiles;
+    L.grid = dim3(gx, ngroups, 1);
+    return "";
+}
+inline cudaError_t xwgrad_launch(const XwgradLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(xwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    launch_k(xwgrad_kernel, L.grid, kXwThreads, L.smem, st, L.z, L.x, L.p);
     return cudaGetLastError();
 }
 

@@ -28,7 +28,8 @@ struct HwgradParams {
     int cw;                         // input channels per CTA group (min(ctot, 64))
     int ndh_max;                    // filter rows per CTA group (3, or fewer when 3 * 3 * cw > 512 TMEM columns)
     int stages;
-    float* gpk;                     // packed gradient [cout][9][ctot] fp32
+    float* gpk;                     // packed gradient [cout][9][gtot] fp32
+    int gtot;                       // gradient row length (>= ctot: further channels are another launch's)
     int* err;
 };
 
@@ -210,7 +211,7 @@ hwgrad_kernel(const __grid_constant__ HwgradParams P) {
                     tmem_ld_wait();
                     if (co < P.cout) {
                         const int s = c0 / P.cw, ci = c_lo + (c0 - s * P.cw);
-                        float* gp = P.gpk + ((size_t)co * 9 + (dh0 + d) * 3 + s) * ctot + ci;
+                        float* gp = P.gpk + ((size_t)co * 9 + (dh0 + d) * 3 + s) * P.gtot + ci;
 #pragma unroll
                         for (int j = 0; j < 16; j += 4)
                             red_add_v4(gp + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),

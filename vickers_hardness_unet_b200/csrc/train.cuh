@@ -685,20 +685,34 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     };
     // halo-resident wgrad (hwgrad.cuh) of a narrow 3x3/s1 conv over cat(nearest2x(low)[cup], src[cskip])
     auto add_hwg = [&](int stage, int conv, const void* low, int cup, const void* src, int cskip, const void* dz, int Hh,
-                       int Ww) -> std::string {
+                       int Ww, int gtot = 0) -> std::string {
         const ConvRef& c = S.convs[conv];
         if (std::find(stage_convs[stage].begin(), stage_convs[stage].end(), conv) == stage_convs[stage].end())
             stage_convs[stage].push_back(conv);
         HwgradLaunch HL;
-        std::string e = hwgrad_build(HL, low, cup, src, cskip, dz, c.cout, N, Hh, Ww, T.gpk + c.w, ctx->d_err, SM);
+        std::string e = hwgrad_build(HL, low, cup, src, cskip, dz, c.cout, N, Hh, Ww, T.gpk + c.w, ctx->d_err, SM, gtot);
         if (!e.empty()) return c.name + " wgrad: " + e;
-        add_b(stage, "wgrad:" + c.name, [HL](cudaStream_t st) { return hwgrad_launch(HL, st); });
+        add_b(stage, "wgrad:" + c.name + (gtot ? "[up]" : ""), [HL](cudaStream_t st) { return hwgrad_launch(HL, st); });
+        return "";
+    };
+    // TMA halo wgrad (xwgrad.cuh) of a 3x3/s1 conv over a dense source: columns [dci0, dci0 + cin) of the packed gradient
+    auto add_xwg = [&](int stage, int conv, const std::string& nm, const void* x, int cin, const void* dz, int Hh, int Ww,
+                       int ctot, int dci0) -> std::string {
+        const ConvRef& c = S.convs[conv];
+        if (std::find(stage_convs[stage].begin(), stage_convs[stage].end(), conv) == stage_convs[stage].end())
+            stage_convs[stage].push_back(conv);
+        XwgradLaunch XL;
+        std::string e = xwgrad_build(XL, x, cin, dz, c.cout, N, Hh, Ww, T.gpk + c.w, ctot, dci0, ctx->d_err, SM);
+        if (!e.empty()) return nm + " wgrad: " + e;
+        add_b(stage, "wgrad:" + nm, [XL](cudaStream_t st) { return xwgrad_launch(XL, st); });
         return "";
     };
     auto wg_conv3 = [&](int stage, int ui, const void* x_in, int x_C, int x_H, int x_W) -> std::string {
         // regular k x k conv weight gradient
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
+        if (c.k == 3 && c.stride == 1 && xwgrad_ok(c.cin, c.cout, u.Ho, u.Wo))
+            return add_xwg(stage, u.conv, c.name, x_in, c.cin, u.dz, u.Ho, u.Wo, c.cin, 0);
         if (c.k == 3 && c.stride == 1 && hwgrad_ok(0, c.cin, c.cout))
             return add_hwg(stage, u.conv, nullptr, 0, x_in, c.cin, u.dz, u.Ho, u.Wo);
         WgSpec s;
@@ -770,12 +784,22 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         bn_bwd(0, r.u1, dA[r.u1], true, nullptr);
         const int cin_total = d.cup + d.cskip;
         const bool c1_hwg = hwgrad_ok(d.cup, d.cskip, d.cout);
+        const bool skip_xwg = d.cskip && xwgrad_ok(d.cskip, d.cout, u1.Ho, u1.Wo) && (!c1_hwg || hwgrad_ok(d.cup, 0, d.cout));
         if (c1_hwg) {
-            // one launch over cat(nearest2x(low), skip): gradient w.r.t. the original 3x3 weights
-            if (!(err = add_hwg(0, d.c1, r.low, d.cup, r.skip, d.cskip, u1.dz, u1.Ho, u1.Wo)).empty()) return err;
+            // up-sampled channels (and the skip channels unless xwgrad takes them) over cat(nearest2x(low), skip):
+            // gradient w.r.t. the original 3x3 weights
+            if (skip_xwg) {
+                if (!(err = add_hwg(0, d.c1, r.low, d.cup, nullptr, 0, u1.dz, u1.Ho, u1.Wo, cin_total)).empty()) return err;
+            } else if (!(err = add_hwg(0, d.c1, r.low, d.cup, r.skip, d.cskip, u1.dz, u1.Ho, u1.Wo)).empty()) {
+                return err;
+            }
+        }
+        if (skip_xwg) {
+            if (!(err = add_xwg(0, d.c1, c1.name + "[skip]", r.skip, d.cskip, u1.dz, u1.Ho, u1.Wo, cin_total, d.cup)).empty())
+                return err;
         }
         // weight gradient, skip channels: regular 3x3 over the skip tensor
-        if (d.cskip && !c1_hwg) {
+        if (d.cskip && !c1_hwg && !skip_xwg) {
             WgSpec s;
             s.name = c1.name + "[skip]";
             s.z = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, d.cout);

@@ -1049,6 +1049,81 @@ static void bench_xwgrad(const char* name, int N, int H, int W, int cin, int cou
     check_err_flag(name);
     cudaFree(d_src); cudaFree(d_dz); cudaFree(d_g);
 }
+// xwgrad up mode: dW of a 3x3 s1 conv over nearest2x(low) given the high-resolution dZ
+static void case_xwgrad_up(const char* name, int N, int H, int W, int cup, int cout, int cextra) {
+    const int ctot = cup + cextra, dci0 = 0;
+    HostT low(N, H / 2, W / 2, cup), upx(N, H, W, cup), dz(N, H, W, cout);
+    fill_rand_bf16(low.v, 1.0f);
+    fill_rand_bf16(dz.v, 1.0f);
+    for (int n = 0; n < N; ++n)
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w)
+                for (int c = 0; c < cup; ++c) upx.at(n, h, w, c) = low.at(n, h / 2, w / 2, c);
+    std::vector<float> ref((size_t)cout * 9 * ctot, 0.f);
+#pragma omp parallel for collapse(2)
+    for (int co = 0; co < cout; ++co)
+        for (int tap = 0; tap < 9; ++tap) {
+            const int r = tap / 3, s = tap % 3;
+            for (int ci = 0; ci < cup; ++ci) {
+                double acc = 0;
+                for (int n = 0; n < N; ++n)
+                    for (int h = 0; h < H; ++h)
+                        for (int w = 0; w < W; ++w) acc += (double)dz.at(n, h, w, co) * upx.get(n, h + r - 1, w + s - 1, ci);
+                ref[((size_t)co * 9 + tap) * ctot + dci0 + ci] = (float)acc;
+            }
+        }
+    __nv_bfloat16* d_low = to_dev_bf16(low.v);
+    __nv_bfloat16* d_dz = to_dev_bf16(dz.v);
+    float* d_g;
+    CK(cudaMalloc(&d_g, ref.size() * 4));
+    CK(cudaMemset(d_g, 0, ref.size() * 4));
+    XwgradLaunch L;
+    std::string e = xwgrad_build(L, d_low, cup, d_dz, cout, N, H / 2, W / 2, d_g, ctot, dci0, g_ctx->d_err, g_ctx->num_sms, true);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    printf("       %s: grid %dx%dx%d smem %u stages %d th %d co_blk %d cw %d wide %d\n", name, L.grid.x, L.grid.y, L.grid.z,
+           L.smem, L.p.stages, L.p.th, L.p.co_blk, L.p.cw, L.p.wide);
+    CK(xwgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> got(ref.size());
+        CK(cudaMemcpy(got.data(), d_g, got.size() * 4, cudaMemcpyDeviceToHost));
+        report(name, compare(got, ref), 2e-3, got, ref, ctot);
+    }
+    cudaFree(d_low); cudaFree(d_dz); cudaFree(d_g);
+}
+static void bench_xwgrad_up(const char* name, int N, int H, int W, int cup, int cout, int iters) {
+    __nv_bfloat16 *d_low, *d_dz;
+    float* d_g;
+    CK(cudaMalloc(&d_low, (size_t)N * (H / 2) * (W / 2) * cup * 2));
+    CK(cudaMalloc(&d_dz, (size_t)N * H * W * cout * 2));
+    CK(cudaMalloc(&d_g, (size_t)cout * 9 * cup * 4));
+    CK(cudaMemset(d_low, 0x3C, (size_t)N * (H / 2) * (W / 2) * cup * 2));
+    CK(cudaMemset(d_dz, 0x3C, (size_t)N * H * W * cout * 2));
+    XwgradLaunch L;
+    std::string e = xwgrad_build(L, d_low, cup, d_dz, cout, N, H / 2, W / 2, d_g, cup, 0, g_ctx->d_err, g_ctx->num_sms, true);
+    if (!e.empty()) { printf("[FAIL] bench %s: %s\n", name, e.c_str()); return; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) CK(xwgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) CK(xwgrad_launch(L, 0));
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double bytes = 2.0 * N * H * W * (double)cout + 2.0 * N * (H / 2) * (W / 2) * (double)cup;
+    printf("[BENCH-XW] %-30s %8.1f us %6.2f TB/s  grid %dx%dx%d stages %d th %d smem %u\n", name, ms * 1e3,
+           bytes / ms * 1e-9, L.grid.x, L.grid.y, L.grid.z, L.p.stages, L.p.th, L.smem);
+    check_err_flag(name);
+    cudaFree(d_low); cudaFree(d_dz); cudaFree(d_g);
+}
 static void bench_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout, int iters) {
     const int ctot = cup + cskip;
     __nv_bfloat16 *d_low, *d_src, *d_dz;
@@ -1331,6 +1406,11 @@ int main(int argc, char** argv) {
         case_xwgrad("xwgrad wide 256->256 3x32x32", 3, 32, 32, 256, 256, 0);
         case_xwgrad("xwgrad wide 64->128 1x64x64 (column offset 128)", 1, 64, 64, 64, 128, 128);
         case_xwgrad("xwgrad wide 512->512 2x16x16", 2, 16, 16, 512, 512, 0);
+        case_xwgrad_up("xwgrad up32->16 2x32x64", 2, 32, 64, 32, 16, 0);
+        case_xwgrad_up("xwgrad up64->32 2x32x32 (of 128 columns)", 2, 32, 32, 64, 32, 64);
+        case_xwgrad_up("xwgrad up128->64 1x48x32 (of 192 columns)", 1, 48, 32, 128, 64, 64);
+        case_xwgrad_up("xwgrad wide up256->128 2x32x32 (of 384 columns)", 2, 32, 32, 256, 128, 128);
+        case_xwgrad_up("xwgrad wide up512->256 1x32x32 (of 768 columns)", 1, 32, 32, 512, 256, 256);
     }
     if (want("xbench")) {
         bench_xwgrad("D4c2 16->16 @512^2 x16", 16, 512, 512, 16, 16, 5);
@@ -1340,6 +1420,11 @@ int main(int argc, char** argv) {
         bench_xwgrad("L2 128->128 @64^2 x16", 16, 64, 64, 128, 128, 10);
         bench_xwgrad("L3 256->256 @32^2 x16", 16, 32, 32, 256, 256, 10);
         bench_xwgrad("L4 512->512 @16^2 x16", 16, 16, 16, 512, 512, 10);
+        bench_xwgrad_up("D4c1 up32->16 @512^2 x16", 16, 512, 512, 32, 16, 5);
+        bench_xwgrad_up("D3c1 up64->32 @256^2 x16", 16, 256, 256, 64, 32, 5);
+        bench_xwgrad_up("D2c1 up128->64 @128^2 x16", 16, 128, 128, 128, 64, 10);
+        bench_xwgrad_up("D1c1 up256->128 @64^2 x16", 16, 64, 64, 256, 128, 10);
+        bench_xwgrad_up("D0c1 up512->256 @32^2 x16", 16, 32, 32, 512, 256, 10);
     }
     if (want("wbench")) {
         bench_hwgrad("D4c2 16->16 @512^2 x16", 16, 512, 512, 0, 16, 16, 5);

@@ -795,12 +795,14 @@ inline bool xwgrad_ok(int cin, int cout, int H, int W) {
     if (getenv("UNETB200_NO_XWGRAD")) return false;
     return W % kXwTileW == 0 && H % 2 == 0 && H >= 8;
 }
+// up = true: x is the LOW-resolution tensor [N,H,W,cin] of a nearest-2x up-sample and dz is [N,2H,2W,cout]
 inline std::string xwgrad_build(XwgradLaunch& L, const void* x, int cin, const void* dz, int cout, int N, int H, int W,
-                                float* gpk, int ctot, int dci0, int* err, int num_sms) {
+                                float* gpk, int ctot, int dci0, int* err, int num_sms, bool up = false) {
     memset(&L.p, 0, sizeof(L.p));
     if (!xwgrad_ok(cin, cout, H, W)) return "xwgrad: unsupported configuration";
     XwgradParams& P = L.p;
     P.H = H; P.W = W; P.N = N;
+    P.up = up ? 1 : 0;
     P.wide = cout >= 128;
     P.co_blk = P.wide ? 128 : (cout < 32 ? cout : 32);
     P.zc_box = P.co_blk < 64 ? P.co_blk : 64;
@@ -821,10 +823,11 @@ inline std::string xwgrad_build(XwgradLaunch& L, const void* x, int cin, const v
     P.stages = stages;
     L.smem = xwgrad_smem(P.th, P.zc_box, P.n_zbox, P.cw, stages).total + 1024;
     {
-        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2};
-        uint32_t box[4] = {(uint32_t)P.zc_box, (uint32_t)kXwTileW, (uint32_t)(P.th + 2), 1};
-        uint32_t es[4] = {1, 1, 1, 1};
+        const uint64_t m = up ? 2 : 1;   // up mode: every second pixel / row of the high-resolution gradient
+        uint64_t dims[4] = {(uint64_t)cout, m * W, m * H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cout * 2, m * W * cout * 2, m * H * m * W * cout * 2};
+        uint32_t box[4] = {(uint32_t)P.zc_box, (uint32_t)(m * kXwTileW), (uint32_t)(m * (P.th + 2)), 1};
+        uint32_t es[4] = {1, (uint32_t)m, (uint32_t)m, 1};
         std::string e = make_tmap_bf16(&L.z, dz, 4, dims, str, box, es, swizzle_for_bytes(P.zc_box * 2));
         if (!e.empty()) return "xwgrad dZ map: " + e;
     }
@@ -838,10 +841,10 @@ inline std::string xwgrad_build(XwgradLaunch& L, const void* x, int cin, const v
     }
     const int ngroups = (cout / P.co_blk) * (cin / P.cw);
     const int total_tiles = P.tiles_w * P.tiles_h * N;
-    int gx = num_sms / ngroups;
+    int gx = num_sms / (ngroups * (up ? 4 : 1));
     if (gx < 1) gx = 1;
     if (gx > total_tiles) gx = total_tiles;
-    L.grid = dim3(gx, ngroups, 1);
+    L.grid = dim3(gx, ngroups, up ? 4 : 1);
     return "";
 }
 inline cudaError_t xwgrad_launch(const XwgradLaunch& L, cudaStream_t st) {

@@ -697,12 +697,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     };
     // TMA halo wgrad (xwgrad.cuh) of a 3x3/s1 conv over a dense source: columns [dci0, dci0 + cin) of the packed gradient
     auto add_xwg = [&](int stage, int conv, const std::string& nm, const void* x, int cin, const void* dz, int Hh, int Ww,
-                       int ctot, int dci0) -> std::string {
+                       int ctot, int dci0, bool up = false) -> std::string {
         const ConvRef& c = S.convs[conv];
         if (std::find(stage_convs[stage].begin(), stage_convs[stage].end(), conv) == stage_convs[stage].end())
             stage_convs[stage].push_back(conv);
         XwgradLaunch XL;
-        std::string e = xwgrad_build(XL, x, cin, dz, c.cout, N, Hh, Ww, T.gpk + c.w, ctot, dci0, ctx->d_err, SM);
+        std::string e = xwgrad_build(XL, x, cin, dz, c.cout, N, Hh, Ww, T.gpk + c.w, ctot, dci0, ctx->d_err, SM, up);
         if (!e.empty()) return nm + " wgrad: " + e;
         add_b(stage, "wgrad:" + nm, [XL](cudaStream_t st) { return xwgrad_launch(XL, st); });
         return "";
@@ -783,7 +783,13 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         if (!(err = dgrad3(0, r.u2, dA[r.u1], nullptr)).empty()) return err;
         bn_bwd(0, r.u1, dA[r.u1], true, nullptr);
         const int cin_total = d.cup + d.cskip;
-        const bool c1_hwg = hwgrad_ok(d.cup, d.cskip, d.cout);
+        // up-sampled channels: xwgrad up mode over the low-resolution tensor (anchors = its pixels, 4 output parities)
+        const bool up_xwg = xwgrad_ok(d.cup, d.cout, r.Hl, r.Wl);
+        if (up_xwg) {
+            if (!(err = add_xwg(0, d.c1, c1.name + "[up]", r.low, d.cup, u1.dz, r.Hl, r.Wl, cin_total, 0, true)).empty())
+                return err;
+        }
+        const bool c1_hwg = !up_xwg && hwgrad_ok(d.cup, d.cskip, d.cout);
         const bool skip_xwg = d.cskip && xwgrad_ok(d.cskip, d.cout, u1.Ho, u1.Wo) && (!c1_hwg || hwgrad_ok(d.cup, 0, d.cout));
         if (c1_hwg) {
             // up-sampled channels (and the skip channels unless xwgrad takes them) over cat(nearest2x(low), skip):
@@ -814,7 +820,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             if (!(err = add_wg(0, s)).empty()) return err;
         }
         // weight gradient, up-sampled channels: per output parity a 2x2 low-res neighbourhood, fanned out to 3x3
-        for (int par = 0; par < (c1_hwg ? 0 : 4); ++par) {
+        for (int par = 0; par < ((c1_hwg || up_xwg) ? 0 : 4); ++par) {
             const int ph = par >> 1, pw = par & 1;
             WgSpec s;
             s.name = c1.name + "[up parity]";

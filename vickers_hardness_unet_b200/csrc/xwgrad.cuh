@@ -17,6 +17,12 @@
 // Accumulators stay in TMEM for the whole kernel (the pixel range is split over the CTAs of a group); at the end each
 // CTA adds its partial into the packed fp32 gradient [cout][9][ctot] with 16-byte vector reductions.  Zero fill of the
 // out-of-image part of both boxes makes partial tiles and the image border exact.  blockIdx.y = (co block, ci block).
+//
+// Up mode (decoder conv1, channels of the nearest-2x up-sampled tensor):  X = the LOW-resolution tensor, anchors = its
+// pixels u, and blockIdx.z = output parity (a, b): the dZ box is loaded with TMA element strides (2, 2) starting at
+// (2*w0 + b, 2*(h0-1) + a), i.e. it is the dense image G_ab[u] = dZ[2u + (a, b)].  The main loop is unchanged; a block
+// (row shift dh = 1 - j, column shift dw = s - 1 of `low` against G_ab) is added to every 3x3 tap (r, s') with
+// floor((a + r - 1) / 2) = dh and floor((b + s' - 1) / 2) = dw (1, 2 or 4 taps; blocks with no tap are skipped).
 #pragma once
 #include "ptx.cuh"
 
@@ -33,6 +39,7 @@ struct XwgradParams {
     int co_blk, cw;         // channels per CTA group
     int zc_box, n_zbox;     // dZ box channels (<= 64) and boxes per step
     int wide;
+    int up;                 // 1: up mode (H, W = extent of the low-resolution tensor; dZ is [N, 2H, 2W, cout])
     int stages;
     int ctot, dci0;         // packed gradient: row length and first column of X's channels
     float* gpk;
@@ -79,6 +86,9 @@ xwgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
     const int total_tiles = P.tiles_w * P.tiles_h * P.N;
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(nacc * ncol)) tmem_cols <<= 1;
+    const int pa = P.up ? (int)(blockIdx.z >> 1) : 0, pb = P.up ? (int)(blockIdx.z & 1) : 0;   // output parity
+    // wide mode: accumulators (row shifts dh = 1 - d) that carry taps: all three, or two of them in up mode
+    const int d_lo = (P.wide && P.up && pa == 0) ? 1 : 0, d_hi = (P.wide && P.up && pa == 1) ? 2 : nacc;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmZ);
@@ -114,9 +124,10 @@ xwgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
                 }
                 const uint32_t zb = base + stage * L.stage_bytes, xb = zb + L.z_bytes;
                 mbar_expect_tx(full_bar(stage), tx);
+                const int zw = P.up ? 2 * tw * kXwTileW + pb : tw * kXwTileW;
+                const int zh = P.up ? 2 * (th_ * P.th - 1) + pa : th_ * P.th - 1;
                 for (int b = 0; b < P.n_zbox; ++b)
-                    tma_load_4d(zb + b * L.zbox_bytes, &tmZ, full_bar(stage), co0 + b * P.zc_box, tw * kXwTileW,
-                                th_ * P.th - 1, tn);
+                    tma_load_4d(zb + b * L.zbox_bytes, &tmZ, full_bar(stage), co0 + b * P.zc_box, zw, zh, tn);
                 tma_load_4d(xb, &tmX, full_bar(stage), ci0, tw * kXwTileW - 1, th_ * P.th, tn);
                 if (++stage == P.stages) {
                     stage = 0;
@@ -145,19 +156,37 @@ xwgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
                 const uint64_t a_base = umma_desc(zb, P.wide ? L.zbox_bytes : zrow, zrow, lay_z);
                 // B = X: N-block s = filter column s = the same rows one pixel further
                 const uint64_t b_base = umma_desc(xb, R, xrow, lay_x);
-                if (P.wide) {
+                // fully unrolled issue bodies: the single issuing thread is the critical path (a dynamic inner loop
+                // over the accumulators cost 50 % on the wide layers)
+                const uint32_t a_step = (2 * zrow) >> 4, b_step = (2 * xrow) >> 4, zr = zrow >> 4;
+                uint64_t ad = a_base + (uint64_t)(d_lo * zr), bd = b_base;
+                const uint32_t t0 = tmem_base + d_lo * ncol, t1 = t0 + ncol, t2 = t1 + ncol;
+                if (!P.wide) {
+#pragma unroll 4
                     for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t bd = b_base + ((uint32_t)(2 * k) * xrow >> 4);
-#pragma unroll
-                        for (int d = 0; d < 3; ++d)
-                            umma_bf16(tmem_base + d * ncol, a_base + ((uint32_t)(2 * k + d) * zrow >> 4), bd, idesc, accum);
+                        umma_bf16(t0, ad, bd, idesc, accum);
                         accum = 1;
+                        ad += a_step;
+                        bd += b_step;
+                    }
+                } else if (d_hi - d_lo == 3) {
+#pragma unroll 4
+                    for (int k = 0; k < ksteps; ++k) {
+                        umma_bf16(t0, ad, bd, idesc, accum);
+                        umma_bf16(t1, ad + zr, bd, idesc, accum);
+                        umma_bf16(t2, ad + 2 * zr, bd, idesc, accum);
+                        accum = 1;
+                        ad += a_step;
+                        bd += b_step;
                     }
                 } else {
+#pragma unroll 4
                     for (int k = 0; k < ksteps; ++k) {
-                        umma_bf16(tmem_base, a_base + ((uint32_t)(2 * k) * zrow >> 4), b_base + ((uint32_t)(2 * k) * xrow >> 4),
-                                  idesc, accum);
+                        umma_bf16(t0, ad, bd, idesc, accum);
+                        umma_bf16(t1, ad + zr, bd, idesc, accum);
                         accum = 1;
+                        ad += a_step;
+                        bd += b_step;
                     }
                 }
                 umma_commit(empty_bar(stage));
@@ -179,21 +208,36 @@ xwgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ C
         tc_fence_after();
         const int j = P.wide ? 0 : m / P.co_blk;
         const int co = co0 + (P.wide ? m : m - j * P.co_blk);
-        const bool valid = P.wide ? true : j < 3;
-        for (int d = 0; d < nacc; ++d) {
-            const int r = 2 - (P.wide ? d : j);
+        // filter taps a (shift, parity) block is added to: plain mode 1 tap; up mode 0, 1 or 2 per dimension
+        auto taps = [&](int delta, int par, int plain, int (&out)[2]) -> int {
+            if (!P.up) {
+                out[0] = plain;
+                return 1;
+            }
+            int n = 0;
+            for (int t = 0; t < 3; ++t)
+                if (((par + t + 1) >> 1) - 1 == delta) out[n++] = t;   // floor((par + t - 1) / 2) == delta
+            return n;
+        };
+        for (int d = d_lo; d < d_hi; ++d) {
+            const int jj = P.wide ? d : j;
+            int rr[2] = {0, 0}, cc[2] = {0, 0};
+            const int nr = (P.wide || j < 3) ? taps(1 - jj, pa, 2 - jj, rr) : 0;
             for (int c0 = 0; c0 < ncol; c0 += 16) {
+                const int s = c0 / P.cw, ci = ci0 + (c0 - s * P.cw);
+                const int nc = taps(s - 1, pb, s, cc);
+                if (nc == 0) continue;                // warp-uniform (nr is not in narrow mode: tcgen05.ld is warp-collective)
                 uint32_t v[16];
                 tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + d * ncol + c0, v);
                 tmem_ld_wait();
-                if (valid) {
-                    const int s = c0 / P.cw, ci = ci0 + (c0 - s * P.cw);
-                    float* gp = P.gpk + ((size_t)co * 9 + r * 3 + s) * P.ctot + P.dci0 + ci;
+                for (int a = 0; a < nr; ++a)
+                    for (int b = 0; b < nc; ++b) {
+                        float* gp = P.gpk + ((size_t)co * 9 + rr[a] * 3 + cc[b]) * P.ctot + P.dci0 + ci;
 #pragma unroll
-                    for (int e = 0; e < 16; e += 4)
-                        red_add_v4(gp + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
-                                   __uint_as_float(v[e + 3]));
-                }
+                        for (int e = 0; e < 16; e += 4)
+                            red_add_v4(gp + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                                       __uint_as_float(v[e + 3]));
+                    }
             }
         }
     }

@@ -64,7 +64,7 @@ class _Checker:
         return bad
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 96), (3, 128, 128)])
+@pytest.mark.parametrize("shape", [(2, 64, 96), (3, 128, 128), (1, 256, 256)])
 def test_every_backward_kernel_on_its_own_inputs(shape):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False

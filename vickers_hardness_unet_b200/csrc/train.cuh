@@ -1142,6 +1142,7 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             ctx->prof_mark("head_bwd:segmentation_head", st);
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
+            if (npx >= (1ll << 31)) return ctx_fail(ctx, "train_backward: N*H*W must be below 2^31 (32-bit pixel arithmetic)");
             launch_k(head_bwd_data_kernel, ew_grid(npx, 256, SM), 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W);
             const int nb = 8 * SM;
             launch_k(head_bwd_weight_kernel, nb, 288, 0, st, P.head_in, dlogits, P.red_part, N, H, W);

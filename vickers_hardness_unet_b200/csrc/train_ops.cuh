@@ -434,9 +434,10 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* 
     const long long total = (long long)N * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int x = int(i % W);
-        const int y = int((i / W) % H);
-        const long long nb = (i / ((long long)W * H)) * H * W;
+        const unsigned ui = (unsigned)i, row = ui / (unsigned)W;   // N*H*W < 2^32 (checked by the host): 32-bit div/mod
+        const int x = int(ui - row * (unsigned)W);
+        const int y = int(row % (unsigned)H);
+        const long long nb = (long long)(row / (unsigned)H) * H * W;
         float d[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -477,25 +478,45 @@ head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ A, const float* __restr
     float acc[16], bsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-    const long long groups = ((long long)N * H * W + 31) / 32;
-    const long long total = (long long)N * H * W;
-    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
-        const long long i = g * 32 + lane;
-        if (i >= total) continue;
-        const int x = int(i % W);
-        const int y = int((i / W) % H);
-        const float d = __ldg(dL + i);
-        bsum += d;
+    // a group = 32 consecutive pixels of one image row (32-bit index arithmetic: the 64-bit div/mod per pixel of the
+    // first version cost more than the loads); two groups in flight per warp
+    const int gpr = (W + 31) >> 5;
+    const int groups = N * H * gpr;
+    auto one = [&](int g, float& d, uint4& a0, uint4& a1) -> bool {
+        d = 0.f;
+        a0 = a1 = make_uint4(0, 0, 0, 0);
+        if (g >= groups) return false;
+        const int row = g / gpr, x = (g - row * gpr) * 32 + lane;
+        if (x >= W) return false;
+        const int y = row % H;
+        const long long i = (long long)row * W + x;
+        d = __ldg(dL + i);
         const int yy = y + r - 1, xx = x + s - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) return true;
         const uint4* ap = reinterpret_cast<const uint4*>(A + (i + (long long)(r - 1) * W + (s - 1)) * 16);
+        a0 = __ldg(ap);
+        a1 = __ldg(ap + 1);
+        return true;
+    };
+    for (int g = blockIdx.x; g < groups; g += 2 * gridDim.x) {
+        float d0, d1;
+        uint4 p0, p1, q0, q1;
+        one(g, d0, p0, p1);
+        one(g + gridDim.x, d1, q0, q1);
+        bsum += d0 + d1;
         float v[8];
-        unpack8(__ldg(ap), v);
+        unpack8(p0, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k] * d;
-        unpack8(__ldg(ap + 1), v);
+        for (int k = 0; k < 8; ++k) acc[k] += v[k] * d0;
+        unpack8(p1, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[8 + k] += v[k] * d;
+        for (int k = 0; k < 8; ++k) acc[8 + k] += v[k] * d0;
+        unpack8(q0, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k] * d1;
+        unpack8(q1, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[8 + k] += v[k] * d1;
     }
     float* out = partial + (size_t)blockIdx.x * 145;
 #pragma unroll

@@ -52,6 +52,7 @@ struct EpilogueDesc {
     const float* shift = nullptr;
     int relu = 0;
     View4 residual;          // ptr == nullptr: none
+    bool residual_f32 = false;  // residual.ptr addresses fp32 elements (wconv only: the training forward's partial)
     float* stats = nullptr;  // [m_tiles][cout][2]
 };
 
@@ -541,7 +542,8 @@ inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const v
     P.cin = cin; P.cout = cout;
     P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
     P.out = reinterpret_cast<__nv_bfloat16*>(out);
-    P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.residual = ep.residual_f32 ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.residual32 = ep.residual_f32 ? reinterpret_cast<const float*>(ep.residual.ptr) : nullptr;
     P.stats = ep.stats;
     P.err = err;
     int bst = 9;   // multiple of 3: the producer waits once per group of 3 weight tiles
@@ -572,11 +574,14 @@ inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const v
 inline cudaError_t wconv_launch(const WconvLaunch& L, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(wconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(wconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    launch_k(wconv_kernel, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
+    if (L.p.residual32) launch_k(wconv_kernel<true>, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
+    else launch_k(wconv_kernel<false>, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
     return cudaGetLastError();
 }
 
@@ -675,7 +680,8 @@ inline bool wpconv_ok(int cup, int cout) { return cup >= 64 && cup % 64 == 0 && 
 // out[N, 2Hl, 2Wl, cout] = scale * conv3x3(nearest2x(low[N,Hl,Wl,cup])) by parity folding.  wpk_dec1 = the PK_DEC1 matrix
 // [4 parities][cout][kt], kt = 9*cskip + 4*cup (low taps start at column koff = 9*cskip).
 inline std::string wpconv_build(WpconvLaunch& L, const void* low, int cup, const void* wpk_dec1, int kt, int koff, int cout,
-                                int N, int Hl, int Wl, void* out, const float* scale, int* err, int num_sms) {
+                                int N, int Hl, int Wl, void* out, const float* scale, int* err, int num_sms,
+                                bool out_f32 = false) {
     memset(&L.p, 0, sizeof(L.p));
     WpconvParams& P = L.p;
     if (!wpconv_ok(cup, cout)) return "wpconv: unsupported channel configuration";
@@ -685,7 +691,8 @@ inline std::string wpconv_build(WpconvLaunch& L, const void* low, int cup, const
     P.n_tiles = cout / 64;
     P.cup = cup; P.cout = cout; P.koff = koff;
     P.scale = scale;
-    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.out = out_f32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(out);
+    P.out32 = out_f32 ? reinterpret_cast<float*>(out) : nullptr;
     P.err = err;
     int bst = 16;  // multiple of 4: the producer waits once per group of 4 weight tiles
     while (bst > 4 && wpconv_smem(bst).total + 1024 > 232448u) bst -= 4;
@@ -715,11 +722,14 @@ inline std::string wpconv_build(WpconvLaunch& L, const void* low, int cup, const
 inline cudaError_t wpconv_launch(const WpconvLaunch& L, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wpconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        cudaError_t e = cudaFuncSetAttribute(wpconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(wpconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    launch_k(wpconv_kernel, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
+    if (L.p.out32) launch_k(wpconv_kernel<true>, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
+    else launch_k(wpconv_kernel<false>, L.grid, kWcThreads, L.smem, st, L.a, L.b, L.p);
     return cudaGetLastError();
 }
 

@@ -424,16 +424,20 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const u
 
 // ------------------------------------------------------------------------------------------------ seg head backward
 // dA[n,h,w,c] = sum_{r,s} dL[n, h+1-r, w+1-s] * w[c][r][s]   (bf16 out, 16 channels per pixel)
-__global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
-                                     __nv_bfloat16* __restrict__ dA, int N, int H, int W) {
+__global__ void __launch_bounds__(256)
+head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
+                     __nv_bfloat16* __restrict__ dA, int N, int H, int W) {
     griddep_launch();
     griddep_wait();
-    __shared__ float sw[144];
-    if (threadIdx.x < 144) sw[threadIdx.x] = w[threadIdx.x];  // [c][r][s]
-    __syncthreads();
+    // thread = (pixel, 8-channel half): its 72 weights live in registers for the whole grid-stride loop (the first
+    // version read 144 weights per pixel from shared memory: LDS-bound)
+    const int half = threadIdx.x & 1;
+    float wr[72];
+#pragma unroll
+    for (int k = 0; k < 72; ++k) wr[k] = __ldg(w + half * 72 + k);   // [c][r][s], c = half*8 + k/9
     const long long total = (long long)N * H * W;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 1; i < total;
+         i += ((long long)gridDim.x * blockDim.x) >> 1) {
         const unsigned ui = (unsigned)i, row = ui / (unsigned)W;   // N*H*W < 2^32 (checked by the host): 32-bit div/mod
         const int x = int(ui - row * (unsigned)W);
         const int y = int(row % (unsigned)H);
@@ -446,22 +450,15 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dL, const float* 
                 const int yy = y + 1 - r, xx = x + 1 - s;
                 d[r * 3 + s] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dL + nb + (long long)yy * W + xx) : 0.f;
             }
-        float o[16];
+        float o[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 8; ++c) {
             float a = 0.f;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) a += d[k] * sw[c * 9 + k];
+            for (int k = 0; k < 9; ++k) a += d[k] * wr[c * 9 + k];
             o[c] = a;
         }
-        float lo[8], hi[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            lo[k] = o[k];
-            hi[k] = o[8 + k];
-        }
-        reinterpret_cast<uint4*>(dA)[i * 2] = pack8(lo);
-        reinterpret_cast<uint4*>(dA)[i * 2 + 1] = pack8(hi);
+        reinterpret_cast<uint4*>(dA)[i * 2 + half] = pack8(o);
     }
 }
 

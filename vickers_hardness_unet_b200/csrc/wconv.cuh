@@ -36,6 +36,7 @@ struct WconvParams {
     int relu;
     __nv_bfloat16* out;                // [N, H, W, cout]
     const __nv_bfloat16* residual;     // dense, same shape, or nullptr
+    const float* residual32;           // fp32 residual (kRes32 instantiation: the training forward's up-sampled partial)
     float* stats;                      // [gridDim.x][cout][2] or nullptr
     int* err;
 };
@@ -54,6 +55,7 @@ __host__ __device__ inline WconvSmem wconv_smem(int bstages) {
     return s;
 }
 
+template <bool kRes32>
 __global__ void __launch_bounds__(kWcThreads, 1)
 wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ WconvParams P) {
@@ -246,7 +248,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int half = 0; half < 2; ++half) {   // 2 x 32 channels
                 uint32_t r[32];
                 uint4 rv[4];
-                if (P.residual && valid) {
+                if (!kRes32 && P.residual && valid) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         rv[j] = __ldg(reinterpret_cast<const uint4*>(P.residual + off + half * 32) + j);
@@ -274,7 +276,14 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     v[5] = __uint_as_float(r[j * 8 + 5]) * sc1.y + sh1.y;
                     v[6] = __uint_as_float(r[j * 8 + 6]) * sc1.z + sh1.z;
                     v[7] = __uint_as_float(r[j * 8 + 7]) * sc1.w + sh1.w;
-                    if (P.residual && valid) {
+                    if (kRes32) {
+                        if (valid) {
+                            const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.residual32 + off + half * 32 + j * 8));
+                            const float4 r1 = __ldg(reinterpret_cast<const float4*>(P.residual32 + off + half * 32 + j * 8) + 1);
+                            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                        }
+                    } else if (P.residual && valid) {
                         v[0] += bf16_lo(rv[j].x); v[1] += bf16_hi(rv[j].x);
                         v[2] += bf16_lo(rv[j].y); v[3] += bf16_hi(rv[j].y);
                         v[4] += bf16_lo(rv[j].z); v[5] += bf16_hi(rv[j].z);
@@ -346,6 +355,7 @@ struct WpconvParams {
     int bstages;
     const float* scale;                // [cout] or nullptr
     __nv_bfloat16* out;
+    float* out32;                      // kOut32 instantiation: fp32 partial for the training forward
     int* err;
 };
 constexpr uint32_t kWpBStage = 64 * 128;   // 8 KB
@@ -363,6 +373,7 @@ __host__ __device__ inline WpconvSmem wpconv_smem(int bstages) {
     return s;
 }
 
+template <bool kOut32>
 __global__ void __launch_bounds__(kWcThreads, 1)
 wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ WpconvParams P) {
@@ -539,7 +550,8 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             for (int s = 0; s < 2; ++s) {
                 const int lh = th * 16 + hl, lw = tw * 16 + s * 8 + wl;
                 const bool valid = lh < P.Hl && lw < P.Wl;
-                __nv_bfloat16* op = P.out + (((size_t)tn * Ho + 2 * lh + ph) * Wo + 2 * lw + pw) * P.cout + nt * 64;
+                const size_t ooff = (((size_t)tn * Ho + 2 * lh + ph) * Wo + 2 * lw + pw) * P.cout + nt * 64;
+                __nv_bfloat16* op = P.out + ooff;
                 const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + (par * 2 + s) * 64;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -556,6 +568,16 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         const int c = nt * 64 + half * 32 + j * 8;
                         const float4 sc0 = *reinterpret_cast<const float4*>(ss + c);
                         const float4 sc1 = *reinterpret_cast<const float4*>(ss + c + 4);
+                        if (kOut32) {
+                            if (valid) {
+                                float4* o32 = reinterpret_cast<float4*>(P.out32 + ooff + half * 32 + j * 8);
+                                o32[0] = make_float4(__uint_as_float(r[j * 8 + 0]) * sc0.x, __uint_as_float(r[j * 8 + 1]) * sc0.y,
+                                                     __uint_as_float(r[j * 8 + 2]) * sc0.z, __uint_as_float(r[j * 8 + 3]) * sc0.w);
+                                o32[1] = make_float4(__uint_as_float(r[j * 8 + 4]) * sc1.x, __uint_as_float(r[j * 8 + 5]) * sc1.y,
+                                                     __uint_as_float(r[j * 8 + 6]) * sc1.z, __uint_as_float(r[j * 8 + 7]) * sc1.w);
+                            }
+                            continue;
+                        }
                         uint4 o;
                         o.x = pack_bf16(__uint_as_float(r[j * 8 + 0]) * sc0.x, __uint_as_float(r[j * 8 + 1]) * sc0.y);
                         o.y = pack_bf16(__uint_as_float(r[j * 8 + 2]) * sc0.z, __uint_as_float(r[j * 8 + 3]) * sc0.w);

@@ -324,9 +324,22 @@ inline bool tconv_ok(int cin, int cout, bool parity) {
 }
 inline long long tconv_w_elems(int cin, int cout, bool parity) { return (parity ? 16ll : 9ll) * cin * cout; }
 
+// Inference plans set this while they build: weights / folded BN constants are never written by a kernel of the
+// inference stream, so tconv may copy them to shared memory BEFORE griddepcontrol.wait (PDL prologue overlap).  Training
+// re-packs weights every step in the same stream and keeps the wait first.
+inline bool& tconv_const_weights_flag() {
+    static thread_local bool f = false;
+    return f;
+}
+struct TconvConstWeightsScope {
+    bool prev;
+    TconvConstWeightsScope() : prev(tconv_const_weights_flag()) { tconv_const_weights_flag() = !getenv("UNETB200_NO_WPREFETCH"); }
+    ~TconvConstWeightsScope() { tconv_const_weights_flag() = prev; }
+};
 inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool parity, const void* wpk, int cout, int N,
                                int H, int W, void* out, const EpilogueDesc& ep, int* err, int num_sms) {
     memset(&L.p, 0, sizeof(L.p));
+    if (tconv_const_weights_flag()) L.p.dbg |= 16;
     TconvParams& P = L.p;
     if (!tconv_ok(cin, cout, parity)) return "tconv: unsupported channel configuration";
     if (parity && ((H | W) & 1)) return "tconv: parity mode needs even H, W";
@@ -419,6 +432,7 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
 inline std::string tconv_build_stem(TconvLaunch& L, const void* xp, const void* wpk, int N, int H, int W, void* out,
                                     const EpilogueDesc& ep, int* err, int num_sms) {
     memset(&L.p, 0, sizeof(L.p));
+    if (tconv_const_weights_flag()) L.p.dbg |= 16;
     TconvParams& P = L.p;
     if ((H | W) & 1) return "tconv stem: H and W must be even";
     if (ep.residual.ptr) return "tconv stem: no residual";

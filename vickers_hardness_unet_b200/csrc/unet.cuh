@@ -380,6 +380,9 @@ inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers,
     }
     if (!ctx->weights_event) UB_CUDA(cudaEventCreateWithFlags(&ctx->weights_event, cudaEventDisableTiming));
     UB_CUDA(cudaEventRecord(ctx->weights_event, st));
+    // inference kernels read the packed weights / folded constants BEFORE griddepcontrol.wait (see tconv.cuh): the packs
+    // must have completed before any of them can be launched.  Weight loads are rare (once per checkpoint / validation).
+    if (fold_bn) UB_CUDA(cudaStreamSynchronize(st));
     ctx->weights_ready = true;
     return 0;
 }
@@ -500,6 +503,7 @@ struct ArenaCarver {
 
 // Builds (or sizes, when ctx->arena == nullptr) the launch list for batch N.  Returns "" on success.
 inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_t* arena_needed) {
+    TconvConstWeightsScope const_weights_scope;
     const NetSpec& S = ctx->spec;
     const int H = ctx->H, W = ctx->W;
     ArenaCarver A(ctx->arena, ctx->arena_bytes);

@@ -544,6 +544,7 @@ inline bool wconv_ok(int cin, int cout) { return cin >= 64 && cin % 64 == 0 && c
 inline std::string wconv_build(WconvLaunch& L, const void* src, int cin, const void* wpk, int cout, int N, int H, int W,
                                void* out, const EpilogueDesc& ep, int* err, int num_sms, long long ldb = 0) {
     memset(&L.p, 0, sizeof(L.p));
+    L.p.const_w = tconv_const_weights_flag() ? 1 : 0;
     WconvParams& P = L.p;
     if (!wconv_ok(cin, cout)) return "wconv: unsupported channel configuration";
     if (ep.residual.ptr && (ep.residual.sW != cout || ep.residual.sH != (long long)W * cout ||

@@ -31,6 +31,7 @@ struct WconvParams {
     int tiles_w, tiles_h, n_tiles;     // 16 x 16 output tiles per image; cout / 128
     int cin, cout;
     int bstages;
+    int const_w;                       // inference: weights are constants of the stream -> first tiles fetched before the PDL wait
     const float* scale;                // [cout] or nullptr
     const float* shift;
     int relu;
@@ -78,6 +79,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int tiles_img = P.tiles_w * P.tiles_h;
     const int total_items = tiles_img * P.N * P.n_tiles;
     const int chunks = P.cin >> 6;
+    const int n_pre = P.const_w ? (P.bstages < 9 ? P.bstages : 9) : 0;   // weight tiles issued before the PDL wait
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
@@ -93,12 +95,21 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(bempty(s), 1);
         }
         fence_mbar_init();
+        // PDL prologue: the first weight tiles of this CTA's first item (taps 0.. of chunk 0) do not depend on the
+        // previous kernel when the weights are constants of the stream (inference)
+        if (P.const_w && (int)blockIdx.x < total_items) {
+            const int nt0 = blockIdx.x % P.n_tiles;
+            for (int t = 0; t < n_pre; ++t) {
+                mbar_expect_tx(bfull(t), kWcBStage);
+                tma_load_2d(base + L.b_off + t * kWcBStage, &tmB, bfull(t), t * P.cin, nt0 * kWcN);
+            }
+        }
     }
     if (warp == 1) {
         tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
         tmem_relinquish();
     }
-    griddep_wait();   // PDL: nothing above touches global memory
+    griddep_wait();   // PDL: nothing above touches global memory that a kernel of this stream writes
     {
         float* ss = reinterpret_cast<float*>(sm + L.ss_off);
         float* cst = reinterpret_cast<float*>(sm + L.cstat_off);
@@ -126,7 +137,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0) {
         // ================================================================= TMA producer (one thread)
         if (lane == 0) {
-            int hs = 0, bs = 0;
+            int hs = 0, bs = 0, pre = n_pre;
             uint32_t hph = 0, bph = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 int nt, tw, th, tn;
@@ -151,8 +162,12 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             atomicExch(P.err, 42);
                             goto done;
                         }
-                        mbar_expect_tx(bfull(bs), kWcBStage);
-                        tma_load_2d(base + L.b_off + bs * kWcBStage, &tmB, bfull(bs), tap * P.cin + c * 64, nt * kWcN);
+                        if (pre > 0) {
+                            --pre;   // issued in the prologue
+                        } else {
+                            mbar_expect_tx(bfull(bs), kWcBStage);
+                            tma_load_2d(base + L.b_off + bs * kWcBStage, &tmB, bfull(bs), tap * P.cin + c * 64, nt * kWcN);
+                        }
                         if (++bs == P.bstages) {
                             bs = 0;
                             bph ^= 1;

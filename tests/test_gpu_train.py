@@ -240,3 +240,20 @@ def test_device_metrics_equal_reference_formulas():
         assert abs(float(got[k]) - want[k]) <= 1e-6 and abs(float(got_l[k]) - want[k]) <= 1e-6, (got, got_l, want)
     assert abs(vb.metrics.dice_coef(prob.cuda(), target.cuda()) - want[0]) <= 1e-6
     assert abs(vb.metrics.iou_coef(prob.cuda(), target.cuda()) - want[1]) <= 1e-6
+
+
+def test_device_prefetcher_yields_every_batch_once_in_order():
+    """vb.data.DevicePrefetcher (side-stream upload of batch k+1 under step k) must hand over exactly the loader's
+    batches, also when a slot is reused while the consumer is still reading the other one."""
+    g = torch.Generator().manual_seed(5)
+    host = [(torch.randn(2, 3, 64, 64, generator=g).pin_memory(), torch.rand(2, 1, 64, 64, generator=g).pin_memory())
+            for _ in range(7)]
+    seen = []
+    for x, y in vb.data.DevicePrefetcher(iter(host), "cuda"):
+        assert x.is_cuda and y.is_cuda
+        seen.append((x.clone(), y.clone()))      # consumer work on the compute stream
+        torch.cuda._sleep(2_000_000)             # keep the compute stream busy while the next upload runs
+    assert len(seen) == len(host)
+    for (x, y), (hx, hy) in zip(seen, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
+    assert list(vb.data.DevicePrefetcher(iter([]), "cuda")) == []

@@ -7,6 +7,7 @@ from .unet import Unet  # noqa: F401
 from . import losses  # noqa: F401
 from . import distributed  # noqa: F401
 from . import metrics  # noqa: F401
+from . import data  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 
-__all__ = ["Unet", "losses", "distributed", "metrics", "FusedAdamW", "UnetB200Error"]
+__all__ = ["Unet", "losses", "distributed", "metrics", "data", "FusedAdamW", "UnetB200Error"]

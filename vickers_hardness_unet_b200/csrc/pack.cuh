@@ -19,27 +19,36 @@ struct PackEntry {
     long long src_off;        // element offset into the flat fp32 parameter array
     long long dst_off;        // element offset into the bf16 destination arena
     long long total;          // logical elements of this entry
-    int block_begin;          // first block (2048 elements per block) of this entry in the launch
+    int block_begin;          // first block of this entry in the launch
     int pad;
+    // iteration order (set by PackTable::add): a thread owns `jper` columns j and loops over the entry's `nloop` filter
+    // taps, logical element i = (j / tap_stride) * tap_stride * nloop + j % tap_stride + t * tap_stride.  All taps of
+    // one (co, ci) pair are 36 contiguous source bytes: read by ONE thread they hit L1 after the first load (the
+    // element-per-thread order pulled every 32-byte sector of the fp32 weights nine times through L2).
+    int nloop, jper;
+    long long tap_stride;
 };
 
 // value of logical element i of entry E and the destination index (relative to E.dst_off) it is stored at
-__device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __restrict__ w, long long i, long long& dst) {
+// IdxT = int for every entry of this network (largest: 512*512*9 elements): 64-bit div/mod per element made the pack
+// kernels instruction-bound.
+template <typename IdxT>
+__device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __restrict__ w, IdxT i, IdxT& dst) {
     dst = i;
     switch (E.type) {
         case PK_CONV: {  // a = R, b = S, c = flip: [co][(r*S+s)*cin + ci]   (flip: [ci][((R-1-r)*S + (S-1-s))*cout + co])
             const int R = E.a, S = E.b;
             if (!E.c) {
                 const int ci = int(i % E.cin);
-                const long long t = i / E.cin;
+                const IdxT t = i / E.cin;
                 const int rs = int(t % (R * S)), co = int(t / (R * S));
-                return w[((long long)co * E.cin + ci) * R * S + rs];
+                return w[((IdxT)co * E.cin + ci) * R * S + rs];
             }
             const int co = int(i % E.cout);
-            const long long t = i / E.cout;
+            const IdxT t = i / E.cout;
             const int rs = int(t % (R * S)), ci = int(t / (R * S));
             const int r = R - 1 - rs / S, s = S - 1 - rs % S;
-            return w[(((long long)co * E.cin + ci) * R + r) * S + s];
+            return w[(((IdxT)co * E.cin + ci) * R + r) * S + s];
         }
         case PK_STEM: {  // [64][r*32 + px*4 + ch], px 0..7 <-> kernel column px-1 (px 0 and ch 3 are zero)
             const int ch = int(i % 4), px = int((i / 4) % 8), r = int((i / 32) % 7), co = int(i / 224);
@@ -47,36 +56,36 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
         }
         case PK_DEC1: {  // cin = cup, a = cskip: out[parity][cout][9*cskip + 4*cup] (parity-folded 2x2 taps on the low-res x)
             const int cup = E.cin, cskip = E.a, kt = 9 * cskip + 4 * cup, cint = cup + cskip;
-            const int k = int(i % kt), co = int((i / kt) % E.cout), par = int(i / ((long long)kt * E.cout));
+            const int k = int(i % kt), co = int((i / kt) % E.cout), par = int(i / ((IdxT)kt * E.cout));
             const int ph = par >> 1, pw = par & 1;
             if (k < 9 * cskip) {
                 const int c = k % cskip, rs = k / cskip;
-                return w[((long long)co * cint + cup + c) * 9 + rs];
+                return w[((IdxT)co * cint + cup + c) * 9 + rs];
             }
             const int kk = k - 9 * cskip, c = kk % cup, ab = kk / cup, aa = ab >> 1, bb = ab & 1;
             const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
             const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
             float v = 0.f;
             for (int r = r0; r <= r1; ++r)
-                for (int s = s0; s <= s1; ++s) v += w[((long long)co * cint + c) * 9 + r * 3 + s];
+                for (int s = s0; s <= s1; ++s) v += w[((IdxT)co * cint + c) * 9 + r * 3 + s];
             return v;
         }
         case PK_DLOW: {  // cin = cup, a = cin_total: out[c][t*cout + co], t = ((ph*2 + a)*2 + pw)*2 + b
-            const int co = int(i % E.cout), t = int((i / E.cout) % 16), c = int(i / ((long long)E.cout * 16));
+            const int co = int(i % E.cout), t = int((i / E.cout) % 16), c = int(i / ((IdxT)E.cout * 16));
             const int bb = t & 1, pw = (t >> 1) & 1, aa = (t >> 2) & 1, ph = (t >> 3) & 1;
             const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
             const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
             float v = 0.f;
             for (int r = r0; r <= r1; ++r)
-                for (int s = s0; s <= s1; ++s) v += w[((long long)co * E.a + c) * 9 + r * 3 + s];
+                for (int s = s0; s <= s1; ++s) v += w[((IdxT)co * E.a + c) * 9 + r * 3 + s];
             return v;
         }
         case PK_TAPS: {  // a = cin_total, b = ci0, c = (R << 8) | S, d = (ld << 0); pad = col0:  out[ci][col0 + t*cout + co]
-            const int co = int(i % E.cout), t = int((i / E.cout) % E.ntaps), ci = int(i / ((long long)E.cout * E.ntaps));
+            const int co = int(i % E.cout), t = int((i / E.cout) % E.ntaps), ci = int(i / ((IdxT)E.cout * E.ntaps));
             const int R = E.c >> 8, S = E.c & 0xFF;
             const int rs = int((E.taps >> (4 * t)) & 0xF), r = rs >> 2, s = rs & 3;
-            dst = (long long)ci * E.d + E.pad + t * E.cout + co;
-            return w[(((long long)co * E.a + E.b + ci) * R + r) * S + s];
+            dst = (IdxT)ci * E.d + E.pad + t * E.cout + co;
+            return w[(((IdxT)co * E.a + E.b + ci) * R + r) * S + s];
         }
         case PK_STEM2: {  // tconv stem operand: [K chunk j = r*4 + q][cout group g][co % 8][8 elements], element e of chunk
             // (r, q) = input pixel px = 2q + e/4 (kernel column px - 1; px 0 is padding), channel e % 4 (3 is padding)
@@ -101,7 +110,7 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int cup = E.cin;
             const unsigned row_bytes = cup * 2;
             const int c = int(i % cup);
-            long long t = i / cup;
+            IdxT t = i / cup;
             const int co = int(t % E.cout);
             t /= E.cout;
             const int ab = int(t % 4), par = int(t / 4);
@@ -110,7 +119,7 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
             float v = 0.f;
             for (int r = r0; r <= r1; ++r)
-                for (int s = s0; s <= s1; ++s) v += w[((long long)co * E.a + c) * 9 + r * 3 + s];
+                for (int s = s0; s <= s1; ++s) v += w[((IdxT)co * E.a + c) * 9 + r * 3 + s];
             const unsigned off = (unsigned)(i * 2);
             dst = (off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4)) / 2;
             return v;
@@ -119,15 +128,32 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int ctot = E.cin, cpr = ctot < 64 ? ctot : 64, nblk = ctot > 64 ? ctot / 64 : 1;
             const unsigned row_bytes = cpr * 2;
             const int cc = int(i % cpr);
-            long long t = i / cpr;
+            IdxT t = i / cpr;
             const int co = int(t % E.cout);
             t /= E.cout;
             const int blk = int(t % nblk), tap = int(t / nblk);
             const int c = blk * 64 + cc, r = tap / 3, s = tap - 3 * r;
             const unsigned off = (unsigned)(i * 2);
             dst = (off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4)) / 2;
-            if (!E.c) return w[(((long long)co * E.a + E.b + c) * 3 + r) * 3 + s];
-            return w[(((long long)c * E.a + E.b + co) * 3 + (2 - r)) * 3 + (2 - s)];
+            if (!E.c) return w[(((IdxT)co * E.a + E.b + c) * 3 + r) * 3 + s];
+            return w[(((IdxT)c * E.a + E.b + co) * 3 + (2 - r)) * 3 + (2 - s)];
+        }
+    }
+}
+
+template <typename IdxT>
+__device__ __forceinline__ void pack_entry_block(const PackEntry& E, const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+    const IdxT nloop = E.nloop, ts = (IdxT)E.tap_stride;
+    const IdxT jtotal = (IdxT)(E.total / E.nloop);
+    IdxT j = (IdxT)(blockIdx.x - E.block_begin) * (IdxT)(256 * E.jper) + (IdxT)threadIdx.x;
+    for (int it = 0; it < E.jper; ++it, j += 256) {
+        if (j >= jtotal) break;
+        const IdxT grp = j / ts;
+        const IdxT i0 = grp * ts * nloop + (j - grp * ts);
+        for (IdxT t = 0; t < nloop; ++t) {
+            IdxT d;
+            const float v = pack_elem<IdxT>(E, w, i0 + t * ts, d);
+            out[d] = __float2bfloat16(v);
         }
     }
 }
@@ -146,14 +172,8 @@ pack_table_kernel(const PackEntry* __restrict__ tab, int n, const float* __restr
     const PackEntry E = tab[lo];
     const float* w = params + E.src_off;
     __nv_bfloat16* out = dst_base + E.dst_off;
-    long long i = (long long)(blockIdx.x - E.block_begin) * 2048 + threadIdx.x;
-#pragma unroll
-    for (int it = 0; it < 8; ++it, i += 256) {
-        if (i >= E.total) break;
-        long long d;
-        const float v = pack_elem(E, w, i, d);
-        out[d] = __float2bfloat16(v);
-    }
+    if (E.total < (1ll << 30)) pack_entry_block<int>(E, w, out);
+    else pack_entry_block<long long>(E, w, out);
 }
 
 // host side: a table under construction, uploaded once (the layouts only depend on the network description)
@@ -163,7 +183,25 @@ struct PackTable {
     int nblocks = 0;
     void add(PackEntry e) {
         e.block_begin = nblocks;
-        nblocks += (int)((e.total + 2047) / 2048);
+        e.nloop = 1;
+        e.tap_stride = e.total > 0 ? e.total : 1;
+        if (e.type == PK_CONV && e.a * e.b > 1) {
+            e.nloop = e.a * e.b;
+            e.tap_stride = e.c ? e.cout : e.cin;
+        } else if (e.type == PK_HCONV) {
+            e.nloop = 9;
+            e.tap_stride = e.total / 9;
+        } else if (e.type == PK_TAPS && e.ntaps > 1) {
+            e.nloop = e.ntaps;
+            e.tap_stride = e.cout;
+        }
+        if (e.total % e.nloop) {   // not expected: fall back to one element per loop
+            e.nloop = 1;
+            e.tap_stride = e.total > 0 ? e.total : 1;
+        }
+        e.jper = e.nloop >= 8 ? 1 : 8 / e.nloop;
+        const long long jtotal = e.total / e.nloop, per_block = 256ll * e.jper;
+        nblocks += (int)((jtotal + per_block - 1) / per_block);
         host.push_back(e);
     }
     cudaError_t upload() {

@@ -574,15 +574,20 @@ loss_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, fl
         partial[blockIdx.x * 4 + threadIdx.x] = v;
     }
 }
-// result[0..2] = bce, dice, bce+dice ; result[3..5] = I, P, T (saved for backward); single thread
+// result[0..2] = bce, dice, bce+dice ; result[3..5] = I, P, T (saved for backward); one warp
 __global__ void loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double n, float eps,
                                      float* __restrict__ result) {
     griddep_launch();
     griddep_wait();
-    if (threadIdx.x || blockIdx.x) return;
+    if (blockIdx.x || threadIdx.x >= 32) return;   // one warp: lanes stride over the partial rows (fixed order: deterministic)
     double s[4] = {0, 0, 0, 0};
-    for (int b = 0; b < nblocks; ++b)
-        for (int k = 0; k < 4; ++k) s[k] += partial[b * 4 + k];
+    for (int b = threadIdx.x; b < nblocks; b += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + b * 4);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = warp_sum_d(s[k]);
+    if (threadIdx.x) return;
     const double card = s[2] + s[3];
     double dice = 1.0 - 2.0 * s[1] / (card > eps ? card : (double)eps);
     if (!(s[3] > 0)) dice = 0.0;

@@ -16,10 +16,10 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     const long long total = (long long)N * H * (Wp / 2);  // two pixels (16 B) per thread
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int wp2 = int(i % (Wp / 2));
-        const long long nh = i / (Wp / 2);
-        const int h = int(nh % H);
-        const int n = int(nh / H);
+        const unsigned u = (unsigned)i, nh = u / (unsigned)(Wp / 2);   // 32-bit index arithmetic
+        const int wp2 = int(u - nh * (unsigned)(Wp / 2));
+        const int n = int(nh / (unsigned)H);
+        const int h = int(nh - (unsigned)n * (unsigned)H);
         float v[2][3];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -212,12 +212,12 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
     const long long total = (long long)N * Ho * Wo * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int c8 = int(i % C8);
-        long long t = i / C8;
-        const int wo = int(t % Wo);
-        t /= Wo;
-        const int ho = int(t % Ho);
-        const int n = int(t / Ho);
+        // 32-bit index arithmetic (the host keeps element counts below 2^32): 64-bit div/mod per element is ~100 instructions
+        const unsigned u = (unsigned)i, t1 = u / (unsigned)C8, t2 = t1 / (unsigned)Wo;
+        const int c8 = int(u - t1 * (unsigned)C8);
+        const int wo = int(t1 - t2 * (unsigned)Wo);
+        const int n = int(t2 / (unsigned)Ho);
+        const int ho = int(t2 - (unsigned)n * (unsigned)Ho);
         uint4 m = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // -inf pairs
 #pragma unroll
         for (int r = 0; r < 3; ++r) {

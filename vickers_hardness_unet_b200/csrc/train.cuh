@@ -865,6 +865,13 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                                   ep, ctx->d_err, SM);
                 if (!err.empty()) return c1.name + " dskip: " + err;
                 add_b(0, "dgrad_skip:" + c1.name, [HL](cudaStream_t st) { return hconv_launch(HL, st); });
+            } else if (wconv_ok(d.cout, d.cskip)) {
+                // wide blocks: the PK_TAPS operand [cskip][9 * cout] (flipped taps) is the K-major matrix wconv streams
+                WconvLaunch WL;
+                err = wconv_build(WL, u1.dz, d.cout, T.wdg + T.wdg_off[d.c1], d.cskip, N, u1.Ho, u1.Wo, r.d_skip, ep,
+                                  ctx->d_err, SM);
+                if (!err.empty()) return c1.name + " dskip: " + err;
+                add_b(0, "dgrad_skip:" + c1.name, [WL](cudaStream_t st) { return wconv_launch(WL, st); });
             } else {
                 IgemmLaunch L;
                 err = build_conv(ctx, L, t, T.wdg + T.wdg_off[d.c1], u1.dz, N, u1.Ho, u1.Wo, r.d_skip, ep);

@@ -336,12 +336,12 @@ __global__ void maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ in, __
     const long long total = (long long)N * Ho * Wo * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int c8 = int(i % C8);
-        long long t = i / C8;
-        const int wo = int(t % Wo);
-        t /= Wo;
-        const int ho = int(t % Ho);
-        const int n = int(t / Ho);
+        // 32-bit index arithmetic (the host keeps element counts below 2^32): 64-bit div/mod per element is ~100 instructions
+        const unsigned u = (unsigned)i, t1 = u / (unsigned)C8, t2 = t1 / (unsigned)Wo;
+        const int c8 = int(u - t1 * (unsigned)C8);
+        const int wo = int(t1 - t2 * (unsigned)Wo);
+        const int n = int(t2 / (unsigned)Ho);
+        const int ho = int(t2 - (unsigned)n * (unsigned)Ho);
         float best[8];
         uint32_t bi[8];
 #pragma unroll
@@ -385,12 +385,11 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const u
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const int c8 = int(i % C8);
-        long long t = i / C8;
-        const int w = int(t % W);
-        t /= W;
-        const int h = int(t % H);
-        const int n = int(t / H);
+        const unsigned u = (unsigned)i, t1 = u / (unsigned)C8, t2 = t1 / (unsigned)W;   // 32-bit: see maxpool3x3s2_idx_kernel
+        const int c8 = int(u - t1 * (unsigned)C8);
+        const int w = int(t1 - t2 * (unsigned)W);
+        const int n = int(t2 / (unsigned)H);
+        const int h = int(t2 - (unsigned)n * (unsigned)H);
         float acc[8];
         if (dSkip) unpack8(__ldg(reinterpret_cast<const uint4*>(dSkip) + i), acc);
         else {

@@ -751,6 +751,10 @@ inline int ctx_create(Ctx** out, int device, int max_batch, int H, int W, std::s
         *err = "max_batch must be >= 1";
         return 1;
     }
+    if ((long long)max_batch * H * W >= (1ll << 31)) {   // the pool / pack / head kernels index elements with 32 bits
+        *err = "max_batch * H * W must be below 2^31";
+        return 1;
+    }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
         *err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);

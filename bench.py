@@ -384,6 +384,11 @@ def main():
                          "kernel": "conv stack = all ub::wconv_kernel / tconv_kernel / igemm_kernel launches of one step (algorithmic FLOPs)",
                          "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / prof["total_ms"],
                          "launches_per_step": prof["n_igemm"]})
+            from vickers_hardness_unet_b200.profile import infer_layer_work, layer_roofline
+            roof["per_layer"] = layer_roofline(prof["rows"], infer_layer_work(model, B, S, S),
+                                               pk["bf16_tflops_sustained"], pk["hbm_gbs"])
+            roof["per_layer"]["note"] = ("each conv launch bounded by max(FLOPs / measured bf16 peak, min HBM bytes / "
+                                         "measured copy bandwidth); CUDA-event time per launch")
             if a.profile_out:
                 with open(a.profile_out, "w") as f:
                     f.write(prof["table"])

@@ -1124,6 +1124,88 @@ static void bench_xwgrad_up(const char* name, int N, int H, int W, int cup, int 
     check_err_flag(name);
     cudaFree(d_low); cudaFree(d_dz); cudaFree(d_g);
 }
+// dlow: gradient of a decoder conv1 w.r.t. its low-resolution input.  Host builds the PK_DLOW operand V[ci][t*cz + co]
+// (3x3 weights pre-summed per high-res offset, rounded to bf16 like the device pack) and the reference
+// dLow[u, ci] = sum_t dZ[2u + (oh_t, ow_t), co] * V[ci][t][co].
+static void case_dlow(const char* name, int N, int Hl, int Wl, int cz, int cup, int iters = 0) {
+    const int H = 2 * Hl, W = 2 * Wl;
+    HostT dz(N, H, W, cz);
+    if (iters == 0) fill_rand_bf16(dz.v, 1.0f);
+    std::vector<float> w((size_t)cz * cup * 9);          // OIHW: [co = cz][ci = cup][3][3]
+    for (auto& x : w) x = frand() * 0.2f;
+    std::vector<float> V((size_t)cup * 16 * cz);
+    int oh_t[16], ow_t[16];
+    for (int t = 0; t < 16; ++t) {
+        const int bb = t & 1, pw = (t >> 1) & 1, aa = (t >> 2) & 1, ph = (t >> 3) & 1;
+        oh_t[t] = 2 - 2 * aa - ph;
+        ow_t[t] = 2 - 2 * bb - pw;
+        const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
+        const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
+        for (int c = 0; c < cup; ++c)
+            for (int co = 0; co < cz; ++co) {
+                float v = 0.f;
+                for (int r = r0; r <= r1; ++r)
+                    for (int q = s0; q <= s1; ++q) v += w[((size_t)co * cup + c) * 9 + r * 3 + q];
+                V[((size_t)c * 16 + t) * cz + co] = bf16r(v);
+            }
+    }
+    __nv_bfloat16* d_dz = to_dev_bf16(dz.v);
+    __nv_bfloat16* d_v = to_dev_bf16(V);
+    __nv_bfloat16* d_out;
+    const size_t nout = (size_t)N * Hl * Wl * cup;
+    CK(cudaMalloc(&d_out, nout * 2));
+    CK(cudaMemset(d_out, 0, nout * 2));
+    DlowLaunch L;
+    std::string e = dlow_build(L, d_dz, cz, d_v, cup, N, Hl, Wl, d_out, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    if (iters > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int i = 0; i < 2; ++i) CK(dlow_launch(L, 0));
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) CK(dlow_launch(L, 0));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= iters;
+        const double bytes = 2.0 * N * H * W * (double)cz + 2.0 * nout;
+        printf("[BENCH-DL] %-30s %8.1f us %6.2f TB/s  grid %d stages %d smem %u\n", name, ms * 1e3, bytes / ms * 1e-9,
+               L.grid, L.p.stages, L.smem);
+        check_err_flag(name);
+        cudaFree(d_dz); cudaFree(d_v); cudaFree(d_out);
+        return;
+    }
+    printf("       %s: grid %d smem %u stages %d\n", name, L.grid, L.smem, L.p.stages);
+    CK(dlow_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> ref(nout, 0.f);
+#pragma omp parallel for collapse(2)
+        for (int n = 0; n < N; ++n)
+            for (int h = 0; h < Hl; ++h)
+                for (int x = 0; x < Wl; ++x)
+                    for (int c = 0; c < cup; ++c) {
+                        double acc = 0;
+                        for (int t = 0; t < 16; ++t)
+                            for (int co = 0; co < cz; ++co)
+                                acc += (double)dz.get(n, 2 * h + oh_t[t], 2 * x + ow_t[t], co) * V[((size_t)c * 16 + t) * cz + co];
+                        ref[(((size_t)n * Hl + h) * Wl + x) * cup + c] = (float)acc;
+                    }
+        std::vector<__nv_bfloat16> hb(nout);
+        CK(cudaMemcpy(hb.data(), d_out, nout * 2, cudaMemcpyDeviceToHost));
+        std::vector<float> got(nout);
+        for (size_t i = 0; i < nout; ++i) got[i] = __bfloat162float(hb[i]);
+        report(name, compare(got, ref), 6e-3, got, ref, cup);
+    }
+    cudaFree(d_dz); cudaFree(d_v); cudaFree(d_out);
+}
 static void bench_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout, int iters) {
     const int ctot = cup + cskip;
     __nv_bfloat16 *d_low, *d_src, *d_dz;
@@ -1394,6 +1476,16 @@ int main(int argc, char** argv) {
         case_hwgrad("hwgrad up32->16 2x32x64", 2, 32, 64, 32, 0, 16);
         case_hwgrad("hwgrad up64+skip64->32 2x32x32 (4 groups)", 2, 32, 32, 64, 64, 32);
         case_hwgrad("hwgrad 64->64 5x64x64 (multi-tile/CTA)", 5, 64, 64, 0, 64, 64);
+    }
+    if (want("dlow")) {
+        case_dlow("dlow 16->32 2x16x16 (decoder.blocks.4 shape)", 2, 16, 16, 16, 32);
+        case_dlow("dlow 32->64 1x24x16 (partial tile rows)", 1, 24, 16, 32, 64);
+        case_dlow("dlow 16->32 3x32x40 (multi-tile)", 3, 32, 40, 16, 32);
+        case_dlow("dlow 32->64 2x8x8 (one small tile)", 2, 8, 8, 32, 64);
+    }
+    if (want("dlbench")) {
+        case_dlow("D4c1 dlow 16->32 @256^2 x16", 16, 256, 256, 16, 32, 5);
+        case_dlow("D3c1 dlow 32->64 @128^2 x16", 16, 128, 128, 32, 64, 10);
     }
     if (want("xwgrad")) {
         case_xwgrad("xwgrad 16->16 2x32x32", 2, 32, 32, 16, 16, 0);

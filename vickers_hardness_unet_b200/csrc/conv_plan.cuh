@@ -12,6 +12,7 @@
 #include "wconv.cuh"
 #include "wconv2.cuh"
 #include "xwgrad.cuh"
+#include "dlow.cuh"
 #include "tmap.cuh"
 
 namespace ub {
@@ -880,6 +881,68 @@ inline cudaError_t xwgrad_launch(const XwgradLaunch& L, cudaStream_t st) {
         attr_set = true;
     }
     launch_k(xwgrad_kernel, L.grid, kXwThreads, L.smem, st, L.z, L.x, L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ dlow (decoder conv1 -> low-res dgrad)
+struct DlowLaunch {
+    CUtensorMap z, w;
+    DlowParams p;
+    int grid = 0;
+    uint32_t smem = 0;
+};
+inline bool dlow_ok(int cz, int cup, int Hl, int Wl) {
+    if (getenv("UNETB200_NO_DLOW")) return false;
+    return (cz == 16 || cz == 32) && (cup == 32 || cup == 64) && Wl % kDlTileW == 0 && Hl >= 2 && Wl >= 8;
+}
+// dz: [N, 2*Hl, 2*Wl, cz]; wdl: PK_DLOW operand [cup][16 * cz] bf16; out: [N, Hl, Wl, cup]
+inline std::string dlow_build(DlowLaunch& L, const void* dz, int cz, const void* wdl, int cup, int N, int Hl, int Wl,
+                              void* out, int* err, int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    if (!dlow_ok(cz, cup, Hl, Wl)) return "dlow: unsupported configuration";
+    DlowParams& P = L.p;
+    P.Hl = Hl; P.Wl = Wl; P.N = N;
+    P.tiles_w = Wl / kDlTileW;
+    P.tiles_h = (Hl + kDlTileH - 1) / kDlTileH;
+    P.cz = cz; P.cup = cup;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out);
+    P.err = err;
+    if (const char* e = getenv("UNETB200_DLOW_DBG")) P.dbg = atoi(e);
+    int stages = 6;
+    for (; stages >= 2; --stages)
+        if (dlow_smem(cz, cup, stages).total + 1024 <= 232448u) break;
+    if (stages < 2) return "dlow: does not fit in shared memory";
+    P.stages = stages;
+    L.smem = dlow_smem(cz, cup, stages).total + 1024;
+    {
+        // pixel-pair view of the dense NHWC gradient: [2*cz, Wl pairs, 2*Hl rows, N]
+        uint64_t dims[4] = {2ull * cz, (uint64_t)Wl, 2ull * Hl, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cz * 4, 2ull * Wl * cz * 2, 4ull * Hl * Wl * cz * 2};
+        uint32_t box[4] = {2u * cz, (uint32_t)kDlBoxW, (uint32_t)kDlBoxH, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.z, dz, 4, dims, str, box, es, swizzle_for_bytes(cz * 4));
+        if (!e.empty()) return "dlow dZ map: " + e;
+    }
+    {
+        uint64_t dims[2] = {16ull * cz, (uint64_t)cup};
+        uint64_t str[1] = {16ull * cz * 2};
+        uint32_t box[2] = {(uint32_t)cz, (uint32_t)cup};
+        uint32_t es[2] = {1, 1};
+        std::string e = make_tmap_bf16(&L.w, wdl, 2, dims, str, box, es, swizzle_for_bytes(cz * 2));
+        if (!e.empty()) return "dlow weight map: " + e;
+    }
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    L.grid = total_tiles < num_sms ? total_tiles : num_sms;
+    return "";
+}
+inline cudaError_t dlow_launch(const DlowLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dlow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    launch_k(dlow_kernel, L.grid, kDlThreads, L.smem, st, L.z, L.w, L.p);
     return cudaGetLastError();
 }
 

@@ -882,6 +882,15 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         {
             // gradient w.r.t. the low-res input -> becomes d_cur of the previous decoder block / layer4 output
             __nv_bfloat16* d_low = (i > 0) ? dA[decs[i - 1].u2] : dA[blocks.back().u2];
+            if (dlow_ok(d.cout, d.cup, r.Hl, r.Wl)) {
+                // narrow blocks: four resident parity images of dZ, 16 shifted-descriptor taps (dlow.cuh)
+                DlowLaunch DL;
+                err = dlow_build(DL, u1.dz, d.cout, T.wdg + T.wdg_off2[d.c1], d.cup, N, r.Hl, r.Wl, d_low, ctx->d_err, SM);
+                if (!err.empty()) return c1.name + " dlow: " + err;
+                add_b(0, "dgrad_low:" + c1.name, [DL](cudaStream_t st) { return dlow_launch(DL, st); });
+                d_cur = d_low;
+                continue;
+            }
             SrcDesc s;
             s.v = nhwc_view(u1.dz, N, u1.Ho, u1.Wo, d.cout);
             s.es_w = s.es_h = 2;

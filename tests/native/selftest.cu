@@ -1206,6 +1206,78 @@ static void case_dlow(const char* name, int N, int Hl, int Wl, int cz, int cup, 
     }
     cudaFree(d_dz); cudaFree(d_v); cudaFree(d_out);
 }
+// swgrad: weight gradient of the 7x7/s2 stem from the packed image and dZ, vs a CPU reference (x rounded to bf16 as packed)
+static void case_swgrad(const char* name, int N, int H, int W, int iters = 0) {
+    const int Ho = H / 2, Wo = W / 2;
+    std::vector<float> x((size_t)N * 3 * H * W);
+    for (auto& v : x) v = bf16r(frand() * 2.f);
+    HostT dz(N, Ho, Wo, 64);
+    if (iters == 0) fill_rand_bf16(dz.v, 1.0f);
+    float* d_x = to_dev_f32(x);
+    __nv_bfloat16* d_xp;
+    CK(cudaMalloc(&d_xp, (size_t)N * H * (W + 8) * 4 * 2 + 128));
+    CK(cudaMemset(d_xp, 0, (size_t)N * H * (W + 8) * 4 * 2 + 128));
+    pack_input_kernel<<<ew_grid((long long)N * H * ((W + 8) / 2), 256, 148), 256>>>(d_x, d_xp, N, H, W);
+    __nv_bfloat16* d_dz = to_dev_bf16(dz.v);
+    float* d_g;
+    CK(cudaMalloc(&d_g, 64 * 147 * 4));
+    CK(cudaMemset(d_g, 0, 64 * 147 * 4));
+    SwgradLaunch L;
+    std::string e = swgrad_build(L, d_xp, d_dz, N, H, W, d_g, g_ctx->d_err, g_ctx->num_sms);
+    if (!e.empty()) {
+        printf("[FAIL] %s: %s\n", name, e.c_str());
+        g_fail++;
+        return;
+    }
+    if (iters > 0) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        for (int i = 0; i < 2; ++i) CK(swgrad_launch(L, 0));
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) CK(swgrad_launch(L, 0));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms /= iters;
+        const double bytes = 2.0 * N * Ho * Wo * 64.0 + 2.0 * N * H * (W + 8) * 4.0;
+        printf("[BENCH-SW] %-30s %8.1f us %6.2f TB/s  grid %d stages %d wt %d smem %u\n", name, ms * 1e3, bytes / ms * 1e-9,
+               L.grid, L.p.stages, L.p.wt, L.smem);
+        check_err_flag(name);
+        cudaFree(d_x); cudaFree(d_xp); cudaFree(d_dz); cudaFree(d_g);
+        return;
+    }
+    printf("       %s: grid %d smem %u stages %d wt %d\n", name, L.grid, L.smem, L.p.stages, L.p.wt);
+    CK(swgrad_launch(L, 0));
+    CK(cudaDeviceSynchronize());
+    if (!check_err_flag(name)) {
+        std::vector<float> ref((size_t)64 * 147, 0.f);
+#pragma omp parallel for collapse(2)
+        for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < 3; ++ci)
+                for (int r = 0; r < 7; ++r)
+                    for (int q = 0; q < 7; ++q) {
+                        double acc = 0;
+                        for (int n = 0; n < N; ++n)
+                            for (int ho = 0; ho < Ho; ++ho) {
+                                const int hi = 2 * ho + r - 3;
+                                if (hi < 0 || hi >= H) continue;
+                                for (int wo = 0; wo < Wo; ++wo) {
+                                    const int wi = 2 * wo + q - 3;
+                                    if (wi < 0 || wi >= W) continue;
+                                    acc += (double)dz.at(n, ho, wo, co) * x[(((size_t)n * 3 + ci) * H + hi) * W + wi];
+                                }
+                            }
+                        ref[(size_t)co * 147 + ci * 49 + r * 7 + q] = (float)acc;
+                    }
+        std::vector<float> got(ref.size());
+        CK(cudaMemcpy(got.data(), d_g, got.size() * 4, cudaMemcpyDeviceToHost));
+        report(name, compare(got, ref), 2e-3, got, ref, 147);
+    }
+    cudaFree(d_x); cudaFree(d_xp); cudaFree(d_dz); cudaFree(d_g);
+}
 static void bench_hwgrad(const char* name, int N, int H, int W, int cup, int cskip, int cout, int iters) {
     const int ctot = cup + cskip;
     __nv_bfloat16 *d_low, *d_src, *d_dz;
@@ -1477,6 +1549,12 @@ int main(int argc, char** argv) {
         case_hwgrad("hwgrad up64+skip64->32 2x32x32 (4 groups)", 2, 32, 32, 64, 64, 32);
         case_hwgrad("hwgrad 64->64 5x64x64 (multi-tile/CTA)", 5, 64, 64, 0, 64, 64);
     }
+    if (want("swgrad")) {
+        case_swgrad("swgrad 2x64x128 (wt 64)", 2, 64, 128);
+        case_swgrad("swgrad 1x32x96 (wt 16)", 1, 32, 96);
+        case_swgrad("swgrad 3x96x64 (wt 32, several row tiles)", 3, 96, 64);
+    }
+    if (want("swbench")) case_swgrad("stem wgrad @512^2 x16", 16, 512, 512, 5);
     if (want("dlow")) {
         case_dlow("dlow 16->32 2x16x16 (decoder.blocks.4 shape)", 2, 16, 16, 16, 32);
         case_dlow("dlow 32->64 1x24x16 (partial tile rows)", 1, 24, 16, 32, 64);

@@ -21,6 +21,7 @@ GROUPS = {
     "split": "wide decoder conv1 as wpconv + wconv with residual",
     "pair": "CTA-pair (cta_group::2) wide conv (wconv2)",
     "hwgrad": "halo-resident weight gradient",
+    "swgrad": "7x7/s2 stem weight gradient (input-row anchors, two dZ rows per MMA)",
     "dlow": "decoder conv1 data gradient w.r.t. the low-resolution input (parity images + 16 shifted taps)",
     "xwgrad": "TMA-fed halo weight gradient (all nine taps per pass; narrow and wide modes)",
 }

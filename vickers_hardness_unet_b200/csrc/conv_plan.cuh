@@ -13,6 +13,7 @@
 #include "wconv2.cuh"
 #include "xwgrad.cuh"
 #include "dlow.cuh"
+#include "swgrad.cuh"
 #include "tmap.cuh"
 
 namespace ub {
@@ -943,6 +944,65 @@ inline cudaError_t dlow_launch(const DlowLaunch& L, cudaStream_t st) {
         attr_set = true;
     }
     launch_k(dlow_kernel, L.grid, kDlThreads, L.smem, st, L.z, L.w, L.p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ swgrad (stem weight gradient)
+struct SwgradLaunch {
+    CUtensorMap z, x;
+    SwgradParams p;
+    int grid = 0;
+    uint32_t smem = 0;
+};
+inline bool swgrad_ok(int H, int W) { return !getenv("UNETB200_NO_SWGRAD") && H % 16 == 0 && W % 32 == 0 && H >= 16 && W >= 32; }
+// xp: packed image [N][H][W+8][4] bf16; dz: [N, H/2, W/2, 64]; grad: OIHW fp32 [64][3][7][7] (accumulated)
+inline std::string swgrad_build(SwgradLaunch& L, const void* xp, const void* dz, int N, int H, int W, float* grad, int* err,
+                                int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    if (!swgrad_ok(H, W)) return "swgrad: unsupported extent";
+    SwgradParams& P = L.p;
+    P.Ho = H / 2; P.Wo = W / 2; P.N = N;
+    P.wt = P.Wo % 64 == 0 ? 64 : (P.Wo % 32 == 0 ? 32 : 16);
+    P.tiles_w = P.Wo / P.wt;
+    P.tiles_q = (P.Ho + kSwTQ - 1) / kSwTQ;
+    P.grad = grad;
+    P.err = err;
+    int stages = 4;
+    for (; stages >= 2; --stages)
+        if (swgrad_smem(P.wt, stages).total + 1024 <= 232448u) break;
+    if (stages < 2) return "swgrad: does not fit in shared memory";
+    P.stages = stages;
+    L.smem = swgrad_smem(P.wt, stages).total + 1024;
+    {
+        uint64_t dims[4] = {64, (uint64_t)P.Wo, (uint64_t)P.Ho, (uint64_t)N};
+        uint64_t str[3] = {128, (uint64_t)P.Wo * 128, (uint64_t)P.Ho * P.Wo * 128};
+        uint32_t box[4] = {64, (uint32_t)P.wt, (uint32_t)(kSwTQ + 3), 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.z, dz, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (!e.empty()) return "swgrad dZ map: " + e;
+    }
+    {
+        // window view: "pixel" wo of an input row = 32 elements (8 input pixels x 4 channels) from padded column 2*wo
+        const uint64_t Wp = (uint64_t)W + 8;
+        uint64_t dims[4] = {32, (uint64_t)P.Wo, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {16, Wp * 8, (uint64_t)H * Wp * 8};
+        uint32_t box[4] = {32, (uint32_t)P.wt, (uint32_t)(2 * kSwTQ), 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.x, xp, 4, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (!e.empty()) return "swgrad X map: " + e;
+    }
+    const int total_tiles = P.tiles_w * P.tiles_q * N;
+    L.grid = total_tiles < num_sms ? total_tiles : num_sms;
+    return "";
+}
+inline cudaError_t swgrad_launch(const SwgradLaunch& L, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(swgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    launch_k(swgrad_kernel, L.grid, kSwThreads, L.smem, st, L.z, L.x, L.p);
     return cudaGetLastError();
 }
 

@@ -994,6 +994,13 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             return cudaGetLastError();
         });
         bn_bwd(3, u_stem, dF1, true, nullptr);
+        if (swgrad_ok(H, W)) {
+            // all seven filter rows from one pass over dZ (swgrad.cuh)
+            SwgradLaunch WL;
+            err = swgrad_build(WL, plan.xp, us.dz, N, H, W, grads + S.convs[S.stem].w, ctx->d_err, SM);
+            if (!err.empty()) return "encoder.conv1.weight wgrad: " + err;
+            add_b(3, "wgrad:encoder.conv1.weight", [WL](cudaStream_t st) { return swgrad_launch(WL, st); });
+        } else {
         WgSpec s;
         s.name = "encoder.conv1.weight";
         s.z = nhwc_view(us.dz, N, Hh, Wh, 64);
@@ -1007,6 +1014,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             s.taps.push_back(t);
         }
         if (!(err = add_wg(3, s)).empty()) return err;
+        }
     }
     // ---- upload wgrad work items and patch the launches
     plan.items_used = plan.host_items.size();

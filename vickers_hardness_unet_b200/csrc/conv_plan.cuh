@@ -324,7 +324,8 @@ inline bool tconv_ok(int cin, int cout, bool parity) {
     if (parity && cout > 32) return false;  // 4 accumulators x cout x >= 2 sets must fit the TMEM budget
     return true;
 }
-inline long long tconv_w_elems(int cin, int cout, bool parity) { return (parity ? 16ll : 9ll) * cin * cout; }
+// parity mode: 18 [cout][cin] blocks (tc_issue_parity: 9 halo shifts, runs of 4 + 2 + 2 + 3 + 3 + 1 + 1 + 1 + 1 parities)
+inline long long tconv_w_elems(int cin, int cout, bool parity) { return (parity ? 18ll : 9ll) * cin * cout; }
 
 // Inference plans set this while they build: weights / folded BN constants are never written by a kernel of the
 // inference stream, so tconv may copy them to shared memory BEFORE griddepcontrol.wait (PDL prologue overlap).  Training
@@ -378,7 +379,9 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     if (items > 8) return "tconv: too many accumulator column groups";
     const int acc_cols = nt * cout;
     // cout >= 32: whole sub-tiles leave through swizzled smem staging + TMA store (see TconvParams::stage_out)
-    const uint32_t out_bytes = (!parity && cout >= 32) ? (uint32_t)nt * 128u * cout * 2u : 0u;
+    // parity mode: the four parity sub-tiles interleave into one dense hi-res tile (A/B: UNETB200_NO_PARITY_STAGE=1)
+    static const bool par_stage = getenv("UNETB200_NO_PARITY_STAGE") == nullptr;
+    const uint32_t out_bytes = ((parity && par_stage) || (!parity && cout >= 32)) ? (uint32_t)nt * 128u * cout * 2u : 0u;
     L.occ = 1;
     int stages = 0;
     if (items <= 4 && 2 * acc_cols <= 256) {
@@ -398,7 +401,15 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     const int groups = tc_epi_warps(L.occ) / 4;
     L.iph = (items + groups - 1) / groups;
     const int cgs = cout / 16;
-    if (out_bytes && L.iph <= cgs && cgs % L.iph == 0 && items % groups == 0) {
+    if (out_bytes && parity && items % groups == 0) {
+        P.stage_out = 2;
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)W * cout * 2, (uint64_t)H * W * cout * 2};
+        uint32_t box[4] = {(uint32_t)cout, 16, 32, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.d, out, 4, dims, str, box, es, swizzle_for_bytes(cout * 2));
+        if (!e.empty()) return "tconv D map: " + e;
+    } else if (out_bytes && !parity && L.iph <= cgs && cgs % L.iph == 0 && items % groups == 0) {
         P.stage_out = 1;
         P.spw = (cgs / L.iph) * 128;
         uint64_t dims[4] = {(uint64_t)cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};

@@ -105,23 +105,32 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             return co == 0 ? hi : wv - hi;
         }
         case PK_HPAR: {  // tconv parity operand: cout = rows, cin = cup (<= 64), a = cin_total of the OIHW tensor.
-            // logical [parity][a*2+b][co][c] = sum of the 3x3 taps that land on low-res neighbour (a, b) for output
-            // parity (ph, pw) (same row/column sets as PK_DEC1), 16-byte chunks swizzled like PK_HCONV
+            // 18 blocks [blk][co][c] in the issue order of tc_issue_parity (tconv.cuh): block = (halo shift (r, s), output
+            // parity (ph, pw)); value = sum of the 3x3 taps that land on low-res neighbour (a, b) = (r - ph, s - pw) for
+            // that parity (same row/column sets as PK_DEC1), ZERO when (a, b) is not a neighbour (the filler blocks of
+            // the N = 3 runs); 16-byte chunks swizzled like PK_HCONV
             const int cup = E.cin;
             const unsigned row_bytes = cup * 2;
             const int c = int(i % cup);
             IdxT t = i / cup;
             const int co = int(t % E.cout);
-            t /= E.cout;
-            const int ab = int(t % 4), par = int(t / 4);
-            const int aa = ab >> 1, bb = ab & 1, ph = par >> 1, pw = par & 1;
+            const int blk = int(t / E.cout);
+            int hr, hs, par;
+            if (blk < 4) hr = 1, hs = 1, par = blk;
+            else if (blk < 6) hr = 0, hs = 1, par = blk - 4;
+            else if (blk < 8) hr = 2, hs = 1, par = blk - 4;
+            else if (blk < 11) hr = 1, hs = 0, par = blk - 8;
+            else if (blk < 14) hr = 1, hs = 2, par = blk - 10;
+            else hr = ((blk - 14) >> 1) * 2, hs = ((blk - 14) & 1) * 2, par = blk - 14;
+            const int ph = par >> 1, pw = par & 1, aa = hr - ph, bb = hs - pw;
+            const unsigned off = (unsigned)(i * 2);
+            dst = (off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4)) / 2;
+            if (aa < 0 || aa > 1 || bb < 0 || bb > 1) return 0.f;
             const int r0 = ph == 0 ? (aa == 0 ? 0 : 1) : (aa == 0 ? 0 : 2), r1 = ph == 0 ? (aa == 0 ? 0 : 2) : (aa == 0 ? 1 : 2);
             const int s0 = pw == 0 ? (bb == 0 ? 0 : 1) : (bb == 0 ? 0 : 2), s1 = pw == 0 ? (bb == 0 ? 0 : 2) : (bb == 0 ? 1 : 2);
             float v = 0.f;
             for (int r = r0; r <= r1; ++r)
                 for (int s = s0; s <= s1; ++s) v += w[((IdxT)co * E.a + c) * 9 + r * 3 + s];
-            const unsigned off = (unsigned)(i * 2);
-            dst = (off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4)) / 2;
             return v;
         }
         default: {  // PK_HCONV: cout = rows, cin = ctot, a = dim1_total, b = ci0, c = transposed (see pack_hconv_w_kernel)

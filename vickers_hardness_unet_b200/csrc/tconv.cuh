@@ -49,7 +49,8 @@ struct TconvParams {
     int stage_out;                  // 1: the epilogue transposes through swizzled smem and stores whole sub-tiles with TMA
                                     // (cout >= 32: a register store of 16 channels per pixel touches 32 different 128-byte
                                     // lines per warp instruction and the LSU serialises them: measured 2100 of 5900
-                                    // cycles per tile on the stem); 0: straight from registers (cout = 16, parity mode)
+                                    // cycles per tile on the stem); 0: straight from registers (cout = 16);
+                                    // 2: parity mode, one interleaved 32 x 16 hi-res tile per pipeline step
     int spw;                        // epilogue threads per sub-tile (named-barrier population), stage_out only
     // segmentation-head epilogue (kHead kernels: Conv2d(16,1,3,padding=1) + bias, the conv has cout = 16 accumulator
     // columns of which column 0 holds the bf16 high part and column 1 the bf16 low part of the fp32 weights)
@@ -103,25 +104,34 @@ __device__ __forceinline__ void tc_issue_plain(uint32_t d_tmem, uint64_t a_base,
         }
     }
 }
-// parity mode: accumulator s = (ph, pw); low-res neighbour (a, b) sits at halo pixel (a + ph, b + pw)
+// parity mode: accumulator s = (ph, pw); low-res neighbour (a, b) sits at halo pixel (a + ph, b + pw), so a halo shift
+// (r, c) of the 3x3 neighbourhood serves every parity with r - ph and c - pw in {0, 1}: the centre all four, an edge shift
+// two, a corner one.  ONE MMA per shift covers a contiguous run of the parity accumulators (N = 4, 2, 3 or 1 x cout; the
+// N = 3 runs of the shifts (1,0) / (1,2) carry a zero weight block for the parity in the middle): 9 reads of the 4 KB A
+// operand per K step instead of 16 — that read is what binds these layers (profiles/r1s3_umma_smem_bandwidth.txt).
+// Weight slabs (PK_HPAR, pack.cuh hpar_block): 18 blocks of [cout][cin] in the issue order below.
 template <int KS>
 __device__ __forceinline__ void tc_issue_parity(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t pitch16,
                                                 uint32_t cout, uint32_t idesc) {
     constexpr uint32_t kRow16 = KS * 2;
-    const uint32_t b_tap = cout * kRow16;
+    const uint32_t b_blk = cout * kRow16;                    // one [cout][cin] weight block in 16-byte units
+    const uint32_t n_step = ((cout >> 3) & 0x3Fu) << 17;     // idesc n_dim increment per extra parity
+    //                          centre  top  bottom  left  right  corners
+    constexpr int kR[9]   = {1, 0, 2, 1, 1, 0, 0, 2, 2};
+    constexpr int kC[9]   = {1, 1, 1, 0, 2, 0, 2, 0, 2};
+    constexpr int kLo[9]  = {0, 0, 2, 0, 1, 0, 1, 2, 3};     // first parity accumulator of the run
+    constexpr int kNp[9]  = {4, 2, 2, 3, 3, 1, 1, 1, 1};     // parities in the run
+    constexpr int kBlk[9] = {0, 4, 6, 8, 11, 14, 15, 16, 17};
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const uint32_t d = d_tmem + s * cout;
+    for (int j = 0; j < 9; ++j) {
+        const uint32_t d = d_tmem + kLo[j] * cout;
+        const uint32_t id = idesc + (uint32_t)(kNp[j] - 1) * n_step;
 #pragma unroll
-        for (int ab = 0; ab < 4; ++ab) {
-#pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-                const uint64_t ad = a_base + (uint32_t)((ab >> 1) + (s >> 1)) * pitch16 +
-                                    (uint32_t)(((ab & 1) + (s & 1)) * kRow16 + kk * 2);
-                const uint64_t bd = b_base + (uint32_t)(s * 4 + ab) * b_tap + (uint32_t)(kk * 2);
-                if (ab == 0 && kk == 0) umma_bf16_c<false>(d, ad, bd, idesc);
-                else umma_bf16_c<true>(d, ad, bd, idesc);
-            }
+        for (int kk = 0; kk < KS; ++kk) {
+            const uint64_t ad = a_base + (uint32_t)kR[j] * pitch16 + (uint32_t)(kC[j] * kRow16 + kk * 2);
+            const uint64_t bd = b_base + (uint32_t)kBlk[j] * b_blk + (uint32_t)(kk * 2);
+            if (j == 0 && kk == 0) umma_bf16_c<false>(d, ad, bd, id);
+            else umma_bf16_c<true>(d, ad, bd, id);
         }
     }
 }
@@ -357,7 +367,11 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // staged stores: all items of a thread belong to ONE sub-tile (host guarantees kIph divides cout/16)
         const int my_sub = it_s[0];
         const uint32_t out_row_bytes = (uint32_t)P.cout * 2u, out_swz = out_row_bytes / 16u - 1u;
-        const bool store_issuer = kStage && n_mine > 0 && q == 0 && lane == 0 && (i0 % cgs) == 0;
+        // stage_out == 2 (parity mode): the four parity sub-tiles interleave into ONE dense 32 x 16 hi-res staging tile
+        // (a register store would write cout*2 bytes every second pixel: half-used 128-byte lines from every warp store)
+        const bool par_stage = kStage && P.stage_out == 2;
+        const bool store_issuer = par_stage ? (e == 0 && lane == 0)
+                                            : (kStage && n_mine > 0 && q == 0 && lane == 0 && (i0 % cgs) == 0);
         const int th_px = P.mode == 2 ? P.nt : (P.mode ? 32 : 16), tw_px = P.mode == 2 ? 128 : (P.mode ? 16 : 8 * P.nt);
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -386,7 +400,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (kStage && n_mine > 0) {
                 // the previous tile's TMA store has finished READING this sub-tile's staging before anyone rewrites it
                 if (store_issuer) tma_wait_read<0>();
-                named_bar_sync(2 + 2 * my_sub, P.spw);
+                if (par_stage) named_bar_sync(2, 32 * kEw);
+                else named_bar_sync(2 + 2 * my_sub, P.spw);
             }
             UB_TC_TICK(t_b)
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * acc_cols;
@@ -446,8 +461,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 if (kStage) {
                     // row = TMEM lane = pixel in TMA box order; 16-byte chunks XOR-swizzled like the output tensor map
-                    uint32_t so = (uint32_t)row * out_row_bytes + (uint32_t)c0 * 2u;
-                    uint8_t* sp = sm + L.out_off + it_s[k] * 128u * out_row_bytes;
+                    uint32_t so = (uint32_t)(par_stage ? it_dh[k] * 16 + it_dw[k] : row) * out_row_bytes + (uint32_t)c0 * 2u;
+                    uint8_t* sp = sm + L.out_off + (par_stage ? 0u : it_s[k] * 128u * out_row_bytes);
                     *reinterpret_cast<uint4*>(sp + (so ^ (((so >> 7) & out_swz) << 4))) = o[0];
                     so += 16;
                     *reinterpret_cast<uint4*>(sp + (so ^ (((so >> 7) & out_swz) << 4))) = o[1];
@@ -478,12 +493,20 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             if (kStage && n_mine > 0 && !(P.dbg & 4)) {
                 fence_async_smem();                       // staging writes -> visible to the TMA store (async proxy)
+                if (par_stage) {
+                    named_bar_sync(3, 32 * kEw);
+                    if (store_issuer) {
+                        tma_store_4d(&tmD, base + L.out_off, 0, w0, h0, it.tn);   // [cout, 16, 32, 1], clipped by the TMA
+                        tma_commit();
+                    }
+                } else {
                 named_bar_sync(3 + 2 * my_sub, P.spw);
                 if (store_issuer) {
                     const uint32_t src = base + L.out_off + my_sub * 128u * out_row_bytes;
                     if (P.mode == 2) tma_store_4d(&tmD, src, 0, w0, h0 + my_sub, it.tn);
                     else tma_store_4d(&tmD, src, 0, w0 + 8 * my_sub, h0, it.tn);   // partial tiles are clipped by the TMA
                     tma_commit();
+                }
                 }
             }
             UB_TC_TICK(t_work)

@@ -397,12 +397,6 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             tc_fence_after();
             UB_TC_TICK(t_wait)
-            if (kStage && n_mine > 0) {
-                // the previous tile's TMA store has finished READING this sub-tile's staging before anyone rewrites it
-                if (store_issuer) tma_wait_read<0>();
-                if (par_stage) named_bar_sync(2, 32 * kEw);
-                else named_bar_sync(2 + 2 * my_sub, P.spw);
-            }
             UB_TC_TICK(t_b)
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * acc_cols;
 #pragma unroll
@@ -458,6 +452,13 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     o[j].y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
                     o[j].z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
                     o[j].w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                }
+                if (kStage && k == 0) {
+                    // the previous tile's TMA store has finished READING the staging buffer before anyone rewrites it; the
+                    // first item's TMEM load and epilogue math above overlapped that store
+                    if (store_issuer) tma_wait_read<0>();
+                    if (par_stage) named_bar_sync(2, 32 * kEw);
+                    else named_bar_sync(2 + 2 * my_sub, P.spw);
                 }
                 if (kStage) {
                     // row = TMEM lane = pixel in TMA box order; 16-byte chunks XOR-swizzled like the output tensor map

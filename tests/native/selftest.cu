@@ -789,10 +789,12 @@ static void bench_tconv(const char* name, int N, int H, int W, int cin, int cout
             std::vector<long long> hp((size_t)L.grid * 16);
             CK(cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost));
             const double per = (double)tiles / L.grid;
-            const char* nm[12] = {"P:wait_empty", "P:issue", "", "", "M:wait_tempty", "M:wait_full", "M:issue", "M:commit",
-                                  "E:prefetch", "E:wait_tfull", "E:ld+arrive", "E:work"};
+            // E: prefetch (residual loads) | wait_tfull | - | math+smem writes+2nd TMEM load | first TMEM load | staging-free
+            // barrier | fence + store barrier + TMA store issue
+            const char* nm[15] = {"P:wait_empty", "P:issue", "", "", "M:wait_tempty", "M:wait_full", "M:issue", "M:commit",
+                                  "E:prefetch", "E:wait_tfull", "E:-", "E:work", "E:ld0", "E:bar_free", "E:fence+bar+store"};
             printf("          cycles/tile (CTA 0):");
-            for (int k = 0; k < 12; ++k)
+            for (int k = 0; k < 15; ++k)
                 if (nm[k][0]) printf(" %s=%.0f", nm[k], hp[k] / per);
             printf("\n");
         }

@@ -228,7 +228,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t row_bytes = (uint32_t)P.cin * 2;
     const bool prof = (P.dbg & 8) != 0;
-    long long t_wait = 0, t_work = 0, t_a = 0, t_b = 0, tc = prof ? clock64() : 0;
+    long long t_wait = 0, t_work = 0, t_a = 0, t_b = 0, t_c = 0, t_d = 0, t_e = 0, tc = prof ? clock64() : 0;
 #define UB_TC_TICK(var)                         \
     if (prof) {                                 \
         const long long now_ = clock64();       \
@@ -404,6 +404,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 uint32_t r[16];
                 tmem_ld16(taddr + it_s[k] * P.cout + it_c0[k], r);
                 tmem_ld_wait();
+                if (k == 0) { UB_TC_TICK(t_c) }
                 if (k == kIph - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -457,8 +458,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     // the previous tile's TMA store has finished READING the staging buffer before anyone rewrites it; the
                     // first item's TMEM load and epilogue math above overlapped that store
                     if (store_issuer) tma_wait_read<0>();
+                    UB_TC_TICK(t_work)
                     if (par_stage) named_bar_sync(2, 32 * kEw);
                     else named_bar_sync(2 + 2 * my_sub, P.spw);
+                    UB_TC_TICK(t_d)
                 }
                 if (kStage) {
                     // row = TMEM lane = pixel in TMA box order; 16-byte chunks XOR-swizzled like the output tensor map
@@ -492,6 +495,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                 }
             }
+            UB_TC_TICK(t_work)
             if (kStage && n_mine > 0 && !(P.dbg & 4)) {
                 fence_async_smem();                       // staging writes -> visible to the TMA store (async proxy)
                 if (par_stage) {
@@ -510,7 +514,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 }
             }
-            UB_TC_TICK(t_work)
+            UB_TC_TICK(t_e)
             if (++acc == P.nacc) {
                 acc = 0;
                 acc_phase ^= 1;
@@ -522,6 +526,9 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             P.prof[blockIdx.x * 16 + 9] = t_wait;
             P.prof[blockIdx.x * 16 + 10] = t_b;
             P.prof[blockIdx.x * 16 + 11] = t_work;
+            P.prof[blockIdx.x * 16 + 12] = t_c;
+            P.prof[blockIdx.x * 16 + 13] = t_d;
+            P.prof[blockIdx.x * 16 + 14] = t_e;
         }
         if (P.stats) {
             named_bar_sync(1, 32 * kEw);

@@ -12,7 +12,7 @@ $(PKG)/libunetb200.so: $(SRC)
 
 build/selftest: tests/native/selftest.cu $(SRC)
 	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -Xcompiler -fopenmp -o $@ tests/native/selftest.cu
+	$(NVCC) $(NVFLAGS) -DUB_TC_PROF -Xcompiler -fopenmp -o $@ tests/native/selftest.cu
 
 clean:
 	rm -f $(PKG)/libunetb200.so build/selftest

@@ -1484,6 +1484,9 @@ int main(int argc, char** argv) {
         case_tconv("tconv parity up32->16 2x32x64", 2, 32, 64, 32, 16, true, false, true, true, true);
         case_tconv("tconv parity up32->16 7x96x80 (multi-tile, partial)", 7, 96, 80, 32, 16, true, false, true, true, true);
         case_tconv("tconv parity up64->32 1x32x32", 1, 32, 32, 64, 32, true, false, true, true, false);
+        // hi-res extents that are not multiples of the 32 x 16 staged tile: the TMA store clips, the statistics mask
+        case_tconv("tconv parity up32->16 3x40x24 (clipped store)", 3, 40, 24, 32, 16, true, false, true, true, true);
+        case_tconv("tconv parity up64->32 2x24x40 (clipped store)", 2, 24, 40, 64, 32, true, false, true, true, true);
     }
     if (want("split")) {
         case_dec1_split("split up128+skip128->128 1x8x8", 1, 8, 8, 128, 128, 128);

@@ -512,7 +512,55 @@ inline cudaError_t tconv_launch_t(const TconvLaunch& L, cudaStream_t st) {
     launch_k(tconv_kernel<kOcc, kIph, kStage>, L.grid, tc_threads(kOcc), L.smem, st, L.a, L.d, L.p);
     return cudaGetLastError();
 }
-// seg head: plain 16 -> 16 launch (PK_HEAD weights) whose epilogue writes logits / prob / mask; outputs are set per call
+// seg head Conv2d(16, 1, 3, padding=1) over src[N,H,W,16]: tconv mode 3 (three filter columns stacked as N-blocks, PK_HEAD
+// weights; tc_issue_head3 in tconv.cuh).  Tile = 16 rows x 30 output columns (4 sub-tiles of 4 rows x 32 halo pixels).
+inline std::string tconv_build_head(TconvLaunch& L, const void* src, const void* wpk, int N, int H, int W, int* err,
+                                    int num_sms) {
+    memset(&L.p, 0, sizeof(L.p));
+    if (tconv_const_weights_flag()) L.p.dbg |= 16;
+    TconvParams& P = L.p;
+    const int nt = 4;
+    const uint32_t row_bytes = 32;
+    P.H = H; P.W = W; P.N = N;
+    P.mode = 3;
+    P.cin = 16; P.cout = 16;
+    P.nt = nt;
+    P.tiles_w = (W + 29) / 30;
+    P.tiles_h = (H + 4 * nt - 1) / (4 * nt);
+    P.halo_w = 32;
+    P.tx_bytes = 32u * kTcHaloH * row_bytes;         // kTcHaloH = 4 * nt + 2 rows
+    P.stage_bytes = (P.tx_bytes + 1023u) & ~1023u;
+    P.w_bytes = 3 * 16 * 16 * 2;
+    P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
+    P.err = err;
+    L.occ = 2;
+    L.iph = 2;                                       // 4 sub-tiles over 8 epilogue warps (two per TMEM lane quadrant)
+    int stages = 0;
+    for (int st = 4; st >= 2; --st)
+        if (2 * (tconv_smem(P.w_bytes, P.stage_bytes, st, 0).total + 1024 + 1024) <= 232448u) {
+            stages = st;
+            break;
+        }
+    if (stages < 2) return "tconv head: does not fit in shared memory";
+    P.stages = stages;
+    P.nacc = 4;                                      // 4 x 64 accumulator columns of the CTA's 256
+    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, stages, 0).total + 1024;
+    L.d = CUtensorMap{};
+    {
+        uint64_t dims[4] = {16, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {32, (uint64_t)W * 32, (uint64_t)H * W * 32};
+        uint32_t box[4] = {16, 32, (uint32_t)kTcHaloH, 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.a, src, 4, dims, str, box, es, swizzle_for_bytes(row_bytes));
+        if (!e.empty()) return "tconv head A map: " + e;
+    }
+    const int total_tiles = P.tiles_w * P.tiles_h * N;
+    const int slots = num_sms * L.occ;
+    const int waves = (total_tiles + slots - 1) / slots;
+    L.grid = (total_tiles + waves - 1) / waves;
+    return "";
+}
+// seg head launch: the epilogue writes logits / prob / mask; outputs are set per call
 inline cudaError_t tconv_launch_head(const TconvLaunch& L, float* logits, float* prob, uint8_t* mask, float thresh_logit,
                                      cudaStream_t st) {
     if (L.occ != 2 || L.iph != 2 || L.p.stage_out) return cudaErrorInvalidValue;

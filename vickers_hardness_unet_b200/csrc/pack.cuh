@@ -93,16 +93,17 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             const int r = j >> 2, q = j & 3, px = 2 * q + (e8 >> 2), ch = e8 & 3, co = g * 8 + co8;
             return (ch < 3 && px >= 1) ? w[((co * 3 + ch) * 7 + r) * 7 + (px - 1)] : 0.f;
         }
-        case PK_HEAD: {  // seg head [1][16][3][3] as a 16 -> 16 tconv operand [tap][co][ci]: row 0 = bf16(w), row 1 = the
-            // bf16 of the rounding residual w - bf16(w) (the epilogue adds the two accumulator columns: fp32-accurate
-            // weights on the bf16 tensor core), rows 2..15 = 0; 32-byte rows, SWIZZLE_32B like PK_HCONV
-            const int ci = int(i % 16), co = int((i / 16) % 16), tap = int(i / 256);
+        case PK_HEAD: {  // seg head [1][16][3][3] as the stacked-column tconv operand (tconv mode 3): [filter row r][16 rows]
+            // [16 ci], row 2c = bf16(w[r][c]), row 2c + 1 = the bf16 of the rounding residual w - bf16(w) for filter column
+            // c = 0..2 (the epilogue adds the two accumulator columns: fp32-accurate weights on the bf16 tensor core),
+            // rows 6..15 = 0; 32-byte rows, SWIZZLE_32B like PK_HCONV.  Elements past the 3 x 16 x 16 block are zero.
+            const int ci = int(i % 16), row = int((i / 16) % 16), r = int(i / 256);
             const unsigned off = (unsigned)(i * 2);
             dst = (off ^ (((off >> 7) & 1u) << 4)) / 2;
-            if (co > 1) return 0.f;
-            const float wv = w[ci * 9 + tap];
+            if (r > 2 || row > 5) return 0.f;
+            const float wv = w[ci * 9 + r * 3 + (row >> 1)];
             const float hi = __bfloat162float(__float2bfloat16(wv));
-            return co == 0 ? hi : wv - hi;
+            return (row & 1) == 0 ? hi : wv - hi;
         }
         case PK_HPAR: {  // tconv parity operand: cout = rows, cin = cup (<= 64), a = cin_total of the OIHW tensor.
             // 18 blocks [blk][co][c] in the issue order of tc_issue_parity (tconv.cuh): block = (halo shift (r, s), output

@@ -32,6 +32,7 @@ struct TconvParams {
     int H, W, N;                    // OUTPUT extent
     int mode;                       // 0: plain 3x3 over src[N,H,W,cin]; 1: parity (src = low-res [N,H/2,W/2,cin], 2x2 taps);
                                     // 2: 7x7/s2 stem over the packed image xp[N][2H][2W+8][4] (see tc_issue_stem)
+                                    // 3: seg head with the three filter columns stacked as N-blocks (see tc_issue_head3)
     int nt;                         // accumulators (sub-tiles) per pipeline step
     int tiles_w, tiles_h;           // tile grid per image (plain: 8*nt x 16 output px; parity: 8 x 16 low-res px)
     int cin, cout;
@@ -163,6 +164,26 @@ __device__ __forceinline__ void tc_issue_stem(uint32_t d_tmem, uint32_t stage_ad
     }
 }
 
+// Head mode 3 (Conv2d(16, 1, 3, padding=1)): the A operand (4 KB per MMA) is what a 16-channel conv pays for, so the three
+// filter COLUMNS become N-blocks of one MMA instead of three shifted A reads: a sub-tile is 4 image rows x 32 consecutive
+// pixels of a halo box that is exactly 32 pixels wide (image rows are contiguous in smem, so SBO = 8 pixels), accumulator
+// column 2c / 2c + 1 of pixel x holds (hi / lo weight parts of filter column c) . input(x) summed over the three filter
+// rows (row taps = whole-row shifts of the A start address): 3 MMAs per sub-tile instead of 9.  The epilogue adds the
+// neighbours' columns with two warp shuffles (lane = pixel): logit(x) = D_0(x-1) + D_1(x) + D_2(x+1); pixels 0 and 31 of a
+// row are halo, a tile yields 30 output columns.
+__device__ __forceinline__ void tc_issue_head3(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t idesc, int nt) {
+    for (int s = 0; s < nt; ++s) {
+        const uint32_t d = d_tmem + s * 16;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint64_t ad = a_base + (uint32_t)((4 * s + r) * 32 * 2);   // 32 pixels x 32 B per image row, 16-byte units
+            const uint64_t bd = b_base + (uint32_t)(r * 16 * 2);            // 16 rows x 32 B per filter row
+            if (r == 0) umma_bf16_c<false>(d, ad, bd, idesc);
+            else umma_bf16_c<true>(d, ad, bd, idesc);
+        }
+    }
+}
+
 // kIph = accumulator column groups (16 channels of one sub-tile) each epilogue thread handles per pipeline step
 template <int kOcc, int kIph, bool kStage, bool kHead = false>
 __global__ void __launch_bounds__(tc_threads(kOcc), kOcc)
@@ -227,6 +248,9 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t row_bytes = (uint32_t)P.cin * 2;
+    // Role-cycle counters exist only in builds with -DUB_TC_PROF (tests/native/selftest): seven live 64-bit counters cost
+    // the 96-register kernel 16-40 bytes of local-memory spill per thread, measurable on every launch.
+#ifdef UB_TC_PROF
     const bool prof = (P.dbg & 8) != 0;
     long long t_wait = 0, t_work = 0, t_a = 0, t_b = 0, t_c = 0, t_d = 0, t_e = 0, tc = prof ? clock64() : 0;
 #define UB_TC_TICK(var)                         \
@@ -235,6 +259,11 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         var += now_ - tc;                       \
         tc = now_;                              \
     }
+#define UB_TC_PROF_ONLY(...) __VA_ARGS__
+#else
+#define UB_TC_TICK(var)
+#define UB_TC_PROF_ONLY(...)
+#endif
 
     if (warp == 0) {
         // ================================================================= TMA producer (one thread)
@@ -251,6 +280,9 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (P.mode == 2) {  // 128-byte groups of 8 pixel pairs of the packed image: output column wo <-> pair wo
                     x0 = it.tw * 16;
                     y0 = 2 * it.th * P.nt - 3;
+                } else if (kHead && P.mode == 3) {
+                    x0 = it.tw * 30 - 1;
+                    y0 = it.th * 4 * P.nt - 1;
                 }
                 if (P.dbg & 1) {
                     mbar_arrive(full_bar(stage));
@@ -264,10 +296,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     phase ^= 1;
                 }
             }
-            if (prof) {
+            UB_TC_PROF_ONLY(if (prof) {
                 P.prof[blockIdx.x * 16 + 0] = t_wait;
                 P.prof[blockIdx.x * 16 + 1] = t_work;
-            }
+            })
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer (one thread)
@@ -277,7 +309,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint32_t idesc = umma_idesc_bf16(128, P.cout, 0, 0);
             const uint32_t layout = row_bytes == 32 ? 6u : (row_bytes == 64 ? 4u : 2u);
             const uint64_t b_base = umma_desc(base + L.w_off, 16, 8 * row_bytes, layout);
-            const uint64_t a_base0 = umma_desc(base + L.halo_off, 16, P.halo_w * row_bytes, layout);
+            const uint64_t a_base0 = umma_desc(base + L.halo_off, 16, ((kHead && P.mode == 3) ? 8 : P.halo_w) * row_bytes, layout);
             const uint32_t pitch16 = ((uint32_t)P.halo_w * row_bytes) >> 4;
             const int ks = P.cin >> 4;
             for (int n = blockIdx.x; n < total_tiles; n += gridDim.x) {
@@ -298,6 +330,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (P.mode == 2) {
                         tc_issue_stem(d_tmem, base + L.halo_off + stage * P.stage_bytes, base + L.w_off,
                                       (uint32_t)P.halo_w * 16u, idesc, P.nt);
+                    } else if (kHead && P.mode == 3) {
+                        tc_issue_head3(d_tmem, a_base, b_base, idesc, P.nt);
                     } else if (P.mode) {
                         switch (ks) {
                             case 1: tc_issue_parity<1>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
@@ -325,12 +359,12 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     acc_phase ^= 1;
                 }
             }
-            if (prof) {
+            UB_TC_PROF_ONLY(if (prof) {
                 P.prof[blockIdx.x * 16 + 4] = t_a;
                 P.prof[blockIdx.x * 16 + 5] = t_wait;
                 P.prof[blockIdx.x * 16 + 6] = t_work;
                 P.prof[blockIdx.x * 16 + 7] = t_b;
-            }
+            })
         }
     } else {
         // ================================================================= epilogue (kEw warps): thread = pixel of a sub-tile
@@ -354,6 +388,9 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (P.mode == 2) {
                 it_dh[k] = it_s[k];
                 it_dw[k] = row;
+            } else if (kHead && P.mode == 3) {
+                it_dh[k] = 4 * it_s[k] + q;
+                it_dw[k] = lane - 1;
             } else if (P.mode) {
                 it_dh[k] = 2 * hl + (it_s[k] >> 1);
                 it_dw[k] = 2 * wl + (it_s[k] & 1);
@@ -372,7 +409,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool par_stage = kStage && P.stage_out == 2;
         const bool store_issuer = par_stage ? (e == 0 && lane == 0)
                                             : (kStage && n_mine > 0 && q == 0 && lane == 0 && (i0 % cgs) == 0);
-        const int th_px = P.mode == 2 ? P.nt : (P.mode ? 32 : 16), tw_px = P.mode == 2 ? 128 : (P.mode ? 16 : 8 * P.nt);
+        const int th_px = P.mode == 2 ? P.nt : ((kHead && P.mode == 3) ? 4 * P.nt : (P.mode ? 32 : 16));
+        const int tw_px = P.mode == 2 ? 128 : ((kHead && P.mode == 3) ? 30 : (P.mode ? 16 : 8 * P.nt));
         int acc = 0;
         uint32_t acc_phase = 0;
         for (HcTileIter it(P.tiles_w, P.tiles_h, total_tiles); it.valid(); it.next()) {
@@ -383,6 +421,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < kIph; ++k) {
                 valid[k] = k < n_mine && h0 + it_dh[k] < P.H && w0 + it_dw[k] < P.W;
+                if (kHead && P.mode == 3) valid[k] = valid[k] && lane >= 1 && lane <= 30;
                 if (P.residual && valid[k]) {  // issued before the accumulator wait: the loads overlap the tile's MMAs
                     const uint4* rp = reinterpret_cast<const uint4*>(
                         P.residual + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + it_c0[k]);
@@ -413,8 +452,14 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (k >= n_mine || (P.dbg & 4)) continue;
                 if (kHead) {
                     // fp32 logit = (w_hi + w_lo) . x + bias; sigmoid(x) >= t  <=>  x >= logit(t)
+                    float lg = __uint_as_float(r[0]) + __uint_as_float(r[1]);
+                    if (P.mode == 3) {   // stacked filter columns: left neighbour's column 0, own column 1, right neighbour's 2
+                        const float c1 = __uint_as_float(r[2]) + __uint_as_float(r[3]);
+                        const float c2 = __uint_as_float(r[4]) + __uint_as_float(r[5]);
+                        lg = __shfl_up_sync(0xffffffffu, lg, 1) + c1 + __shfl_down_sync(0xffffffffu, c2, 1);
+                    }
+                    lg += head_bias;
                     if (valid[k]) {
-                        const float lg = __uint_as_float(r[0]) + __uint_as_float(r[1]) + head_bias;
                         const size_t o = (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]);
                         if (P.logits) P.logits[o] = lg;
                         if (P.prob) P.prob[o] = 1.f / (1.f + __expf(-lg));
@@ -521,7 +566,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
         if (kStage && store_issuer) tma_wait_all<0>();  // all output stores complete before the CTA exits
-        if (prof && threadIdx.x == 64) {
+        UB_TC_PROF_ONLY(if (prof && threadIdx.x == 64) {
             P.prof[blockIdx.x * 16 + 8] = t_a;
             P.prof[blockIdx.x * 16 + 9] = t_wait;
             P.prof[blockIdx.x * 16 + 10] = t_b;
@@ -529,7 +574,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             P.prof[blockIdx.x * 16 + 12] = t_c;
             P.prof[blockIdx.x * 16 + 13] = t_d;
             P.prof[blockIdx.x * 16 + 14] = t_e;
-        }
+        })
         if (P.stats) {
             named_bar_sync(1, 32 * kEw);
             const float* call = reinterpret_cast<const float*>(sm + L.cstat_off);
@@ -543,6 +588,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     }
 #undef UB_TC_TICK
+#undef UB_TC_PROF_ONLY
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {

@@ -589,8 +589,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     }
     plan.head_in = cur;
     if (!dry) {
-        err = tconv_build(plan.head_fwd, cur, 16, false, ctx->wpk + S.convs[S.head].wpk, 16, N, H, W, nullptr,
-                          EpilogueDesc(), ctx->d_err, SM);
+        err = tconv_build_head(plan.head_fwd, cur, ctx->wpk + S.convs[S.head].wpk, N, H, W, ctx->d_err, SM);
         if (!err.empty()) return "segmentation_head: " + err;
         plan.head_fwd.p.head_bias = ctx->head_w + 144;
     }

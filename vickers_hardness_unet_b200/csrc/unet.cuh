@@ -682,8 +682,7 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
     }
     plan.head_in = cur;
     if (!dry) {
-        err = tconv_build(plan.head, cur, 16, false, ctx->wpk + S.convs[S.head].wpk, 16, N, h, w, nullptr, EpilogueDesc(),
-                          ctx->d_err, ctx->num_sms);
+        err = tconv_build_head(plan.head, cur, ctx->wpk + S.convs[S.head].wpk, N, h, w, ctx->d_err, ctx->num_sms);
         if (!err.empty()) return "segmentation_head: " + err;
         plan.head.p.head_bias = ctx->head_w + 144;
     }

@@ -353,6 +353,57 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     P.H = H; P.W = W; P.N = N;
     P.mode = parity ? 1 : 0;
     P.cin = cin; P.cout = cout;
+    // Cout <= 32: the three filter columns as N-blocks of one MMA (tc_issue_stack): a third of the A-operand reads, and
+    // with lane = pixel of an image row the register stores / residual loads of the epilogue are coalesced, no staging.
+    // OFF by default (UNETB200_STACK=1 enables it): parity-green (22 native checks) but slower than the nine-tap issue on
+    // B200 — 16->16 @512^2 x32 135-140 us vs 115, 32->32 @256^2 79-81 us vs 65 (profiles/r1s4_negative_results.txt #11):
+    // the one-item-per-thread epilogue chain (3 TMEM loads, 32 shuffles) becomes the critical role.  The seg head
+    // (tconv_build_head), whose epilogue emits one value per pixel, uses the same geometry and gains 30 %.
+    static const bool stack_on = getenv("UNETB200_STACK") != nullptr;
+    if (stack_on && !parity && cout <= 32 && W >= 32) {
+        static const bool stack_occ2 = getenv("UNETB200_STACK_OCC1") == nullptr;
+        const int snt = (cout == 16 ? 4 : 2) / (stack_occ2 ? 2 : 1);   // 3 * cout * snt accumulator columns, double buffered
+        P.mode = 3;
+        P.nt = snt;
+        P.tiles_w = (W + 29) / 30;
+        P.tiles_h = (H + 4 * snt - 1) / (4 * snt);
+        P.halo_w = 32;
+        P.tx_bytes = 32u * (uint32_t)(4 * snt + 2) * row_bytes;
+        P.stage_bytes = (P.tx_bytes + 1023u) & ~1023u;
+        P.w_bytes = (uint32_t)tconv_w_elems(cin, cout, false) * 2;
+        P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
+        P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
+        P.out = reinterpret_cast<__nv_bfloat16*>(out);
+        P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+        P.stats = ep.stats;
+        P.err = err;
+        L.occ = stack_occ2 ? 2 : 1;
+        L.iph = 1;                                   // snt * cout / 16 = 4 (2) items over 16 (8) epilogue warps
+        int sst = 0;
+        for (int st = stack_occ2 ? 4 : 6; st >= 2; --st) {
+            const uint32_t tot = tconv_smem(P.w_bytes, P.stage_bytes, st, 0).total + 1024;
+            if (stack_occ2 ? 2 * (tot + 1024) <= 232448u : tot <= 232448u) {
+                sst = st;
+                break;
+            }
+        }
+        if (sst < 2) return "tconv: does not fit in shared memory";
+        P.stages = sst;
+        P.nacc = 2;
+        L.smem = tconv_smem(P.w_bytes, P.stage_bytes, sst, 0).total + 1024;
+        L.d = CUtensorMap{};
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+        uint64_t str[3] = {(uint64_t)cin * 2, (uint64_t)W * cin * 2, (uint64_t)H * W * cin * 2};
+        uint32_t box[4] = {(uint32_t)cin, 32, (uint32_t)(4 * snt + 2), 1};
+        uint32_t es[4] = {1, 1, 1, 1};
+        std::string e = make_tmap_bf16(&L.a, src, 4, dims, str, box, es, swizzle_for_bytes(row_bytes));
+        if (!e.empty()) return "tconv A map: " + e;
+        const int total_tiles = P.tiles_w * P.tiles_h * N;
+        const int slots = num_sms * L.occ;
+        const int waves = (total_tiles + slots - 1) / slots;
+        L.grid = (total_tiles + waves - 1) / waves;
+        return "";
+    }
     int nt;
     if (parity) nt = 4;
     else {
@@ -500,16 +551,16 @@ inline std::string tconv_build_stem(TconvLaunch& L, const void* xp, const void* 
     return "";
 }
 
-template <int kOcc, int kIph, bool kStage>
+template <int kOcc, int kIph, bool kStage, bool kStack = false>
 inline cudaError_t tconv_launch_t(const TconvLaunch& L, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<kOcc, kIph, kStage>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kOcc == 2 ? 115200 : 232448);
+        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<kOcc, kIph, kStage, false, kStack>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kOcc == 2 ? 115200 : 232448);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    launch_k(tconv_kernel<kOcc, kIph, kStage>, L.grid, tc_threads(kOcc), L.smem, st, L.a, L.d, L.p);
+    launch_k(tconv_kernel<kOcc, kIph, kStage, false, kStack>, L.grid, tc_threads(kOcc), L.smem, st, L.a, L.d, L.p);
     return cudaGetLastError();
 }
 // seg head Conv2d(16, 1, 3, padding=1) over src[N,H,W,16]: tconv mode 3 (three filter columns stacked as N-blocks, PK_HEAD
@@ -563,20 +614,22 @@ inline std::string tconv_build_head(TconvLaunch& L, const void* src, const void*
 // seg head launch: the epilogue writes logits / prob / mask; outputs are set per call
 inline cudaError_t tconv_launch_head(const TconvLaunch& L, float* logits, float* prob, uint8_t* mask, float thresh_logit,
                                      cudaStream_t st) {
-    if (L.occ != 2 || L.iph != 2 || L.p.stage_out) return cudaErrorInvalidValue;
+    if (L.occ != 2 || L.iph != 2 || L.p.stage_out || L.p.mode != 3) return cudaErrorInvalidValue;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
+        cudaError_t e = cudaFuncSetAttribute(tconv_kernel<2, 2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 115200);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     TconvParams p = L.p;
     p.logits = logits; p.prob = prob; p.mask = mask; p.thresh_logit = thresh_logit;
-    launch_k(tconv_kernel<2, 2, false, true>, L.grid, tc_threads(2), L.smem, st, L.a, L.d, p);
+    launch_k(tconv_kernel<2, 2, false, true, true>, L.grid, tc_threads(2), L.smem, st, L.a, L.d, p);
     return cudaGetLastError();
 }
 
 inline cudaError_t tconv_launch(const TconvLaunch& L, cudaStream_t st) {
+    if (L.p.mode == 3)   // stacked filter columns (tconv_build)
+        return L.occ == 2 ? tconv_launch_t<2, 1, false, true>(L, st) : tconv_launch_t<1, 1, false, true>(L, st);
     const int key = (L.occ == 2 ? 4 : 0) | (L.iph == 2 ? 2 : 0) | (L.p.stage_out ? 1 : 0);
     switch (key) {
         case 0: return tconv_launch_t<1, 1, false>(L, st);

@@ -184,8 +184,32 @@ __device__ __forceinline__ void tc_issue_head3(uint32_t d_tmem, uint64_t a_base,
     }
 }
 
+// Mode 3 for a whole conv (Cout <= 32): same sub-tile geometry as tc_issue_head3, B = the three filter-column slabs of
+// filter row r (contiguous in the PK_HCONV layout: N = 3 * cout), accumulator block c of pixel x holds W[.][c] . input(x)
+// summed over filter rows and input channels; the epilogue combines D_0(x-1) + D_1(x) + D_2(x+1) with warp shuffles.
+// 3 * KS reads of the 4 KB A operand per sub-tile instead of 9 * KS.
+template <int KS>
+__device__ __forceinline__ void tc_issue_stack(uint32_t d_tmem, uint64_t a_base, uint64_t b_base, uint32_t cout,
+                                               uint32_t idesc, int nt) {
+    constexpr uint32_t kRow16 = KS * 2;
+    const uint32_t b_row = 3 * cout * kRow16;                // three tap slabs = one filter row, 16-byte units
+    for (int s = 0; s < nt; ++s) {
+        const uint32_t d = d_tmem + s * 3 * cout;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const uint64_t ad = a_base + (uint32_t)((4 * s + r) * 32) * kRow16 + (uint32_t)(kk * 2);
+                const uint64_t bd = b_base + (uint32_t)r * b_row + (uint32_t)(kk * 2);
+                if (r == 0 && kk == 0) umma_bf16_c<false>(d, ad, bd, idesc);
+                else umma_bf16_c<true>(d, ad, bd, idesc);
+            }
+        }
+    }
+}
+
 // kIph = accumulator column groups (16 channels of one sub-tile) each epilogue thread handles per pipeline step
-template <int kOcc, int kIph, bool kStage, bool kHead = false>
+template <int kOcc, int kIph, bool kStage, bool kHead = false, bool kStack = false>
 __global__ void __launch_bounds__(tc_threads(kOcc), kOcc)
 tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmD,
              const __grid_constant__ TconvParams P) {
@@ -205,7 +229,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = P.tiles_w * P.tiles_h * P.N;
-    const int acc_cols = P.nt * P.cout;
+    const int sub_cols = (kStack && !kHead) ? 3 * P.cout : P.cout;   // accumulator columns per sub-tile
+    const int acc_cols = P.nt * sub_cols;
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(P.nacc * acc_cols)) tmem_cols <<= 1;
 
@@ -280,7 +305,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (P.mode == 2) {  // 128-byte groups of 8 pixel pairs of the packed image: output column wo <-> pair wo
                     x0 = it.tw * 16;
                     y0 = 2 * it.th * P.nt - 3;
-                } else if (kHead && P.mode == 3) {
+                } else if (kStack) {
                     x0 = it.tw * 30 - 1;
                     y0 = it.th * 4 * P.nt - 1;
                 }
@@ -306,10 +331,10 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
-            const uint32_t idesc = umma_idesc_bf16(128, P.cout, 0, 0);
+            const uint32_t idesc = umma_idesc_bf16(128, (kStack && !kHead) ? 3 * P.cout : P.cout, 0, 0);
             const uint32_t layout = row_bytes == 32 ? 6u : (row_bytes == 64 ? 4u : 2u);
             const uint64_t b_base = umma_desc(base + L.w_off, 16, 8 * row_bytes, layout);
-            const uint64_t a_base0 = umma_desc(base + L.halo_off, 16, ((kHead && P.mode == 3) ? 8 : P.halo_w) * row_bytes, layout);
+            const uint64_t a_base0 = umma_desc(base + L.halo_off, 16, ((kStack) ? 8 : P.halo_w) * row_bytes, layout);
             const uint32_t pitch16 = ((uint32_t)P.halo_w * row_bytes) >> 4;
             const int ks = P.cin >> 4;
             for (int n = blockIdx.x; n < total_tiles; n += gridDim.x) {
@@ -330,8 +355,14 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (P.mode == 2) {
                         tc_issue_stem(d_tmem, base + L.halo_off + stage * P.stage_bytes, base + L.w_off,
                                       (uint32_t)P.halo_w * 16u, idesc, P.nt);
-                    } else if (kHead && P.mode == 3) {
+                    } else if (kStack && kHead) {
                         tc_issue_head3(d_tmem, a_base, b_base, idesc, P.nt);
+                    } else if (kStack) {
+                        switch (ks) {
+                            case 1: tc_issue_stack<1>(d_tmem, a_base, b_base, P.cout, idesc, P.nt); break;
+                            case 2: tc_issue_stack<2>(d_tmem, a_base, b_base, P.cout, idesc, P.nt); break;
+                            default: tc_issue_stack<4>(d_tmem, a_base, b_base, P.cout, idesc, P.nt); break;
+                        }
                     } else if (P.mode) {
                         switch (ks) {
                             case 1: tc_issue_parity<1>(d_tmem, a_base, b_base, pitch16, P.cout, idesc); break;
@@ -388,7 +419,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (P.mode == 2) {
                 it_dh[k] = it_s[k];
                 it_dw[k] = row;
-            } else if (kHead && P.mode == 3) {
+            } else if (kStack) {
                 it_dh[k] = 4 * it_s[k] + q;
                 it_dw[k] = lane - 1;
             } else if (P.mode) {
@@ -409,8 +440,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool par_stage = kStage && P.stage_out == 2;
         const bool store_issuer = par_stage ? (e == 0 && lane == 0)
                                             : (kStage && n_mine > 0 && q == 0 && lane == 0 && (i0 % cgs) == 0);
-        const int th_px = P.mode == 2 ? P.nt : ((kHead && P.mode == 3) ? 4 * P.nt : (P.mode ? 32 : 16));
-        const int tw_px = P.mode == 2 ? 128 : ((kHead && P.mode == 3) ? 30 : (P.mode ? 16 : 8 * P.nt));
+        const int th_px = P.mode == 2 ? P.nt : ((kStack) ? 4 * P.nt : (P.mode ? 32 : 16));
+        const int tw_px = P.mode == 2 ? 128 : ((kStack) ? 30 : (P.mode ? 16 : 8 * P.nt));
         int acc = 0;
         uint32_t acc_phase = 0;
         for (HcTileIter it(P.tiles_w, P.tiles_h, total_tiles); it.valid(); it.next()) {
@@ -421,7 +452,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < kIph; ++k) {
                 valid[k] = k < n_mine && h0 + it_dh[k] < P.H && w0 + it_dw[k] < P.W;
-                if (kHead && P.mode == 3) valid[k] = valid[k] && lane >= 1 && lane <= 30;
+                if (kStack) valid[k] = valid[k] && lane >= 1 && lane <= 30;
                 if (P.residual && valid[k]) {  // issued before the accumulator wait: the loads overlap the tile's MMAs
                     const uint4* rp = reinterpret_cast<const uint4*>(
                         P.residual + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + it_c0[k]);
@@ -441,8 +472,25 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int k = 0; k < kIph; ++k) {
                 uint32_t r[16];
-                tmem_ld16(taddr + it_s[k] * P.cout + it_c0[k], r);
-                tmem_ld_wait();
+                if (kStack && !kHead) {
+                    // D_0 of the left neighbour + own D_1 + D_2 of the right neighbour (lane = pixel of the image row)
+                    uint32_t t[16];
+                    const uint32_t ta = taddr + it_s[k] * sub_cols + it_c0[k];
+                    tmem_ld16(ta, r);
+                    tmem_ld16(ta + P.cout, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        r[j] = __float_as_uint(__shfl_up_sync(0xffffffffu, __uint_as_float(r[j]), 1) + __uint_as_float(t[j]));
+                    tmem_ld16(ta + 2 * P.cout, t);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        r[j] = __float_as_uint(__uint_as_float(r[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(t[j]), 1));
+                } else {
+                    tmem_ld16(taddr + it_s[k] * P.cout + it_c0[k], r);
+                    tmem_ld_wait();
+                }
                 if (k == 0) { UB_TC_TICK(t_c) }
                 if (k == kIph - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp
                     tc_fence_before();
@@ -453,7 +501,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (kHead) {
                     // fp32 logit = (w_hi + w_lo) . x + bias; sigmoid(x) >= t  <=>  x >= logit(t)
                     float lg = __uint_as_float(r[0]) + __uint_as_float(r[1]);
-                    if (P.mode == 3) {   // stacked filter columns: left neighbour's column 0, own column 1, right neighbour's 2
+                    if (kStack) {   // stacked filter columns: left neighbour's column 0, own column 1, right neighbour's 2
                         const float c1 = __uint_as_float(r[2]) + __uint_as_float(r[3]);
                         const float c2 = __uint_as_float(r[4]) + __uint_as_float(r[5]);
                         lg = __shfl_up_sync(0xffffffffu, lg, 1) + c1 + __shfl_down_sync(0xffffffffu, c2, 1);

@@ -7,7 +7,8 @@ One JSON line on stdout (rank 0).  N=1 workload = BASELINE.json configs[1]: batc
 A "step" is one forward pass of the whole network over one batch of synthetic inputs.
   value     images/s with the fp32 NCHW input batch already resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the C-ABI host-buffer call (pinned host input -> H2D -> forward -> D2H of the uint8 mask)
-  roofline  the igemm conv stack (dominant kernel) against the measured dense bf16 peak (MEASURED_PEAKS.json)
+  roofline  the conv stack (all wconv / tconv / wpconv / igemm launches of one step) against the measured dense bf16 peak
+            (MEASURED_PEAKS.json); roofline.per_layer bounds every launch by max(FLOPs / peak, min bytes / HBM copy bandwidth)
   cpu_baseline  the fp32 CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
 `--impl reference` times the reference's CPU implementation of the path (the oracle port: smp is not installable
 offline) on all host threads.

@@ -1537,6 +1537,7 @@ int main(int argc, char** argv) {
         bench_tconv("L1 64->64 +res @128^2 x32", 32, 128, 128, 64, 64, false, true, 10);
         bench_tconv("D4c1 up32->16 @512^2 x32 (parity)", 32, 512, 512, 32, 16, true, false, 5);
         bench_tconv("D3c1 up64->32 @256^2 x32 (parity)", 32, 256, 256, 64, 32, true, false, 5);
+        bench_tconv("D3c1s 64->32 +res @256^2 x32", 32, 256, 256, 64, 32, false, true, 5);
     }
     if (want("bench")) {
         bench_conv("L1 3x3 64->64 @128^2 x32", 32, 128, 128, 64, 64, 3, 1, 20);

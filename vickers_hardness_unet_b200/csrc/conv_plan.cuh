@@ -355,11 +355,13 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     P.cin = cin; P.cout = cout;
     // Cout <= 32: the three filter columns as N-blocks of one MMA (tc_issue_stack): a third of the A-operand reads, and
     // with lane = pixel of an image row the register stores / residual loads of the epilogue are coalesced, no staging.
-    // OFF by default (UNETB200_STACK=1 enables it): parity-green (22 native checks) but slower than the nine-tap issue on
-    // B200 — 16->16 @512^2 x32 135-140 us vs 115, 32->32 @256^2 79-81 us vs 65 (profiles/r1s4_negative_results.txt #11):
-    // the one-item-per-thread epilogue chain (3 TMEM loads, 32 shuffles) becomes the critical role.  The seg head
-    // (tconv_build_head), whose epilogue emits one value per pixel, uses the same geometry and gains 30 %.
-    static const bool stack_on = getenv("UNETB200_STACK") != nullptr;
+    // Used where the MMA issue dominates the tile (Cin >= 64 with Cout <= 32: decoder.blocks.3.conv1 [skip], 64 -> 32 with
+    // residual @256^2 x32: 155 -> 109 us).  For Cin <= 32 the nine-tap issue stays: there the one-item-per-thread epilogue
+    // chain (3 TMEM loads, 32 shuffles) becomes the critical role and the stacked form is slower (16->16 @512^2 135 vs
+    // 115 us, 32->32 @256^2 80 vs 65 us; profiles/r1s4_negative_results.txt #11).  UNETB200_STACK=1 forces it for every
+    // Cout <= 32 launch, UNETB200_NO_STACK=1 switches it off.
+    static const bool stack_all = getenv("UNETB200_STACK") != nullptr, stack_off = getenv("UNETB200_NO_STACK") != nullptr;
+    const bool stack_on = !stack_off && (stack_all || cin >= 64);
     if (stack_on && !parity && cout <= 32 && W >= 32) {
         static const bool stack_occ2 = getenv("UNETB200_STACK_OCC1") == nullptr;
         const int snt = (cout == 16 ? 4 : 2) / (stack_occ2 ? 2 : 1);   // 3 * cout * snt accumulator columns, double buffered

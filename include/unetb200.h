@@ -89,6 +89,14 @@ int unetb200_forward_infer_u8(unetb200_ctx* ctx, const uint8_t* img_dev, int bgr
 /* number of kernel launches one forward_infer call issues at batch N (after the plan for N exists) */
 int unetb200_infer_launch_count(unetb200_ctx* ctx, int N);
 
+/* Test hooks: the activations the last forward_infer at batch N left in the library's arena, by index: NHWC bf16
+ * [n,h,w,c].  Names: "xp" (packed input [N,H,W+8,4]), "<conv weight key>/out" (the tensor that launch wrote: after the
+ * folded BatchNorm (+residual) (+ReLU)), "<decoder conv1 key>/up" (scaled partial over the up-sampled channels),
+ * "encoder.maxpool/out".  The layer-local parity tests re-derive every launch's output from ITS OWN inputs. */
+int unetb200_infer_debug_count(unetb200_ctx* ctx, int N);
+int unetb200_infer_debug_info(unetb200_ctx* ctx, int N, int index, char* name_out, int name_cap, int shape_out[4]);
+int unetb200_infer_debug_copy(unetb200_ctx* ctx, int N, int index, void* dst_dev, long long cap_bytes, void* stream);
+
 /* One forward with a CUDA event recorded between consecutive launches on `stream`: ms_out[i] = device time of launch i
  * (0 = input pack, last = seg head), is_igemm_out[i] = 1 for implicit-GEMM conv launches.  Synchronises the stream. */
 int unetb200_profile_infer(unetb200_ctx* ctx, const float* x_dev, float* logits_dev, int N, void* stream,

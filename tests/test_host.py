@@ -56,7 +56,7 @@ def test_rejects_unsupported_configs_and_cpu_inputs():
     with pytest.raises(ValueError):
         vb.Unet("resnet50")
     with pytest.raises(ValueError):
-        vb.Unet("resnet34", encoder_weights="imagenet")
+        vb.Unet("resnet34", encoder_weights="ssl")
     with pytest.raises(ValueError):
         vb.Unet("resnet34", classes=2)
     m = vb.Unet("resnet34")
@@ -64,6 +64,100 @@ def test_rejects_unsupported_configs_and_cpu_inputs():
         m(torch.zeros(1, 3, 64, 64))
     with pytest.raises(ValueError):
         vb.losses.DiceLoss(mode="multiclass")
+
+
+def test_imagenet_encoder_weights_from_a_local_torchvision_checkpoint(tmp_path, monkeypatch):
+    """train.py:753,595 passes encoder_weights="imagenet": accepted when a torchvision-format resnet34 file is on local
+    disk (what smp would have downloaded), a FileNotFoundError with the path hint otherwise."""
+    import torchvision
+
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path / "empty_hub"))
+    monkeypatch.delenv("UNETB200_RESNET34_WEIGHTS", raising=False)
+    with pytest.raises(FileNotFoundError, match="UNETB200_RESNET34_WEIGHTS"):
+        vb.Unet("resnet34", encoder_weights="imagenet")
+    torch.manual_seed(7)
+    tv = torchvision.models.resnet34(weights=None)
+    with torch.no_grad():
+        for b in tv.buffers():
+            if b.dtype == torch.float32:
+                b.uniform_(0.5, 1.5)
+    f = tmp_path / "resnet34-local.pth"
+    torch.save(tv.state_dict(), f)
+    monkeypatch.setenv("UNETB200_RESNET34_WEIGHTS", str(f))
+    m = vb.Unet("resnet34", encoder_weights="imagenet", in_channels=3, classes=1, activation=None)
+    sd = m.state_dict()
+    for k, v in tv.state_dict().items():
+        if not k.startswith("fc."):
+            assert torch.equal(sd["encoder." + k], v), k
+    bad = tmp_path / "bad.pth"
+    torch.save({"conv1.weight": torch.zeros(1)}, bad)
+    monkeypatch.setenv("UNETB200_RESNET34_WEIGHTS", str(bad))
+    with pytest.raises(RuntimeError, match="not a torchvision resnet34"):
+        vb.Unet("resnet34", encoder_weights="imagenet")
+
+
+def test_weight_cache_key_sees_in_place_updates_after_to():
+    """after `.to()` every Parameter has its own version counter, so the key that decides whether the
+    bf16 operand caches are stale must include the per-parameter versions (stock torch.optim.AdamW updates in place)."""
+    m = vb.Unet("resnet34").to(torch.float32)   # _apply -> _reflatten -> `p.data = view`
+
+    class _Ctx:  # stands in for the native context: records whether a re-pack was requested
+        calls = 0
+        handle = None
+
+        class lib:  # noqa: N801
+            @staticmethod
+            def unetb200_load_weights_ex(*a):
+                _Ctx.calls += 1
+                return 0
+
+        @staticmethod
+        def check(rc, what):
+            assert rc == 0
+
+    m._sync_weights(_Ctx, 0)
+    assert _Ctx.calls == 1
+    m._sync_weights(_Ctx, 0)
+    assert _Ctx.calls == 1                      # nothing changed: no re-pack
+    with torch.no_grad():
+        m.encoder.conv1.weight.add_(1.0)        # what optimizer.step() does
+    m._sync_weights(_Ctx, 0)
+    assert _Ctx.calls == 2
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    for p in m.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    m._sync_weights(_Ctx, 0)
+    assert _Ctx.calls == 3
+    with torch.no_grad():
+        m.encoder.bn1.running_var.mul_(2.0)     # buffers too (eval-mode fold)
+    m.eval()
+    m._sync_weights(_Ctx, 0)
+    assert _Ctx.calls == 4
+
+
+def test_deepcopy_and_pickle_keep_the_flat_layout():
+    """EMA / best-model snapshots: copy.deepcopy(model) and torch.save(model) must work and must not share (or
+    double-free) the native context; the copy's parameters are again views of ONE flat array."""
+    import copy
+    import io
+
+    m = vb.Unet("resnet34")
+    m._ctx = object()            # pretend a forward created the native context (a ctypes handle cannot be pickled)
+    m._packed_version = (1, 2, 3)
+    c = copy.deepcopy(m)
+    assert c._ctx is None and c._packed_version is None and m._ctx is not None
+    assert c.encoder.conv1.weight.data_ptr() == c.flat_params.data_ptr() != m.flat_params.data_ptr()
+    assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))
+    with torch.no_grad():
+        c.segmentation_head._modules["0"].bias.fill_(3.0)
+    assert float(c.flat_params[-1]) == 3.0 and float(m.flat_params[-1]) == 0.0
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert r._ctx is None and r.encoder.conv1.weight.data_ptr() == r.flat_params.data_ptr()
+    assert all(torch.equal(a, b) for a, b in zip(r.state_dict().values(), m.state_dict().values()))
 
 
 def test_shim_exposes_the_two_smp_symbols():

@@ -40,6 +40,9 @@ def _proto(lib):
         "unetb200_infer_host_u8_submit": (i32, [vp, i32, vp, i32, P(f32), P(f32), vp, vp, vp, f32, i32]),
         "unetb200_forward_infer_u8": (i32, [vp, vp, i32, P(f32), P(f32), vp, vp, vp, f32, i32, vp]),
         "unetb200_infer_launch_count": (i32, [vp, i32]),
+        "unetb200_infer_debug_count": (i32, [vp, i32]),
+        "unetb200_infer_debug_info": (i32, [vp, i32, i32, C.c_char_p, i32, P(i32)]),
+        "unetb200_infer_debug_copy": (i32, [vp, i32, i32, vp, i64, vp]),
         "unetb200_profile_infer": (i32, [vp, vp, vp, i32, vp, P(f32), P(i32), i32, P(i32)]),
         "unetb200_profile_name": (i32, [vp, i32, i32, C.c_char_p, i32]),
         "unetb200_conv_nhwc": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -210,6 +210,33 @@ int unetb200_infer_launch_count(unetb200_ctx* h, int N) {
     return it == h->c->infer_plans.end() ? -1 : it->second.launches;
 }
 
+int unetb200_infer_debug_count(unetb200_ctx* h, int N) {
+    auto it = h->c->infer_plans.find(N);
+    return it == h->c->infer_plans.end() ? -1 : (int)it->second.dbg.size();
+}
+int unetb200_infer_debug_info(unetb200_ctx* h, int N, int index, char* name_out, int name_cap, int shape_out[4]) {
+    auto it = h->c->infer_plans.find(N);
+    if (it == h->c->infer_plans.end() || index < 0 || index >= (int)it->second.dbg.size()) return 1;
+    const Ctx::InferPlan::Dbg& d = it->second.dbg[index];
+    if (name_out && name_cap > 0) {
+        strncpy(name_out, d.name.c_str(), name_cap - 1);
+        name_out[name_cap - 1] = 0;
+    }
+    if (shape_out) { shape_out[0] = d.n; shape_out[1] = d.h; shape_out[2] = d.w; shape_out[3] = d.c; }
+    return 0;
+}
+int unetb200_infer_debug_copy(unetb200_ctx* h, int N, int index, void* dst_dev, long long cap_bytes, void* stream) {
+    Ctx* ctx = h->c;
+    auto it = ctx->infer_plans.find(N);
+    if (it == ctx->infer_plans.end() || index < 0 || index >= (int)it->second.dbg.size())
+        return ctx_fail(ctx, "infer_debug_copy: bad index (run a forward at this batch size first)");
+    const Ctx::InferPlan::Dbg& d = it->second.dbg[index];
+    const long long bytes = (long long)d.n * d.h * d.w * d.c * 2;
+    if (bytes > cap_bytes) return ctx_fail(ctx, "infer_debug_copy: destination too small");
+    UB_CUDA(cudaMemcpyAsync(dst_dev, d.ptr, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 int unetb200_profile_infer(unetb200_ctx* h, const float* x_dev, float* logits_dev, int N, void* stream, float* ms_out,
                            int* is_igemm_out, int cap, int* n_out) {
     Ctx* ctx = h->c;

@@ -221,6 +221,9 @@ struct Ctx {
         };
         std::vector<Step> steps;  // everything between input pack and head
         int launches = 0;
+        // named activations of this plan (NHWC bf16) for the layer-local parity tests (unetb200_infer_debug_*)
+        struct Dbg { std::string name; const void* ptr; int n, h, w, c; };
+        std::vector<Dbg> dbg;
     };
     std::map<int, InferPlan> infer_plans;  // keyed by batch size
     // staging for the host-buffer entry points (unetb200_infer_host / _submit / _wait): two slots, so that the H2D
@@ -371,6 +374,8 @@ inline std::string ctx_build_pack_tables(Ctx* ctx) {
 inline int ctx_load_weights(Ctx* ctx, const float* params, const float* buffers, cudaStream_t st, bool fold_bn = true) {
     const NetSpec& S = ctx->spec;
     const ConvRef& hc = S.convs[S.head];
+    // a forward enqueued on another stream (the host-slot pipeline's io_stream) may still be reading the operand caches
+    if (ctx->arena_used && ctx->arena_stream != st) UB_CUDA(cudaStreamWaitEvent(st, ctx->arena_event, 0));
     UB_CUDA(cudaMemcpyAsync(ctx->head_w, params + hc.w, 145 * sizeof(float), cudaMemcpyDeviceToDevice, st));  // weight + bias
     UB_CUDA(ctx->fwd_pack.launch(params, ctx->wpk, st));
     if (fold_bn) {
@@ -510,6 +515,10 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
     const bool dry = (ctx->arena == nullptr);
     plan.N = N;
     plan.steps.clear();
+    plan.dbg.clear();
+    auto reg = [&](const std::string& nm, const void* p, int hh, int ww, int c) {
+        if (!dry) plan.dbg.push_back({nm, p, N, hh, ww, c});
+    };
     auto fold = [&](int bn, int relu) {
         EpilogueDesc ep;
         ep.scale = ctx->fold_scale + S.bns[bn].fold;
@@ -558,6 +567,8 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
 
     plan.xp = A.take((long long)N * H * (W + 8) * 4 + 64);  // + 128 B of slack: see tconv_build_stem
     __nv_bfloat16* f1 = A.take((long long)N * (H / 2) * (W / 2) * 64);
+    reg("xp", plan.xp, H, W + 8, 4);
+    reg("encoder.conv1.weight/out", f1, H / 2, W / 2, 64);
     if (!dry) {
         TconvLaunch TL;
         err = tconv_build_stem(TL, plan.xp, ctx->wpk + S.convs[S.stem].wpk, N, H, W, f1, fold(S.convs[S.stem].bn, 1),
@@ -567,6 +578,7 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
     }
     int h = H / 4, w = W / 4;
     __nv_bfloat16* cur = A.take((long long)N * h * w * 64);
+    reg("encoder.maxpool/out", cur, h, w, 64);
     if (!dry) {
         const int num_sms = ctx->num_sms;
         const int Hh = H / 2, Wh = W / 2;
@@ -587,6 +599,9 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
             __nv_bfloat16* o = A.take((long long)N * ho * wo * c1.cout);
             __nv_bfloat16* ident = cur;
             if (blk.ds >= 0) ident = A.take((long long)N * ho * wo * c1.cout);
+            reg(c1.name + "/out", t, ho, wo, c1.cout);
+            reg(c2.name + "/out", o, ho, wo, c1.cout);
+            if (blk.ds >= 0) reg(S.convs[blk.ds].name + "/out", ident, ho, wo, c1.cout);
             if (!dry) {
                 if (!(err = add_conv(c1, cur, h, w, t, fold(c1.bn, 1))).empty()) return err;
                 if (blk.ds >= 0) {
@@ -612,6 +627,9 @@ inline std::string build_infer_plan(Ctx* ctx, int N, Ctx::InferPlan& plan, size_
         __nv_bfloat16* t = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         __nv_bfloat16* o = A.take((long long)N * (2 * h) * (2 * w) * d.cout);
         __nv_bfloat16* r = (c1.tc == 3 || c1.tc == 4) ? A.take((long long)N * (2 * h) * (2 * w) * d.cout) : nullptr;
+        reg(c1.name + "/out", t, 2 * h, 2 * w, d.cout);
+        reg(c2.name + "/out", o, 2 * h, 2 * w, d.cout);
+        if (r) reg(c1.name + "/up", r, 2 * h, 2 * w, d.cout);   // scale * conv over the up-sampled channels (bf16)
         if (!dry) {
             if (c1.tc == 4) {
                 // wide blocks: launch 1 = wpconv (scale * parity-folded conv of the up-sampled channels on the low-res

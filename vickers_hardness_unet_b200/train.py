@@ -28,13 +28,19 @@ class _UnetTrainFn(torch.autograd.Function):
                                                  flat["b"].data_ptr(), flat["c"].data_ptr(), g.data_ptr(), N,
                                                  _stream(x)), "train_forward")
         model._buffers_epoch += 1  # running statistics changed behind PyTorch's back: eval must re-fold BatchNorm
-        fctx.model, fctx.N = model, N
+        model._fwd_seq += 1        # the arena now holds THIS forward's activations
+        fctx.model, fctx.N, fctx.seq = model, N, model._fwd_seq
         return logits
 
     @staticmethod
     def backward(fctx, dlogits):
         model, N = fctx.model, fctx.N
         ctx = model._ctx
+        if fctx.seq != model._fwd_seq:
+            raise _lib.UnetB200Error(
+                "backward of a train-mode forward that is not the latest one: the library keeps the activations of ONE "
+                "forward (one arena per model); call loss.backward() before the next model(x) in train() mode, or run "
+                "the extra forward under model.eval() / on a copy of the model")
         dl = dlogits.detach().to(torch.float32).contiguous()
         g = model._grad_buffer()
         params = list(model.parameters())
@@ -119,46 +125,3 @@ def bce_dice(logits, target, eps: float = 1e-7):
 
 def dice_loss(logits, target, eps: float = 1e-7):
     return _BceDiceFn.apply(logits, target, eps)[1]
-
-
-# ------------------------------------------------------------------------------------------------ smoke
-def smoke_train_step(m, o):
-    """One tiny train step on cuda:0 against the fp32 CPU oracle (called by __graft_entry__.smoke)."""
-    import copy
-
-    import torch.nn.functional as F
-
-    from . import losses
-    from oracle import OracleDiceLoss  # smoke() is one of the places allowed to use the oracle
-
-    o = copy.deepcopy(o).train()
-    for mod in o.modules():
-        if isinstance(mod, torch.nn.BatchNorm2d):
-            mod.momentum = 0.1
-    m.load_state_dict(o.state_dict(), strict=True)
-    m.train()
-    g = torch.Generator().manual_seed(3)
-    x = torch.randn(2, 3, 64, 64, generator=g)
-    y = (torch.rand(2, 1, 64, 64, generator=g) < 0.2).float()
-    lo = o(x)
-    loss_o = F.binary_cross_entropy_with_logits(lo, y) + OracleDiceLoss()(lo, y)
-    loss_o.backward()
-    lg = m(x.cuda())
-    loss_g = losses.BCEDiceLoss()(lg, y.cuda())
-    loss_g.backward()
-    rel = abs(float(loss_g) - float(loss_o)) / abs(float(loss_o))
-    # whole-network gradients of a random-init net are chaotic under bf16 rounding (tests/test_gpu_train_local.py checks
-    # every backward kernel on its own inputs); here: the tensors next to the loss must agree, all must be finite
-    cos = {}
-    for (n1, p1), (n2, p2) in zip(o.named_parameters(), m.named_parameters()):
-        a, b = p1.grad, p2.grad.cpu()
-        if not torch.isfinite(b).all():
-            raise RuntimeError(f"smoke: non-finite gradient in {n2}")
-        cos[n1] = float((a * b).sum() / (a.norm() * b.norm() + 1e-20))
-    head = min(cos["segmentation_head.0.weight"], cos["segmentation_head.0.bias"], cos["decoder.blocks.4.conv2.1.weight"])
-    print(f"smoke: train loss cuda {float(loss_g):.5f} oracle {float(loss_o):.5f} (rel {rel:.2e}); "
-          f"head / last-BN grad cosine {head:.5f}; median cosine over 140 tensors {sorted(cos.values())[70]:.3f}")
-    if rel > 5e-3 or head < 0.999:
-        raise RuntimeError("smoke: train step differs from the oracle")
-    if m._ctx.device_error_flag() != 0:
-        raise RuntimeError("smoke: device pipeline watchdog fired")

@@ -39,6 +39,31 @@ def _init_tensor(name: str, t: torch.Tensor):
         t.zero_()  # BatchNorm beta / head bias
 
 
+def _find_resnet34_checkpoint() -> str:
+    """`encoder_weights="imagenet"` (/root/reference/train.py:753,595) without a download: a torchvision-format
+    resnet34 state_dict on local disk — $UNETB200_RESNET34_WEIGHTS or torch hub's checkpoint cache (where smp /
+    torchvision would have put `resnet34-*.pth`)."""
+    import glob
+    import os
+
+    cands = []
+    env = os.environ.get("UNETB200_RESNET34_WEIGHTS")
+    if env:
+        cands.append(env)
+    try:
+        hub = torch.hub.get_dir()
+    except Exception:  # pragma: no cover
+        hub = os.path.expanduser("~/.cache/torch/hub")
+    cands += sorted(glob.glob(os.path.join(hub, "checkpoints", "resnet34-*.pth")))
+    for c in cands:
+        if os.path.isfile(c):
+            return c
+    raise FileNotFoundError(
+        "encoder_weights='imagenet' needs a local torchvision-format resnet34 checkpoint (there is no network "
+        "download here): set UNETB200_RESNET34_WEIGHTS=/path/to/resnet34-b627a593.pth or place the file in "
+        f"{os.path.join(hub, 'checkpoints')}; or pass encoder_weights=None and load a state_dict")
+
+
 class Unet(nn.Module):
     def __init__(self, encoder_name: str = "resnet34", encoder_depth: int = 5, encoder_weights=None,
                  decoder_use_batchnorm: bool = True, decoder_channels=(256, 128, 64, 32, 16),
@@ -47,10 +72,9 @@ class Unet(nn.Module):
         super().__init__()
         if encoder_name != "resnet34":
             raise ValueError(f"unet_b200 implements encoder_name='resnet34' only (got {encoder_name!r})")
-        if encoder_weights is not None:
-            raise ValueError(
-                "encoder_weights must be None: pretrained ImageNet weights need a network download; "
-                "load a state_dict instead (key layout is identical to smp)")
+        if encoder_weights not in (None, "imagenet"):
+            raise ValueError(f"encoder_weights must be None or 'imagenet' (got {encoder_weights!r})")
+        pretrained = _find_resnet34_checkpoint() if encoder_weights == "imagenet" else None
         if (encoder_depth != 5 or tuple(decoder_channels) != (256, 128, 64, 32, 16) or not decoder_use_batchnorm
                 or decoder_attention_type is not None or in_channels != 3 or classes != 1
                 or activation is not None or aux_params is not None):
@@ -91,7 +115,43 @@ class Unet(nn.Module):
         self._buffers_epoch = 0  # bumped when the library updates the BatchNorm running statistics (train forward)
         self._grad_views = None
         self._dp = None          # distributed.GradBucketReducer when data parallelism is enabled
+        self._fwd_seq = 0        # id of the last train-mode forward (its activations are the ones in the arena)
+        self._param_list = None
         self.name = "u-resnet34"
+        if pretrained is not None:
+            self._load_torchvision_encoder(pretrained)
+
+    def _load_torchvision_encoder(self, path: str):
+        """Copy a torchvision resnet34 state_dict (keys `conv1.weight`, `layer1.0.bn1.running_mean`, ..., `fc.*`) into
+        `encoder.*`, as smp's ResNetEncoder.load_state_dict does (it drops `fc.weight` / `fc.bias`)."""
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        sd = {k: v for k, v in sd.items() if not k.startswith("fc.")}
+        own = {k[len("encoder."):]: v for k, v in self.state_dict().items() if k.startswith("encoder.")}
+        missing = sorted(set(own) - set(sd))
+        unexpected = sorted(set(sd) - set(own))
+        if missing or unexpected:
+            raise RuntimeError(f"{path} is not a torchvision resnet34 state_dict: missing {missing[:4]}, "
+                               f"unexpected {unexpected[:4]}")
+        with torch.no_grad():
+            for k, v in sd.items():
+                own[k].copy_(v)
+
+    # ------------------------------------------------------------------ copying / pickling (EMA, torch.save(model))
+    def __getstate__(self):
+        """The native context (a ctypes handle) and everything derived from it stay behind: a copy re-creates its own
+        context at its first forward.  Makes copy.deepcopy(model) and torch.save(model) work after a forward."""
+        st = self.__dict__.copy()
+        st["_ctx"] = None
+        st["_dp"] = None
+        st["_packed_version"] = None
+        st["_grad_views"] = None
+        st["_param_list"] = None
+        st["_flat"] = {k: v for k, v in self._flat.items() if k != "g"}
+        return st
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reflatten()   # parameters / buffers back to views of ONE flat array each
 
     # ------------------------------------------------------------------ flat storage upkeep
     def _apply(self, fn, recurse=True):
@@ -124,6 +184,7 @@ class Unet(nn.Module):
         self._flat = flat
         self._packed_version = None
         self._grad_views = None
+        self._param_list = None
         for p in self.parameters():
             p.grad = None
         if self._ctx is not None and self._ctx.device != (dev.index if dev.type == "cuda" else -1):
@@ -181,8 +242,12 @@ class Unet(nn.Module):
         """Refresh the library's bf16 operand caches when the master tensors changed.  fold_bn: also fold eval-mode
         BatchNorm (default: only in eval mode — a training step normalises with batch statistics)."""
         fold_bn = (not self.training) if fold_bn is None else fold_bn
-        ver = (self._flat["p"]._version, self._flat["b"]._version, id(ctx), self._params_epoch,
-               self._buffers_epoch if fold_bn else -1)
+        # `p.data = view` (_reflatten) leaves every Parameter with its OWN version counter, so an in-place update through
+        # the parameter (torch.optim.AdamW, p.add_()) does not bump the flat tensor's version: sum the per-tensor ones
+        if self._param_list is None:
+            self._param_list = list(self.parameters()) + [b for b in self.buffers() if b.dtype == torch.float32]
+        ver = (self._flat["p"]._version, self._flat["b"]._version, sum(t._version for t in self._param_list), id(ctx),
+               self._params_epoch, self._buffers_epoch if fold_bn else -1)
         if ver != self._packed_version:
             ctx.check(ctx.lib.unetb200_load_weights_ex(ctx.handle, self._flat["p"].data_ptr(),
                                                        self._flat["b"].data_ptr(), int(not fold_bn), stream),

@@ -6,7 +6,8 @@
 One JSON line on stdout (rank 0).  N=1 workload = BASELINE.json configs[1]: batch-32 bf16 inference at 512x512.
 A "step" is one forward pass of the whole network over one batch of synthetic inputs.
   value     images/s with the fp32 NCHW input batch already resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the C-ABI host-buffer call (pinned host input -> H2D -> forward -> D2H of the uint8 mask)
+  e2e       same metric through the C-ABI host-buffer call (pinned uint8 frame -> H2D -> normalise + forward -> D2H of the
+            uint8 mask); the fp32-frame form of the call is reported beside it
   roofline  the conv stack (all wconv / tconv / wpconv / igemm launches of one step) against the measured dense bf16 peak
             (MEASURED_PEAKS.json); roofline.per_layer bounds every launch by max(FLOPs / peak, min bytes / HBM copy bandwidth)
   cpu_baseline  the fp32 CPU oracle timed on this box's host cores on a bounded sample (rank 0, N=1)
@@ -30,6 +31,14 @@ sys.path.insert(0, ROOT)
 GFLOP_FWD_512 = 62.512  # algorithmic forward GFLOP / image @512x512 (scales with H*W)
 
 
+def workload_config(B, S, world):
+    """`config` of the JSON line: the SAME dict for both arms (`--impl ours` and `--impl reference`)."""
+    return {"workload": f"Unet(resnet34) {S}x{S} batch-{B}/GPU inference, random-init seed 42 (BASELINE configs[1])",
+            "weights": "random-init seed 42", "input": "fp32 NCHW randn, 2 batches alternated",
+            "l2": "per-step working set >> 126 MB L2 (inputs larger than L2)",
+            "parallelism": f"batch-sharded replicas x{world}, no collective"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,6 +49,7 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--profile-out", default="", help="write the per-launch timing table here (rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock PyTorch/cuDNN timing on this GPU")
     ap.add_argument("--train-batch", type=int, default=16, help="images per GPU per train step (BASELINE configs[2])")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step measurement")
     ap.add_argument("--train-profile-out", default="", help="write the per-launch timing table of one train step here")
@@ -115,6 +125,73 @@ def cpu_oracle_rate(size: int, batch: int, budget_s: float, threads: int):
             ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     return batch / med, n, med
+
+
+def library_baseline(a, dev):
+    """The "library bar" (BASELINE.md section 3): what the reference's user gets today by typing
+    `.to("cuda")` (train.py:592, infer_pth_gui.py:92) — stock PyTorch eager on cuDNN, same B200, same run, same shapes.
+    The smp model is stood in for by the oracle restatement (smp is not installable offline).  Variants:
+      fp32            torch defaults (cuDNN may use TF32 for convs), NCHW            — infer_pth_gui.py:50 as written
+      amp_fp16        autocast(float16) NCHW (+ GradScaler for the train step)      — train.py:431-449 as written
+      bf16_cl         autocast(bfloat16) + channels_last                            — the strongest stock configuration
+    CUDA events, 3 warm-up + 10 timed steps each.  Returns the `library_baseline` object of the JSON line."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import OracleDiceLoss, build_oracle
+
+    B, TB, S = a.batch, a.train_batch, a.size
+    g = torch.Generator(device=dev).manual_seed(7)
+
+    def timeit(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    out = {"what": "stock PyTorch eager (cuDNN %s) on the oracle restatement of smp.Unet, this GPU, this run" %
+                   str(torch.backends.cudnn.version()), "infer": {}, "train": {}}
+    variants = [("fp32", None, False), ("amp_fp16", torch.float16, False), ("bf16_cl", torch.bfloat16, True)]
+    for tag, dt, cl in variants:
+        m = build_oracle(42).to(dev).eval()
+        x = torch.randn(B, 3, S, S, device=dev, generator=g)
+        if cl:
+            m = m.to(memory_format=torch.channels_last)
+            x = x.contiguous(memory_format=torch.channels_last)
+
+        def infer():
+            with torch.no_grad(), torch.autocast("cuda", dtype=dt or torch.float16, enabled=dt is not None):
+                return m(x)
+        ms = timeit(infer)
+        out["infer"][tag] = {"images_per_s": B / (ms * 1e-3), "ms_per_step": ms, "batch": B}
+        del x
+        m.train()
+        opt = torch.optim.AdamW(m.parameters(), lr=5e-5, weight_decay=1e-4)
+        scaler = torch.amp.GradScaler("cuda", enabled=dt is torch.float16)
+        dice = OracleDiceLoss()
+        xt = torch.randn(TB, 3, S, S, device=dev, generator=g)
+        yt = (torch.rand(TB, 1, S, S, device=dev, generator=g) < 0.05).float()
+        if cl:
+            xt = xt.contiguous(memory_format=torch.channels_last)
+
+        def train_step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=dt or torch.float16, enabled=dt is not None):
+                lg = m(xt)
+                loss = F.binary_cross_entropy_with_logits(lg.float(), yt) + dice(lg.float(), yt)
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+        ms = timeit(train_step)
+        out["train"][tag] = {"images_per_s": TB / (ms * 1e-3), "ms_per_step": ms, "batch": TB}
+        del m, opt, xt, yt
+        torch.cuda.empty_cache()
+    return out
 
 
 def bench_train(a, dev, rank, world, barrier):
@@ -200,12 +277,17 @@ def bench_train(a, dev, rank, world, barrier):
     ctx = model._ctx
     nf, nb = ctypes.c_int(), ctypes.c_int()
     ctx.lib.unetb200_train_launch_count(ctx.handle, B, ctypes.byref(nf), ctypes.byref(nb))
+    dp_par = None
+    if world > 1:
+        # multi-GPU correctness inside the bench line: reduced gradients vs the sliced-average emulation on rank 0
+        rel, mx, same = vb.distributed.dp_gradient_parity(dev, rank, world)
+        dp_par = {"dp_parity_rel_l2": rel, "dp_parity_max_abs": mx, "dp_grads_identical_across_ranks": same}
     pk, pk_kind = peaks()
     gflop = 186.3 * (S * S) / (512 * 512)  # algorithmic train-step GFLOP / image
     val = world * B * steps / (ms * 1e-3)
     tf = gflop * B * steps / (ms * 1e-3) / 1e3
     return {"metric": "images_per_sec_train_512", "value": val, "unit": "images/s", "ms_per_step": ms / steps,
-            "steps": steps, "batch_per_gpu": B, "loss": lv,
+            "steps": steps, "batch_per_gpu": B, "loss": lv, **(dp_par or {}),
             "workload": f"Unet(resnet34) {S}x{S} train step BCE+Dice + fused AdamW, batch {B}/GPU (BASELINE configs[2])",
             "parallelism": f"dp{world}: bucketed NCCL all-reduce (4 buckets) overlapped with backward" if world > 1
             else "single GPU, no collective",
@@ -223,7 +305,7 @@ def run_reference(a, rank):
         return
     import torch
     threads = os.cpu_count() or 1
-    sb = min(a.batch, 8)  # bounded sample of the batch-32 step
+    sb = a.batch  # the full batch of the workload: one reference step == one step of our arm
     torch.set_num_threads(threads)
     from oracle import build_oracle
     m = build_oracle(42).eval()
@@ -236,13 +318,14 @@ def run_reference(a, rank):
             m(x)
         dt = time.perf_counter() - t0
     val = sb * a.steps / dt
-    sample = f"{sb} of {a.batch} images per step, {a.steps} steps, fp32 oracle forward (eval, no_grad), {threads} threads"
+    sample = (f"all {sb} images of every step, {a.steps} steps after {max(1, min(a.warmup, 3))} warm-up, fp32 oracle "
+              f"forward (eval, no_grad) on the host, {threads} torch threads")
     print(json.dumps({
         "impl": "reference", "metric": "images_per_sec_infer_512", "value": val, "unit": "images/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Unet(resnet34) {a.size}x{a.size} batch-{a.batch} inference (configs[1])",
-                   "weights": "random-init seed 42"},
+        "config": workload_config(a.batch, a.size, a.gpus),
+        "arm": "reference CPU path: fp32 PyTorch eager on the host cores (infer_pth_gui.py:50-51 on the oracle port)",
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -308,6 +391,24 @@ def main():
         ms = float(t.item())
     value = world * B * a.steps / (ms * 1e-3)
 
+    # ---- sustained: the same step back to back for >= 3 s (clocks sampled by the sampler that is still running), so that
+    # a fraction of the SUSTAINED peak in MEASURED_PEAKS.json is like for like
+    n_sus = max(a.steps, int(3000.0 / (ms / a.steps)) + 1)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    s0.record()
+    for i in range(n_sus):
+        step(i)
+    s1.record()
+    barrier()
+    sus_ms = s0.elapsed_time(s1)
+    if world > 1:
+        t = torch.tensor([sus_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sus_ms = float(t.item())
+    sustained = {"value": world * B * n_sus / (sus_ms * 1e-3), "unit": "images/s", "steps": n_sus,
+                 "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus}
+
     # ---- end to end through the C-ABI host-buffer entry points (pinned host buffers; every step's H2D copy of its
     # input and D2H copy of its result are inside the timed region).  Headline: the two-slot submit / wait form a caller
     # streaming frames uses (request k+1 uploads while request k computes); also the single blocking call and the
@@ -368,10 +469,13 @@ def main():
                "sample": f"fp32 oracle forward, batch 1 @ {S}x{S}, median of {n} runs ({med * 1e3:.0f} ms each), "
                          f"{thr} torch threads on {os.cpu_count()} host cores"}
     train = None
+    lib_bar = None
     if not a.no_train:
         del xs, xh, x8h
         torch.cuda.empty_cache()
         train = bench_train(a, dev, rank, world, barrier)
+    if rank == 0 and world == 1 and not a.no_library_baseline:
+        lib_bar = library_baseline(a, dev)
     if rank == 0:
         gflop = GFLOP_FWD_512 * (S * S) / (512 * 512)
         whole_tf = gflop * B * a.steps / (ms * 1e-3) / 1e3  # whole step, per GPU
@@ -404,18 +508,28 @@ def main():
             "metric": "images_per_sec_infer_512", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"Unet(resnet34) {S}x{S} batch-{B}/GPU bf16 inference (BASELINE configs[1])",
-                       "weights": "random-init seed 42", "input": "fp32 NCHW randn, 2 batches alternated",
-                       "l2": "per-step working set >> 126 MB L2 (inputs larger than L2)",
-                       "parallelism": f"batch-sharded replicas x{world}, no collective"},
-            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
+            "config": workload_config(B, S, world),
+            "arm": "B200 path: bf16 operands, fp32 accumulate (libunetb200.so)",
+            # headline end-to-end call: the uint8 camera frame the reference's callers hold (cv2.imread / letterbox,
+            # infer_pth_gui.py:45-46) goes in, the uint8 mask comes out; BGR->RGB, /255, (x-mean)/std run on the device
+            "e2e": {"value": e2e_u8, "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S,
                     "d2h_bytes_per_step": B * S * S,
-                    "call": "unetb200_infer_host_submit/_wait, 2 slots (pinned fp32 NCHW in, uint8 mask out)",
-                    "blocking_call": {"value": e2e_sync, "call": "unetb200_infer_host (one request at a time)"},
-                    "uint8_frames": {"value": e2e_u8, "h2d_bytes_per_step": B * 3 * S * S,
-                                     "call": "unetb200_infer_host_u8_submit/_wait (uint8 HWC in, normalise on device)"}},
-            "gpu_launches": launches * a.steps, "roofline": roof, "clocks": clocks,
+                    "call": "unetb200_infer_host_u8_submit/_wait, 2 slots (pinned uint8 HWC frames in, normalise on "
+                            "device, uint8 mask out)",
+                    "fp32_frames": {"value": e2e_val, "h2d_bytes_per_step": B * 3 * S * S * 4,
+                                    "call": "unetb200_infer_host_submit/_wait (pinned fp32 NCHW in, host-normalised as "
+                                            "infer_pth_gui.py:46-49 does, uint8 mask out)"},
+                    "blocking_call": {"value": e2e_sync, "call": "unetb200_infer_host (fp32 frames, one request at a time)"}},
+            "gpu_launches": launches * a.steps, "roofline": roof, "clocks": clocks, "sustained": sustained,
         }
+        sus_tf = gflop * sustained["value"] / world / 1e3
+        out["sustained"]["whole_step_tflops"] = sus_tf
+        out["sustained"]["frac_of_sustained_peak"] = sus_tf / pk["bf16_tflops_sustained"]
+        if lib_bar:
+            lib_bar["speedup_vs_best_library"] = {
+                "infer": value / max(v["images_per_s"] for v in lib_bar["infer"].values()),
+                "train": (train["value"] / max(v["images_per_s"] for v in lib_bar["train"].values())) if train else None}
+            out["library_baseline"] = lib_bar
         if cpu:
             out["cpu_baseline"] = cpu
         if train:

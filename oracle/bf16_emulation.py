@@ -38,7 +38,19 @@ def _r(t: torch.Tensor) -> torch.Tensor:
     return _RoundSTE.apply(t)
 
 
-def _dec_conv1_parity(x_low, skip, w, cup, round_up_part=False):
+def round_mantissa(t: torch.Tensor, bits: int) -> torch.Tensor:
+    """fp32 -> `bits` explicit mantissa bits, round-to-nearest-even, fp32 exponent range (bits = 7 is bf16, 10 is
+    fp16 / tf32 precision, 15 is a bf16 hi + lo pair, 23 is the identity).  Used by the precision sweep that answers
+    "how many mantissa bits does the north_star logit tolerance need" (tests/test_gpu_trained.py)."""
+    if bits >= 23:
+        return t
+    sh = 23 - bits
+    i = t.contiguous().view(torch.int32)
+    i = ((i + ((1 << (sh - 1)) - 1) + ((i >> sh) & 1)) >> sh) << sh
+    return i.view(torch.float32)
+
+
+def _dec_conv1_parity(x_low, skip, w, cup, round_up_part=False, _r=_r):
     """cat(nearest2x(x_low), skip) (*) w, computed as the CUDA path does: 4 output parities, summed 2x2 weights.
     round_up_part: the contribution of the up-sampled channels is stored in bf16 before the skip part is added (decoder
     block 3: two tconv launches, csrc/unet.cuh tc == 3)."""
@@ -73,8 +85,13 @@ SPLIT_DECODER_BLOCKS = (3,)
 SPLIT_DECODER_BLOCKS_EVAL = (0, 1, 2, 3)
 
 
-def emulated_forward(o, x, train: bool):
+def emulated_forward(o, x, train: bool, rnd=None, taps=None):
     """Forward of oracle `o` with the CUDA path's bf16 rounding points.
+
+    rnd : the rounding applied at those points (default: bf16 with a straight-through gradient; `lambda t: t` gives the
+          plain fp32 oracle forward, `lambda t: round_mantissa(t, k)` a k-bit-mantissa storage format).
+    taps: optional dict that receives the named activations the CUDA path materialises ("<conv weight key>/out",
+          "encoder.maxpool/out"), for the per-layer error-growth report.
 
     eval : BatchNorm folded into the conv epilogue: a = bf16(relu(acc*scale + shift (+ identity)))
     train: raw conv output stored first, z = bf16(acc); batch statistics are taken from the ROUNDED z; then
@@ -87,25 +104,36 @@ def emulated_forward(o, x, train: bool):
             return F.batch_norm(_r(t), m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
         return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, m.eps)
 
+    _r = rnd if rnd is not None else globals()["_r"]
+
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t.detach()
+        return t
+
     e = o.encoder
     x = _r(x)
-    f1 = _r(F.relu(bn(F.conv2d(x, _r(e.conv1.weight), None, 2, 3), e.bn1)))
-    t = F.max_pool2d(f1, 3, 2, 1)
+    f1 = tap("encoder.conv1.weight/out", _r(F.relu(bn(F.conv2d(x, _r(e.conv1.weight), None, 2, 3), e.bn1))))
+    t = tap("encoder.maxpool/out", F.max_pool2d(f1, 3, 2, 1))
     feats = [f1]
-    for layer in (e.layer1, e.layer2, e.layer3, e.layer4):
-        for blk in layer:
+    for li, layer in enumerate((e.layer1, e.layer2, e.layer3, e.layer4)):
+        for bi, blk in enumerate(layer):
+            pre = f"encoder.layer{li + 1}.{bi}"
             idn = t
-            u = _r(F.relu(bn(F.conv2d(t, _r(blk.conv1.weight), None, blk.stride, 1), blk.bn1)))
+            u = tap(pre + ".conv1.weight/out", _r(F.relu(bn(F.conv2d(t, _r(blk.conv1.weight), None, blk.stride, 1), blk.bn1))))
             if blk.downsample is not None:
-                idn = _r(bn(F.conv2d(t, _r(blk.downsample[0].weight), None, blk.stride, 0), blk.downsample[1]))
-            t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2.weight), None, 1, 1), blk.bn2) + idn))
+                idn = tap(pre + ".downsample.0.weight/out",
+                          _r(bn(F.conv2d(t, _r(blk.downsample[0].weight), None, blk.stride, 0), blk.downsample[1])))
+            t = tap(pre + ".conv2.weight/out", _r(F.relu(bn(F.conv2d(u, _r(blk.conv2.weight), None, 1, 1), blk.bn2) + idn)))
         feats.append(t)
     skips = [feats[3], feats[2], feats[1], feats[0], None]
     cups = [512, 256, 128, 64, 32]
     for i, blk in enumerate(o.decoder.blocks):
-        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i], round_up_part=i in (SPLIT_DECODER_BLOCKS if train else SPLIT_DECODER_BLOCKS_EVAL))
-        u = _r(F.relu(bn(z, blk.conv1[1])))
-        t = _r(F.relu(bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1])))
+        z = _dec_conv1_parity(t, skips[i], blk.conv1[0].weight, cups[i],
+                              round_up_part=i in (SPLIT_DECODER_BLOCKS if train else SPLIT_DECODER_BLOCKS_EVAL), _r=_r)
+        u = tap(f"decoder.blocks.{i}.conv1.0.weight/out", _r(F.relu(bn(z, blk.conv1[1]))))
+        t = tap(f"decoder.blocks.{i}.conv2.0.weight/out",
+                _r(F.relu(bn(F.conv2d(u, _r(blk.conv2[0].weight), None, 1, 1), blk.conv2[1]))))
     head = o.segmentation_head[0]
     return F.conv2d(t, head.weight, head.bias, 1, 1)
 

@@ -69,3 +69,49 @@ def shard_batch(n_total: int, rank: int, world: int):
     per, rem = divmod(n_total, world)
     b = rank * per + min(rank, rem)
     return b, b + per + (1 if rank < rem else 0)
+
+
+def dp_gradient_parity(dev, rank: int, world: int, batch: int = 2, size: int = 128):
+    """Multi-GPU correctness self-check (needs an initialised NCCL group, one process per GPU): the all-reduced gradients
+    of ONE data-parallel step must equal the single-process emulation "run every rank's batch slice separately on one
+    GPU, average the flat gradients" (DDP semantics) and must be bit-identical on every rank.
+    Returns (rel_l2, max_abs, identical_across_ranks) on every rank.  Used by scripts/dp_check.py, tests/test_gpu_dp.py
+    and bench.py (`train.dp_parity_rel_l2`), so that every multi-GPU bench line carries its own correctness figure."""
+    from . import losses
+    from .unet import Unet
+
+    torch.manual_seed(42 + rank)  # deliberately different init per rank: enable_data_parallel must broadcast rank 0's
+    model = Unet("resnet34").to(dev).train()
+    enable_data_parallel(model)
+    crit = losses.BCEDiceLoss()
+    g = torch.Generator().manual_seed(99)
+    X = torch.randn(world * batch, 3, size, size, generator=g)
+    Y = (torch.rand(world * batch, 1, size, size, generator=g) < 0.1).float()
+    b, e = shard_batch(world * batch, rank, world)
+    p0 = model.flat_params.clone()
+    buf0 = model.flat_buffers.clone()
+    crit(model(X[b:e].to(dev)), Y[b:e].to(dev)).backward()
+    torch.cuda.synchronize(dev)
+    got = model.flat_grads.clone()
+    ref0 = got.clone()
+    dist.broadcast(ref0, 0)
+    same = torch.tensor([int(torch.equal(ref0, got))], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    out = torch.zeros(2, device=dev, dtype=torch.float64)
+    if rank == 0:
+        single = Unet("resnet34").to(dev).train()
+        acc = torch.zeros_like(got)
+        for r in range(world):
+            with torch.no_grad():
+                single.flat_params.copy_(p0)
+                single.flat_buffers.copy_(buf0)
+            single._params_epoch += 1
+            bb, ee = shard_batch(world * batch, r, world)
+            single.zero_grad(set_to_none=True)
+            crit(single(X[bb:ee].to(dev)), Y[bb:ee].to(dev)).backward()
+            acc += single.flat_grads
+        acc /= world
+        out[0] = float((got - acc).norm() / acc.norm())
+        out[1] = float((got - acc).abs().max())
+    dist.broadcast(out, 0)
+    return float(out[0]), float(out[1]), bool(int(same.item()))

@@ -252,28 +252,43 @@ def bench_train(a, dev, rank, world, barrier):
         step(xs[1], ys[1])
         ctx.check(ctx.lib.unetb200_profile_dump(ctx.handle, a.train_profile_out.encode()), "profile_dump")
         ctx.lib.unetb200_profile_enable(ctx.handle, 0)
-    # end to end: pinned host batch -> H2D -> step -> loss.item() (the D2H sync of train.py:452)
-    xh = [x.cpu().pin_memory() for x in xs]
-    yh = [y.cpu().pin_memory() for y in ys]
+    # end to end: pinned host batch -> H2D -> step -> loss.item() (the D2H sync of train.py:452).
     # vb.data.DevicePrefetcher: batch k+1 uploads on a side stream while batch k trains (every batch is still copied
-    # host -> device once per step, inside the timed region)
-    def host_batches(n):
-        for i in range(n):
-            yield xh[i & 1], yh[i & 1]
-    for xd, yd in vb.data.DevicePrefetcher(host_batches(2), dev):
-        step(xd, yd)
-        last["loss"].item()
-    barrier()
-    t0 = time.perf_counter()
-    for xd, yd in vb.data.DevicePrefetcher(host_batches(steps), dev):
-        step(xd, yd)
-        lv = last["loss"].item()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
+    # host -> device once per step, inside the timed region).  Headline: uint8 frames + uint8 masks as a data loader
+    # holds them after cv2.imread / letterbox (normalisation of train.py:108-112 on the device); beside it the
+    # reference-style fp32 host tensors (4x the bytes).
+    def e2e_run(xh, yh):
+        class _Loader:   # a re-iterable loader, like the DataLoader of train.py:585 (one pass = one "epoch")
+            n = 2
+
+            def __iter__(self):
+                for i in range(self.n):
+                    yield xh[i & 1], yh[i & 1]
+
+            def __len__(self):
+                return self.n
+        loader = _Loader()
+        pf = vb.data.DevicePrefetcher(loader, dev)   # ONE prefetcher (its device slots are reused across epochs)
+        for xd, yd in pf:
+            step(xd, yd)
+            last["loss"].item()
+        loader.n = steps
+        barrier()
+        t0 = time.perf_counter()
+        for xd, yd in pf:
+            step(xd, yd)
+            lv = last["loss"].item()
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, lv
+    e2e_f32_s, lv = e2e_run([x.cpu().pin_memory() for x in xs], [y.cpu().pin_memory() for y in ys])
+    gh = torch.Generator().manual_seed(99 + rank)
+    x8h = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=gh).pin_memory() for _ in range(2)]
+    y8h = [y.cpu().to(torch.uint8).pin_memory() for y in ys]
+    e2e_s, _ = e2e_run(x8h, y8h)
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device=dev)
+        t = torch.tensor([ms, e2e_s, e2e_f32_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s, e2e_f32_s = float(t[0]), float(t[1]), float(t[2])
     ctx = model._ctx
     nf, nb = ctypes.c_int(), ctypes.c_int()
     ctx.lib.unetb200_train_launch_count(ctx.handle, B, ctypes.byref(nf), ctypes.byref(nb))
@@ -292,7 +307,11 @@ def bench_train(a, dev, rank, world, barrier):
             "parallelism": f"dp{world}: bucketed NCCL all-reduce (4 buckets) overlapped with backward" if world > 1
             else "single GPU, no collective",
             "e2e": {"value": world * B * steps / e2e_s, "unit": "images/s",
-                    "h2d_bytes_per_step": B * 4 * S * S * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": B * 4 * S * S, "d2h_bytes_per_step": 4,
+                    "call": "DevicePrefetcher(pinned uint8 HWC frames + uint8 masks) -> model(frames) -> BCEDiceLoss -> "
+                            "backward -> FusedAdamW.step -> loss.item()",
+                    "fp32_frames": {"value": world * B * steps / e2e_f32_s, "h2d_bytes_per_step": B * 4 * S * S * 4,
+                                    "call": "same with host-normalised fp32 NCHW images + fp32 masks (train.py:428-434)"}},
             "phases": phases, "gpu_launches_per_step": nf.value + nb.value + 4,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": tf / pk["bf16_tflops_sustained"], "peak_kind": pk_kind,

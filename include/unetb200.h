@@ -119,6 +119,12 @@ int unetb200_conv_nhwc(unetb200_ctx* ctx, const void* in_bf16_dev, const float* 
  * unetb200_load_weights must have been called since the parameters last changed. */
 int unetb200_train_forward(unetb200_ctx* ctx, const float* x_dev, float* logits_dev, const float* params_dev,
                            float* buffers_dev, long long* counters_dev, float* grads_dev, int N, void* stream);
+/* Same with uint8 HWC frames [N,H,W,3] as the input (what cv2.imread / the letterbox of train.py:70-75 produce): BGR->RGB,
+ * /255 and (x - mean) / std of train.py:108-112 run inside the input pack, so a data loader ships 0.75 MB instead of
+ * 3 MB per 512x512 image to the GPU. */
+int unetb200_train_forward_u8(unetb200_ctx* ctx, const uint8_t* img_dev, int bgr, const float* mean3, const float* std3,
+                              float* logits_dev, const float* params_dev, float* buffers_dev, long long* counters_dev,
+                              float* grads_dev, int N, void* stream);
 /* loss.backward() through the network (train.py:443,448) given dL/dlogits fp32 [N,1,H,W].  The backward is cut into
  * 4 stages whose parameter gradients are complete when the stage ends (0 = head + decoder, 1 = encoder.layer4,
  * 2 = layer3, 3 = layer2 + layer1 + stem) so that a data-parallel caller can all-reduce bucket k while stage k+1 runs.

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../vickers_hardness_unet_b200/csrc/unet.cuh"
+#include "wconv2_glue.cuh"
 
 using namespace ub;
 

@@ -12,8 +12,8 @@
 // landed" reaches the leader through a forwarder thread (peer's otherwise idle MMA warp: wait own barrier -> remote
 // mbarrier.arrive on the leader's peer-full barrier); both CTAs' epilogue warps arrive on the leader's tempty barrier.
 #pragma once
-#include "hconv.cuh"
-#include "ptx.cuh"
+#include "../../vickers_hardness_unet_b200/csrc/hconv.cuh"
+#include "../../vickers_hardness_unet_b200/csrc/ptx.cuh"
 
 namespace ub {
 

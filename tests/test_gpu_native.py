@@ -9,6 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "build", "selftest")
+BIN_LIB = os.path.join(ROOT, "build", "selftest_lib")   # no -DUB_TC_PROF: the kernel binaries of libunetb200.so
 
 # group filter -> what it covers (a filter selects every group whose name contains it)
 GROUPS = {
@@ -37,3 +38,15 @@ def test_native_selftest(group):
     n = int(r.stdout.rsplit("SELFTEST OK:", 1)[1].split("checks")[0])
     assert n > 0, f"filter {group!r} selected no checks"
     print(f"{group}: {n} checks ({GROUPS[group]})")
+
+
+@pytest.mark.parametrize("group", ["conv", "stem", "wide", "split", "xwgrad", "dlow", "swgrad"])
+def test_native_selftest_library_build(group):
+    """The same checks on the binaries the LIBRARY contains: build/selftest is compiled with -DUB_TC_PROF (role-cycle
+    counters change register allocation of the tconv kernels), build/selftest_lib is not."""
+    if not os.path.exists(BIN_LIB):
+        pytest.fail(f"{BIN_LIB} is missing: run `make`")
+    r = subprocess.run([BIN_LIB, group], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    tail = "\n".join(r.stdout.splitlines()[-40:])
+    assert r.returncode == 0 and "SELFTEST OK" in r.stdout and "[FAIL]" not in r.stdout, tail
+    assert int(r.stdout.rsplit("SELFTEST OK:", 1)[1].split("checks")[0]) > 0

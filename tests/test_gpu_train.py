@@ -279,3 +279,42 @@ def test_device_prefetcher_yields_every_batch_once_in_order():
     for (x, y), (hx, hy) in zip(seen, host):
         assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
     assert list(vb.data.DevicePrefetcher(iter([]), "cuda")) == []
+
+
+def test_uint8_frames_train_step_equals_host_preprocessing():
+    """`model(frames_u8)` in train mode (unetb200_train_forward_u8: BGR->RGB, /255, (x - mean) / std of train.py:108-112
+    inside the input pack) == the same step on the host-normalised fp32 tensor: logits, loss and every gradient; and two
+    forwards before one backward are refused (one activation arena per model)."""
+    o, m = _pair()
+    g = torch.Generator().manual_seed(8)
+    frames = torch.randint(0, 256, (2, 64, 96, 3), dtype=torch.uint8, generator=g).cuda()
+    y8 = (torch.rand(2, 1, 64, 96, generator=g) < 0.2).to(torch.uint8).cuda()
+    mean = torch.tensor(vb.Unet.IMAGENET_MEAN, device="cuda")
+    std = torch.tensor(vb.Unet.IMAGENET_STD, device="cuda")
+    x = ((frames.flip(-1).float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    crit = vb.losses.BCEDiceLoss()
+    sd0 = copy.deepcopy(m.state_dict())
+    la = m(x)
+    crit(la, y8.float()).backward()
+    ga = m.flat_grads.clone()
+    m.load_state_dict(sd0, strict=True)     # running statistics back to the start
+    m.zero_grad(set_to_none=True)
+    lb = m(frames)                          # uint8 dispatch
+    loss_b = crit(lb, y8)                   # uint8 mask: converted on the device
+    loss_b.backward()
+    gb = m.flat_grads
+    d = float((la - lb).abs().max())
+    rel = float((ga - gb).norm() / ga.norm())
+    print(f"\n[uint8 train frames] logits max-abs diff {d:.3e}; gradient rel-L2 {rel:.3e}")
+    assert d <= 2e-2 and rel <= 2e-2      # only difference: (v/255 - mean) * (1/std) vs / std before the bf16 pack
+    m.eval()
+    with torch.no_grad():
+        le = m(frames)
+        lx = m(x)
+    assert float((le - lx).abs().max()) <= 2e-2
+    m.train()
+    l1 = m(frames)
+    _ = m(frames)
+    with pytest.raises(vb.UnetB200Error, match="not the latest"):
+        crit(l1, y8).backward()
+    assert m._ctx.device_error_flag() == 0

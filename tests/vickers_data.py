@@ -101,13 +101,25 @@ def val_metrics(model, data, device, batch: int = 18):
     return float(torch.cat(dices).mean()), float(torch.cat(ious).mean()), float(torch.cat(loss).mean())
 
 
-def train(model, step_fn, data, device, steps: int, batch: int, seed: int, eval_every: int, log=None):
+def lr_at(step: int, steps: int, peak: float, warmup: int = 30) -> float:
+    """Learning rate of step `step` (1-based): linear warm-up, then cosine annealing to 0 at `steps` (the reference
+    anneals per epoch, train.py:607 CosineAnnealingLR(T_max=epochs); here per step because the run is a few epochs)."""
+    import math
+    return peak * min(1.0, step / warmup) * 0.5 * (1.0 + math.cos(math.pi * min(1.0, step / steps)))
+
+
+def train(model, step_fn, data, device, steps: int, batch: int, seed: int, eval_every: int, log=None, opt=None,
+          peak_lr: float = None):
     """Runs `steps` optimisation steps (step_fn(x, y) -> loss tensor/float does zero_grad/forward/loss/backward/step,
-    train.py:428-449) and evaluates the validation split every `eval_every` steps.  -> history list of dicts."""
+    train.py:428-449) and evaluates the validation split every `eval_every` steps.  -> history list of dicts.
+    opt + peak_lr: set param_groups[*]["lr"] = lr_at(step) before every step."""
     hist = []
     sched = batches(data["train_u8"].shape[0], batch, steps, seed)
     for s, (idx, ks) in enumerate(sched, 1):
         model.train()
+        if opt is not None and peak_lr is not None:
+            for gp in opt.param_groups:
+                gp["lr"] = lr_at(s, steps, peak_lr)
         x, y = make_batch(data, idx, ks, device)
         loss = step_fn(x, y)
         if s % eval_every == 0 or s == steps:

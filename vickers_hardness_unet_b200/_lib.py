@@ -47,6 +47,7 @@ def _proto(lib):
         "unetb200_profile_name": (i32, [vp, i32, i32, C.c_char_p, i32]),
         "unetb200_conv_nhwc": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
         "unetb200_train_forward": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "unetb200_train_forward_u8": (i32, [vp, vp, i32, P(f32), P(f32), vp, vp, vp, vp, vp, i32, vp]),
         "unetb200_train_backward": (i32, [vp, vp, i32, i32, i32, vp]),
         "unetb200_grad_bucket_range": (i32, [i32, P(i64), P(i64)]),
         "unetb200_train_launch_count": (i32, [vp, i32, P(i32), P(i32)]),

@@ -316,6 +316,23 @@ int unetb200_train_forward(unetb200_ctx* h, const float* x_dev, float* logits_de
                              (cudaStream_t)stream);
 }
 
+int unetb200_train_forward_u8(unetb200_ctx* h, const uint8_t* img_dev, int bgr, const float* mean3, const float* std3,
+                              float* logits_dev, const float* params_dev, float* buffers_dev, long long* counters_dev,
+                              float* grads_dev, int N, void* stream) {
+    Ctx* ctx = h->c;
+    if (!img_dev || !logits_dev || !params_dev || !buffers_dev || !counters_dev || !grads_dev)
+        return ctx_fail(ctx, "train_forward_u8: null pointer");
+    if (N < 1 || N > ctx->max_batch) return ctx_fail(ctx, "train_forward_u8: batch outside [1, max_batch]");
+    UB_CUDA(cudaSetDevice(ctx->device));
+    NormParams np;
+    for (int c = 0; c < 3; ++c) {
+        np.mean[c] = mean3 ? mean3[c] : 0.f;
+        np.inv_std[c] = 1.f / (std3 ? std3[c] : 1.f);
+    }
+    return ctx_train_forward(ctx, nullptr, logits_dev, params_dev, buffers_dev, counters_dev, grads_dev, N,
+                             (cudaStream_t)stream, img_dev, bgr, &np);
+}
+
 int unetb200_train_backward(unetb200_ctx* h, const float* dlogits_dev, int N, int stage_first, int stage_last,
                             void* stream) {
     Ctx* ctx = h->c;

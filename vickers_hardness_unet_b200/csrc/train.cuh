@@ -54,10 +54,14 @@ struct TrainPlan {
     std::vector<LaunchFn> fwd;          // after input pack, before head
     std::vector<LaunchFn> bwd[4];       // stage 0: decoder, 1: layer4, 2: layer3, 3: layer2 + layer1 + stem
     std::vector<std::string> fwd_names, bwd_names[4];  // "<kind>:<layer>" per launch (profiling)
+    std::vector<uint8_t> bwd_aux[4];    // 1: weight-gradient launch, off the dz -> dgrad -> dA critical path (side stream)
     int n_fwd = 0, n_bwd = 0;
     // scratch
     float* stat_part = nullptr;         // conv-epilogue statistic partials [4][num_sms][512][2]
     float* red_part = nullptr;          // reduction partials (BN backward / head / loss)
+    float* fuse_part = nullptr;         // partial rows written by the producers with fused BatchNorm-backward sums
+    BnBwdFuse head_fuse{};              // seg-head data gradient -> decoder.blocks.4 conv2 sums
+    int head_grid = 0, head_fuse_rows = 0;
     WgItem* items = nullptr;            // device work-item arena for all wgrad launches
     size_t items_cap = 0, items_used = 0;
     std::vector<WgItem> host_items;
@@ -86,7 +90,18 @@ struct TrainState {
     long long wdg_total = 0;
     std::vector<long long> wdg_off;       // per conv: offset of its dgrad operand(s)
     std::vector<long long> wdg_off2;      // decoder conv1: dLow operand
+    // The backward's critical path is BN backward -> dgrad -> BN backward -> ...; the weight gradients only hang off it
+    // (wgrad(u) needs dz(u), nothing on the path needs wgrad(u) before the stage's unpack), so they run on a side
+    // stream and fill the SMs / HBM cycles the small BatchNorm passes and the 64-item layer4 convs leave idle
+    // (measured: 8.42 -> 7.82 ms per step).  UNETB200_NO_AUX=1 keeps everything in order.  Running the dgrad operand
+    // re-pack there as well, under the forward, was measured and dropped: it slows the forward by what it saves.
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool use_aux = true;
     ~TrainState() {
+        if (aux) cudaStreamDestroy(aux);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         plans.clear();
         cudaFree(arena);
         cudaFree(gpk);
@@ -332,6 +347,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     plan.fwd_names.clear();
     for (auto& b : plan.bwd) b.clear();
     for (auto& b : plan.bwd_names) b.clear();
+    for (auto& b : plan.bwd_aux) b.clear();
     plan.host_items.clear();
     std::string err;
 
@@ -635,9 +651,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     auto add_b = [&](int stage, const std::string& nm, LaunchFn f) {
         plan.bwd[stage].push_back(std::move(f));
         plan.bwd_names[stage].push_back(nm);
+        plan.bwd_aux[stage].push_back(nm.rfind("wgrad:", 0) == 0 ? 1 : 0);
     };
     // BN backward of unit ui given dA_in (gradient w.r.t. `a`): dz (+ optional masked gradient g_out)
-    auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out) {
+    // fused_rows > 0: the kernel that produced dA_in already left the per-block sums (fused_rows rows) in fused_part
+    auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out,
+                      int fused_rows = 0, float* fused_part = nullptr) {
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
         const BnRef& b = S.bns[c.bn];
@@ -647,8 +666,8 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         long long nb = (npix + ppb - 1) / ppb / 8;   // >= 8 block iterations (2 pixels each 4): few partial rows
         if (nb > 6 * SM) nb = 6 * SM;
         if (nb < 1) nb = 1;
-        const int nblocks = (int)nb;
-        float* part = plan.red_part;
+        const int nblocks = fused_rows > 0 ? fused_rows : (int)nb;
+        float* part = fused_rows > 0 ? fused_part : plan.red_part;
         // ReLU mask: units with a residual input (g_out != nullptr) read the stored activation; the others recompute
         // it from z with the forward's scale / shift; no ReLU (downsample BN) -> no mask
         const __nv_bfloat16* mask = (relu_mask && g_out) ? u.a : nullptr;
@@ -657,10 +676,11 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const float* gm = params + b.gamma;
         float* dgm = grads + b.gamma;
         float* dbt = grads + b.beta;
-        add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
-            launch_k(bn_bwd_reduce_kernel, nblocks, 256, 0, st, dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
-            return cudaGetLastError();
-        });
+        if (fused_rows == 0)
+            add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
+                launch_k(bn_bwd_reduce_kernel, nblocks, 256, 0, st, dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
+                return cudaGetLastError();
+            });
         add_b(stage, "bn_bwd_finalize:" + c.name, [=](cudaStream_t st) {
             launch_k(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, st, part, nblocks, C, (double)npix, gm, u.mean, u.invstd,
                                                                    dgm, dbt, u.coef);
@@ -672,6 +692,18 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             return cudaGetLastError();
         });
     };
+    // the two element-wise producers of a large dA (seg-head data gradient -> decoder.blocks.4 conv2, max-pool backward ->
+    // stem) accumulate the BatchNorm-backward sums of the consuming unit themselves (train_ops.cuh, BnBwdFuse)
+    plan.fuse_part = plan.red_part + (1u << 20);   // clear of the regular reduce rows (<= 6*SM*512*2) and the head's
+    {
+        const long long npx = (long long)N * H * W;
+        int g = ew_grid(npx, 256, SM);
+        if (g > 6 * SM) g = 6 * SM;
+        plan.head_grid = g;
+        plan.head_fuse_rows = getenv("UNETB200_NO_BN_FUSE") ? 0 : g;
+        const Unit& hu = plan.units[decs[4].u2];
+        plan.head_fuse = BnBwdFuse{plan.head_fuse_rows ? hu.z : nullptr, hu.mean, hu.invstd, hu.scale, hu.shift, plan.fuse_part};
+    }
     std::vector<int> stage_convs[4];
     auto add_wg = [&](int stage, const WgSpec& s) -> std::string {
         if (s.conv >= 0 && std::find(stage_convs[stage].begin(), stage_convs[stage].end(), s.conv) == stage_convs[stage].end())
@@ -779,7 +811,8 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const DecRec& r = decs[i];
         const Unit u1 = plan.units[r.u1], u2 = plan.units[r.u2];
         const ConvRef& c1 = S.convs[d.c1];
-        bn_bwd(0, r.u2, d_cur, true, nullptr);
+        if (i == 4 && plan.head_fuse_rows > 0) bn_bwd(0, r.u2, d_cur, true, nullptr, plan.head_fuse_rows, plan.fuse_part);
+        else bn_bwd(0, r.u2, d_cur, true, nullptr);
         if (!(err = wg_conv3(0, r.u2, u1.a, d.cout, u1.Ho, u1.Wo)).empty()) return err;
         if (!(err = dgrad3(0, r.u2, dA[r.u1], nullptr)).empty()) return err;
         bn_bwd(0, r.u1, dA[r.u1], true, nullptr);
@@ -987,12 +1020,16 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const int Hh = H / 2, Wh = W / 2;
         const __nv_bfloat16* dsk = d_skips[3];
         __nv_bfloat16* dF1 = dA[u_stem];
+        int pg = ew_grid((long long)N * Hh * Wh * 8, 256, SM);
+        if (pg > 6 * SM) pg = 6 * SM;
+        const bool pfuse = !getenv("UNETB200_NO_BN_FUSE");
+        const BnBwdFuse pf{pfuse ? us.z : nullptr, us.mean, us.invstd, us.scale, us.shift, plan.fuse_part};
         add_b(3, "maxpool_bwd:encoder.maxpool", [=](cudaStream_t st) {
-            launch_k(maxpool_bwd_kernel, ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st, d_p1, pool_idx, dsk, dF1, N, Hh,
-                                                                                            Wh, 64);
+            launch_k(maxpool_bwd_kernel, pg, 256, 0, st, d_p1, pool_idx, dsk, dF1, N, Hh, Wh, 64, pf);
             return cudaGetLastError();
         });
-        bn_bwd(3, u_stem, dF1, true, nullptr);
+        if (pfuse) bn_bwd(3, u_stem, dF1, true, nullptr, pg, plan.fuse_part);
+        else bn_bwd(3, u_stem, dF1, true, nullptr);
         if (swgrad_ok(H, W)) {
             // all seven filter rows from one pass over dZ (swgrad.cuh)
             SwgradLaunch WL;
@@ -1099,6 +1136,12 @@ inline int ctx_train_prepare(Ctx* ctx, int N, const float* params, float* buffer
         if (!pe.empty()) return ctx_fail(ctx, pe);
     }
     if (!T.gpk) UB_CUDA(cudaMalloc(&T.gpk, (size_t)ctx->spec.n_params * sizeof(float)));
+    if (!T.aux) {
+        T.use_aux = !getenv("UNETB200_NO_AUX");
+        UB_CUDA(cudaStreamCreateWithFlags(&T.aux, cudaStreamNonBlocking));
+        UB_CUDA(cudaEventCreateWithFlags(&T.ev_fork, cudaEventDisableTiming));
+        UB_CUDA(cudaEventCreateWithFlags(&T.ev_join, cudaEventDisableTiming));
+    }
     size_t need = 0;
     {
         TrainPlan probe;
@@ -1125,14 +1168,21 @@ inline int ctx_train_prepare(Ctx* ctx, int N, const float* params, float* buffer
 
 // model.train(); logits = model(x)   (/root/reference/train.py:413,436): batch-statistics BatchNorm, running statistics
 // and num_batches_tracked updated in the caller's buffers, activations kept in the library's arena for the backward.
+// x8 != nullptr: the input is uint8 HWC camera frames [N,H,W,3]; BGR->RGB, /255, (x - mean) / std (train.py:108-112) run
+// inside the input pack.
 inline int ctx_train_forward(Ctx* ctx, const float* x, float* logits, const float* params, float* buffers,
-                             long long* counters, float* grads, int N, cudaStream_t st) {
+                             long long* counters, float* grads, int N, cudaStream_t st, const uint8_t* x8 = nullptr,
+                             int bgr = 0, const NormParams* norm = nullptr) {
     if (!ctx->weights_ready) return ctx_fail(ctx, "train_forward: weights not loaded");
     TrainPlan* P = nullptr;
     if (ctx_train_prepare(ctx, N, params, buffers, counters, grads, &P)) return 1;
     const int H = ctx->H, W = ctx->W;
     ctx->prof_mark("pack_input:x", st);
-    launch_k(pack_input_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x, P->xp, N, H, W);
+    if (x8)
+        launch_k(pack_input_u8_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x8, P->xp, N, H,
+                                                                                                          W, bgr, *norm);
+    else
+        launch_k(pack_input_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x, P->xp, N, H, W);
     UB_CUDA(cudaGetLastError());
     for (size_t i = 0; i < P->fwd.size(); ++i) {
         ctx->prof_mark(P->fwd_names[i], st);
@@ -1168,17 +1218,36 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
             if (npx >= (1ll << 31)) return ctx_fail(ctx, "train_backward: N*H*W must be below 2^31 (32-bit pixel arithmetic)");
-            launch_k(head_bwd_data_kernel, ew_grid(npx, 256, SM), 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W);
-            const int nb = 8 * SM;
+            launch_k(head_bwd_data_kernel, P.head_grid, 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W, P.head_fuse);
+            const int nb = 2 * SM;
             ctx->prof_mark("head_bwd_w:segmentation_head", st);
-            launch_k(head_bwd_weight_kernel, nb, 288, 0, st, P.head_in, dlogits, P.red_part, N, H, W);
+            launch_k(head_bwd_weight_kernel, nb, 256, 0, st, P.head_in, dlogits, P.red_part, N, H, W);
             launch_k(sum_rows_kernel, (145 + 7) / 8, 256, 0, st, P.red_part, nb, 145, P.grads + hc.w);
             UB_CUDA(cudaGetLastError());
         }
+        const bool side = T.use_aux && !ctx->prof_on;
+        bool aux_pending = false;
+        auto join = [&]() -> int {
+            if (!aux_pending) return 0;
+            UB_CUDA(cudaEventRecord(T.ev_join, T.aux));
+            UB_CUDA(cudaStreamWaitEvent(st, T.ev_join, 0));
+            aux_pending = false;
+            return 0;
+        };
         for (size_t i = 0; i < P.bwd[stage].size(); ++i) {
+            if (side && P.bwd_aux[stage][i]) {
+                // everything this weight gradient reads (dz of its unit, saved activations) precedes it on `st`
+                UB_CUDA(cudaEventRecord(T.ev_fork, st));
+                UB_CUDA(cudaStreamWaitEvent(T.aux, T.ev_fork, 0));
+                UB_CUDA(P.bwd[stage][i](T.aux));
+                aux_pending = true;
+                continue;
+            }
+            if (P.bwd_names[stage][i].rfind("unpack_grads:", 0) == 0 && join()) return 1;
             ctx->prof_mark(P.bwd_names[stage][i], st);
             UB_CUDA(P.bwd[stage][i](st));
         }
+        if (join()) return 1;   // a stage's parameter gradients are final when the call returns (in stream order)
         if (stage == 3) ctx->prof_mark("end:backward", st);
     }
     return 0;

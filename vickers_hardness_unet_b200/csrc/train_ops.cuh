@@ -148,6 +148,56 @@ __device__ __forceinline__ void bn_bwd_mask8(float (&g)[8], const float (&zz)[8]
         for (int k = 0; k < 8; ++k) g[k] = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
     }
 }
+// Block tail shared by every kernel that accumulates the BatchNorm-backward sums (sum g, sum g*zhat): thread t owns the
+// channel group t % (C/8) for its pixels; the block's per-channel totals go to partial[blockIdx.x][C][2].
+// red: 256 * 17 floats of shared memory (row pitch 17 words: conflict-free column walks).
+__device__ __forceinline__ void bn_partials_store(const float (&s1)[8], const float (&s2)[8], int C,
+                                                  float* __restrict__ partial, float* red) {
+    const int C8 = C / 8, ppb = 256 / C8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        red[threadIdx.x * 17 + k] = s1[k];
+        red[threadIdx.x * 17 + 8 + k] = s2[k];
+    }
+    __syncthreads();
+    // thread t < C*2 sums its (channel, which) over the ppb pixel lanes
+    for (int j = threadIdx.x; j < C * 2; j += 256) {
+        const int c = j >> 1, which = j & 1;
+        const int g8 = c / 8, k = c % 8;
+        float acc = 0.f;
+        for (int l = 0; l < ppb; ++l) acc += red[(l * C8 + g8) * 17 + which * 8 + k];
+        partial[((size_t)blockIdx.x * C + c) * 2 + which] = acc;
+    }
+}
+// Per-thread constants + accumulation of the fused form (the producer of dA accumulates the sums of the unit that will
+// consume it: no separate bn_bwd_reduce pass, one read of dA and one launch less).  g = bf16(dA) * [z*scale + shift > 0].
+struct BnBwdFuse {
+    const __nv_bfloat16* z;      // nullptr: nothing fused
+    const float* mean; const float* invstd; const float* scale; const float* shift;
+    float* partial;              // [gridDim.x][C][2]
+};
+struct BnBwdAcc {
+    float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
+    __device__ __forceinline__ void init(const BnBwdFuse& F, int c0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s1[k] = s2[k] = 0.f;
+            mu[k] = F.mean[c0 + k]; is[k] = F.invstd[c0 + k]; sc[k] = F.scale[c0 + k]; sh[k] = F.shift[c0 + k];
+        }
+    }
+    __device__ __forceinline__ void add(const uint4& dA_bf16, const uint4& zv) {
+        float g[8], zz[8];
+        unpack8(dA_bf16, g);
+        unpack8(zv, zz);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float gg = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
+            s1[k] += gg;
+            s2[k] += gg * (zz[k] - mu[k]) * is[k];
+        }
+    }
+};
+
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -207,20 +257,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* 
             }
         }
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {   // row pitch 17 words: conflict-free column walks below
-        red[threadIdx.x * 17 + k] = s1[k];
-        red[threadIdx.x * 17 + 8 + k] = s2[k];
-    }
-    __syncthreads();
-    // thread t < C*2 sums its (channel, which) over the ppb pixel lanes
-    for (int j = threadIdx.x; j < C * 2; j += 256) {
-        const int c = j >> 1, which = j & 1;
-        const int g8 = c / 8, k = c % 8;
-        float acc = 0.f;
-        for (int l = 0; l < ppb; ++l) acc += red[(l * C8 + g8) * 17 + which * 8 + k];
-        partial[((size_t)blockIdx.x * C + c) * 2 + which] = acc;
-    }
+    bn_partials_store(s1, s2, C, partial, red);
 }
 
 // sums the per-block partials; writes dgamma / dbeta and the affine apply coefficients
@@ -376,12 +413,18 @@ __global__ void maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ in, __
 }
 
 // dF[n,h,w,c] = dSkip[n,h,w,c] + sum over the (<= 4) windows containing (h,w) whose recorded winner is (h,w) of dP[window]
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restrict__ idx,
-                                   const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
-                                   int H, int W, int C) {
+// fuse.z != nullptr: also accumulates the BatchNorm-backward sums of the unit that produced F (the stem), see BnBwdFuse;
+// blockDim = 256 and C/8 divides 256, so a thread's channel group is loop invariant.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restrict__ idx,
+                   const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
+                   int H, int W, int C, BnBwdFuse fuse) {
     griddep_launch();
     griddep_wait();
+    __shared__ float red[256 * 17];
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    BnBwdAcc bacc;
+    if (fuse.z) bacc.init(fuse, int(threadIdx.x % C8) * 8);
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -417,17 +460,23 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const u
                 }
             }
         }
-        reinterpret_cast<uint4*>(dF)[i] = pack8(acc);
+        const uint4 ov = pack8(acc);
+        reinterpret_cast<uint4*>(dF)[i] = ov;
+        if (fuse.z) bacc.add(ov, __ldg(reinterpret_cast<const uint4*>(fuse.z) + i));
     }
+    if (fuse.z) bn_partials_store(bacc.s1, bacc.s2, C, fuse.partial, red);
 }
 
 // ------------------------------------------------------------------------------------------------ seg head backward
 // dA[n,h,w,c] = sum_{r,s} dL[n, h+1-r, w+1-s] * w[c][r][s]   (bf16 out, 16 channels per pixel)
 __global__ void __launch_bounds__(256)
 head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
-                     __nv_bfloat16* __restrict__ dA, int N, int H, int W) {
+                     __nv_bfloat16* __restrict__ dA, int N, int H, int W, BnBwdFuse fuse) {
     griddep_launch();
     griddep_wait();
+    __shared__ float red[256 * 17];
+    BnBwdAcc bacc;
+    if (fuse.z) bacc.init(fuse, int(threadIdx.x & 1) * 8);   // C = 16: channel group = half
     // thread = (pixel, 8-channel half): its 72 weights live in registers for the whole grid-stride loop (the first
     // version read 144 weights per pixel from shared memory: LDS-bound)
     const int half = threadIdx.x & 1;
@@ -457,72 +506,76 @@ head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
             for (int k = 0; k < 9; ++k) a += d[k] * wr[c * 9 + k];
             o[c] = a;
         }
-        reinterpret_cast<uint4*>(dA)[i * 2 + half] = pack8(o);
+        const uint4 ov = pack8(o);
+        reinterpret_cast<uint4*>(dA)[i * 2 + half] = ov;
+        if (fuse.z) bacc.add(ov, __ldg(reinterpret_cast<const uint4*>(fuse.z) + i * 2 + half));
     }
+    if (fuse.z) bn_partials_store(bacc.s1, bacc.s2, 16, fuse.partial, red);
 }
 
-// per-block partials of dW[c][r][s] = sum a[n,h+r-1,w+s-1,c] * dL[n,h,w] and dbias = sum dL   -> partial[block][145]
-// blockDim = 288 = 9 warps: warp t owns filter tap t = r*3+s, its lanes own 32 consecutive pixels of a row segment, so
-// every load is a contiguous 128 B (dL) / 1 KB (activations) per warp and each thread keeps only 16 accumulators.
-__global__ void __launch_bounds__(288)
+// per-block partials of dW[c][r][s] = sum_p A[p + (r-1, s-1)][c] * dL[p] and dbias = sum dL   -> partial[block][145]
+// Indexed by the ACTIVATION pixel q = p + (r-1, s-1): a thread owns 8 channels of q (one 16-byte load of the 134 MB
+// tensor, the only HBM stream), needs the nine dL values around q (fp32, L1 / L2 hits: neighbouring lanes read the same
+// lines) and keeps all 72 (channel, tap) partial sums in registers.  Lanes 2k / 2k+1 hold the two channel halves of one
+// pixel, so a warp reads 512 contiguous bytes of A.  The first version walked the 9 taps with 9 warps, each re-reading A
+// (L1-bound, 188 us at batch 16 / 512^2 against an HBM floor of ~25 us).
+__global__ void __launch_bounds__(256, 2)
 head_bwd_weight_kernel(const __nv_bfloat16* __restrict__ A, const float* __restrict__ dL, float* __restrict__ partial,
                        int N, int H, int W) {
     griddep_launch();
     griddep_wait();
-    const int tap = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = tap / 3, s = tap - 3 * r;
-    float acc[16], bsum = 0.f;
+    const int half = threadIdx.x & 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[72], bsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-    // a group = 32 consecutive pixels of one image row (32-bit index arithmetic: the 64-bit div/mod per pixel of the
-    // first version cost more than the loads); two groups in flight per warp
-    const int gpr = (W + 31) >> 5;
-    const int groups = N * H * gpr;
-    auto one = [&](int g, float& d, uint4& a0, uint4& a1) -> bool {
-        d = 0.f;
-        a0 = a1 = make_uint4(0, 0, 0, 0);
-        if (g >= groups) return false;
-        const int row = g / gpr, x = (g - row * gpr) * 32 + lane;
-        if (x >= W) return false;
-        const int y = row % H;
-        const long long i = (long long)row * W + x;
-        d = __ldg(dL + i);
-        const int yy = y + r - 1, xx = x + s - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) return true;
-        const uint4* ap = reinterpret_cast<const uint4*>(A + (i + (long long)(r - 1) * W + (s - 1)) * 16);
-        a0 = __ldg(ap);
-        a1 = __ldg(ap + 1);
-        return true;
-    };
-    for (int g = blockIdx.x; g < groups; g += 2 * gridDim.x) {
-        float d0, d1;
-        uint4 p0, p1, q0, q1;
-        one(g, d0, p0, p1);
-        one(g + gridDim.x, d1, q0, q1);
-        bsum += d0 + d1;
+    for (int k = 0; k < 72; ++k) acc[k] = 0.f;
+    const unsigned total = (unsigned)N * H * W;   // < 2^31 (checked by the host)
+    const unsigned stride = gridDim.x * 128u;
+    const uint4* A4 = reinterpret_cast<const uint4*>(A);
+    for (unsigned q = blockIdx.x * 128u + (threadIdx.x >> 1); q < total; q += stride) {
+        const unsigned row = q / (unsigned)W;
+        const int x = int(q - row * (unsigned)W), y = int(row % (unsigned)H);
+        const uint4 av = __ldg(A4 + (size_t)q * 2 + half);
+        float d[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s2 = 0; s2 < 3; ++s2) {
+                const int yy = y + 1 - r, xx = x + 1 - s2;
+                d[r * 3 + s2] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                    ? __ldg(dL + (long long)q + (long long)(1 - r) * W + (1 - s2)) : 0.f;
+            }
         float v[8];
-        unpack8(p0, v);
+        unpack8(av, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k] * d0;
-        unpack8(p1, v);
+        for (int c = 0; c < 8; ++c)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[8 + k] += v[k] * d0;
-        unpack8(q0, v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += v[k] * d1;
-        unpack8(q1, v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[8 + k] += v[k] * d1;
+            for (int k = 0; k < 9; ++k) acc[c * 9 + k] += v[c] * d[k];
+        if (half == 0) bsum += d[4];
     }
+    __shared__ float red[8][2][72];
+    __shared__ float redb[8];
+#pragma unroll
+    for (int k = 0; k < 72; ++k) {
+        float t = acc[k];
+#pragma unroll
+        for (int o = 16; o >= 2; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);   // lanes of equal parity
+        if (lane < 2) red[warp][lane][k] = t;
+    }
+    bsum = warp_sum(bsum);
+    if (lane == 0) redb[warp] = bsum;
+    __syncthreads();
     float* out = partial + (size_t)blockIdx.x * 145;
+    if (threadIdx.x < 144) {
+        const int hf = threadIdx.x / 72, k = threadIdx.x % 72;   // out index = (hf*8 + c)*9 + tap = threadIdx.x
+        float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const float v = warp_sum(acc[k]);
-        if (lane == 0) out[k * 9 + tap] = v;   // [c][r][s]
-    }
-    if (tap == 4) {
-        const float v = warp_sum(bsum);
-        if (lane == 0) out[144] = v;
+        for (int w = 0; w < 8; ++w) t += red[w][hf][k];
+        out[threadIdx.x] = t;
+    } else if (threadIdx.x == 144) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += redb[w];
+        out[144] = t;
     }
 }
 // out[j] = sum_b partial[b][j]; one WARP per column j (blockDim = 256 -> 8 columns per block)

@@ -18,15 +18,25 @@ def _stream(t: torch.Tensor) -> int:
 
 class _UnetTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(fctx, x, anchor, model):  # noqa: D401  (anchor: any parameter, makes the output require grad)
+    def forward(fctx, x, anchor, model, frames=None):  # noqa: D401  (anchor: any parameter, makes the output require grad)
         ctx = model._ctx
-        N, _, H, W = x.shape
-        logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
         flat = model._flat
         g = model._grad_buffer()
-        ctx.check(ctx.lib.unetb200_train_forward(ctx.handle, x.data_ptr(), logits.data_ptr(), flat["p"].data_ptr(),
-                                                 flat["b"].data_ptr(), flat["c"].data_ptr(), g.data_ptr(), N,
-                                                 _stream(x)), "train_forward")
+        if frames is None:
+            N, _, H, W = x.shape
+            logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+            ctx.check(ctx.lib.unetb200_train_forward(ctx.handle, x.data_ptr(), logits.data_ptr(), flat["p"].data_ptr(),
+                                                     flat["b"].data_ptr(), flat["c"].data_ptr(), g.data_ptr(), N,
+                                                     _stream(x)), "train_forward")
+        else:   # uint8 HWC frames: the reference's host pre-processing (train.py:108-112) runs in the input pack
+            import ctypes as C
+            bgr, mean, std = frames
+            N, H, W, _ = x.shape
+            logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
+            ctx.check(ctx.lib.unetb200_train_forward_u8(ctx.handle, x.data_ptr(), int(bool(bgr)), (C.c_float * 3)(*mean),
+                                                        (C.c_float * 3)(*std), logits.data_ptr(), flat["p"].data_ptr(),
+                                                        flat["b"].data_ptr(), flat["c"].data_ptr(), g.data_ptr(), N,
+                                                        _stream(x)), "train_forward_u8")
         model._buffers_epoch += 1  # running statistics changed behind PyTorch's back: eval must re-fold BatchNorm
         model._fwd_seq += 1        # the arena now holds THIS forward's activations
         fctx.model, fctx.N, fctx.seq = model, N, model._fwd_seq
@@ -64,12 +74,12 @@ class _UnetTrainFn(torch.autograd.Function):
                 p.grad = v
             elif not a:
                 p.grad.add_(v)
-        return None, None, None
+        return None, None, None, None
 
 
-def unet_train_forward(model, ctx, x, stream):
+def unet_train_forward(model, ctx, x, stream, frames=None):
     anchor = next(model.parameters())
-    return _UnetTrainFn.apply(x, anchor, model)
+    return _UnetTrainFn.apply(x, anchor, model, frames)
 
 
 # ------------------------------------------------------------------------------------------------ loss

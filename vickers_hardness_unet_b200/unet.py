@@ -64,6 +64,13 @@ def _find_resnet34_checkpoint() -> str:
         f"{os.path.join(hub, 'checkpoints')}; or pass encoder_weights=None and load a state_dict")
 
 
+class _ShapeProxy:
+    """What `_context` needs to know about an input: device and the NCHW shape it stands for."""
+
+    def __init__(self, t, N, H, W):
+        self.is_cuda, self.device, self.shape = t.is_cuda, t.device, (N, 3, H, W)
+
+
 class Unet(nn.Module):
     def __init__(self, encoder_name: str = "resnet34", encoder_depth: int = 5, encoder_weights=None,
                  decoder_use_batchnorm: bool = True, decoder_channels=(256, 128, 64, 32, 16),
@@ -256,6 +263,8 @@ class Unet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dtype == torch.uint8:
+            return self.forward_frames(x)
         ctx = self._context(x)
         x = x.detach().to(torch.float32).contiguous()
         stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -268,6 +277,30 @@ class Unet(nn.Module):
         logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=x.device)
         ctx.check(ctx.lib.unetb200_forward_infer(ctx.handle, x.data_ptr(), logits.data_ptr(), None, None, 0.5, N,
                                                  stream), "forward_infer")
+        return logits
+
+    def forward_frames(self, frames: torch.Tensor, bgr: bool = True, mean=None, std=None) -> torch.Tensor:
+        """`model(x)` on uint8 HWC frames [N,H,W,3] already on the GPU (what cv2.imread + the letterbox produce): the
+        reference's host pre-processing — BGR->RGB, /255, (x - mean) / std (train.py:108-112, infer_pth_gui.py:46-48) —
+        runs inside the input-pack kernel, in train and eval mode alike.  `model(frames_u8)` dispatches here with the
+        ImageNet constants."""
+        import ctypes as C
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError(f"expected uint8 [N,H,W,3] frames, got {frames.dtype} {tuple(frames.shape)}")
+        mean = self.IMAGENET_MEAN if mean is None else mean
+        std = self.IMAGENET_STD if std is None else std
+        N, H, W, _ = frames.shape
+        ctx = self._context(_ShapeProxy(frames, N, H, W))
+        frames = frames.detach().contiguous()
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        self._sync_weights(ctx, stream)
+        if self.training:
+            from .train import unet_train_forward
+            return unet_train_forward(self, ctx, frames, stream, frames=(bgr, mean, std))
+        logits = torch.empty((N, 1, H, W), dtype=torch.float32, device=frames.device)
+        ctx.check(ctx.lib.unetb200_forward_infer_u8(ctx.handle, frames.data_ptr(), int(bool(bgr)), (C.c_float * 3)(*mean),
+                                                    (C.c_float * 3)(*std), logits.data_ptr(), None, None, 0.5, N, stream),
+                  "forward_infer_u8")
         return logits
 
     @torch.no_grad()

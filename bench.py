@@ -472,6 +472,29 @@ def main():
     e2e_val = timed(pipe_submit(xh), drain)
     e2e_sync = timed(sync_call, lambda: None)
     e2e_u8 = timed(pipe_submit(x8h), drain)
+    # ---- the fp16-operand build of the same kernels (inference only): same tensor-core rate, 10 mantissa bits
+    f16 = None
+    if rank == 0 and world == 1:
+        try:
+            m16 = vb.Unet("resnet34", encoder_weights=None, in_channels=3, classes=1, activation=None, precision="fp16")
+            m16.load_state_dict(model.state_dict())
+            m16 = m16.to(dev).eval()
+            with torch.no_grad():
+                for i in range(3):
+                    m16(xs[i & 1])
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                f0.record()
+                for i in range(a.steps):
+                    m16(xs[i & 1])
+                f1.record()
+                torch.cuda.synchronize(dev)
+            f16 = {"value": B * a.steps / (f0.elapsed_time(f1) * 1e-3), "unit": "images/s",
+                   "what": "Unet(precision='fp16'): libunetb200_f16.so, IEEE-half activations / operands"}
+            del m16
+            torch.cuda.empty_cache()
+        except Exception as e:  # the variant is optional evidence, never the headline
+            f16 = {"error": str(e)[:200]}
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-launch timing of one step (CUDA events on the launch stream) -> conv-stack roofline
@@ -544,6 +567,8 @@ def main():
         sus_tf = gflop * sustained["value"] / world / 1e3
         out["sustained"]["whole_step_tflops"] = sus_tf
         out["sustained"]["frac_of_sustained_peak"] = sus_tf / pk["bf16_tflops_sustained"]
+        if f16:
+            out["fp16_operands"] = f16
         if lib_bar:
             lib_bar["speedup_vs_best_library"] = {
                 "infer": value / max(v["images_per_s"] for v in lib_bar["infer"].values()),

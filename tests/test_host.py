@@ -18,6 +18,21 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/unetb200.h but not exported"
 
 
+def test_fp16_operand_library_exports_the_same_abi():
+    """libunetb200_f16.so (same kernels, IEEE-half storage, inference) is loaded beside the bf16 library and exports
+    every symbol include/unetb200.h declares."""
+    a, b = _lib.load("bf16"), _lib.load("fp16")
+    assert a is not b
+    for n in _lib.exported_symbols():
+        assert hasattr(b, n), n
+    assert b.unetb200_num_params() == a.unetb200_num_params() == 24_436_369
+    with pytest.raises(ValueError):
+        _lib.load("fp8")
+    with pytest.raises(ValueError):
+        vb.Unet("resnet34", precision="int8")
+    assert vb.Unet("resnet34", precision="fp16").precision == "fp16"
+
+
 def test_tensor_table_matches_oracle_state_dict():
     table = _lib.tensor_table()
     osd = build_oracle().state_dict()

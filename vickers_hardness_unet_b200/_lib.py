@@ -10,7 +10,8 @@ from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libunetb200.so"
-_lib = None
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": _HERE / "libunetb200_f16.so"}   # fp16: same kernels, IEEE-half operands (inference)
+_libs = {}
 
 
 class UnetB200Error(RuntimeError):
@@ -78,17 +79,22 @@ def exported_symbols():
     return sorted(set(re.findall(r"\b(unetb200_[a-z_0-9]+)\s*\(", hdr)))
 
 
-def load():
-    global _lib
-    if _lib is None:
-        if not LIB_PATH.exists():
+def load(precision: str = "bf16"):
+    """The C-ABI library for a storage precision: "bf16" (default; training and inference) or "fp16" (inference only).
+    Both export the same symbols (built with -Bsymbolic) and are loaded RTLD_LOCAL, side by side if needed."""
+    lib = _libs.get(precision)
+    if lib is None:
+        path = LIB_PATHS.get(precision)
+        if path is None:
+            raise ValueError(f"precision must be one of {sorted(LIB_PATHS)} (got {precision!r})")
+        if not path.exists():
             raise UnetB200Error(
-                f"{LIB_PATH} is missing: build it with `make` (nvcc, sm_100a). There is no CPU / cuDNN fallback."
+                f"{path} is missing: build it with `make` (nvcc, sm_100a). There is no CPU / cuDNN fallback."
             )
-        lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_GLOBAL", 0))
+        lib = C.CDLL(str(path), mode=getattr(os, "RTLD_LOCAL", 0))
         _proto(lib)
-        _lib = lib
-    return _lib
+        _libs[precision] = lib
+    return lib
 
 
 def grad_bucket_ranges():
@@ -127,8 +133,9 @@ def tensor_table():
 class Context:
     """Owns one unetb200_ctx (device, max_batch, H, W)."""
 
-    def __init__(self, device: int, max_batch: int, H: int, W: int):
-        self.lib = load()
+    def __init__(self, device: int, max_batch: int, H: int, W: int, precision: str = "bf16"):
+        self.lib = load(precision)
+        self.precision = precision
         self.handle = C.c_void_p()
         rc = self.lib.unetb200_create(C.byref(self.handle), device, max_batch, H, W)
         if rc:

@@ -131,7 +131,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, const EpiSmem&
                 for (int rr = g; rr < 128; rr += ngrp) {
                     uint32_t off = rr * row_bytes + c * 2;
                     off ^= ((off >> 7) & swz_mask) << 4;
-                    const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sbuf + off));
+                    const float x = ub_s2f(*reinterpret_cast<const __nv_bfloat16*>(sbuf + off));
                     s1 += x;
                     s2 += x * x;
                 }

@@ -92,14 +92,14 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
             long long t = i / cin;
             const int rs = int(t % (R * S));
             const int co = int(t / (R * S));
-            out[i] = __float2bfloat16(w[((long long)co * cin + ci) * R * S + rs]);
+            out[i] = ub_f2s(w[((long long)co * cin + ci) * R * S + rs]);
         } else {
             const int co = int(i % cout);
             long long t = i / cout;
             const int rs = int(t % (R * S));
             const int ci = int(t / (R * S));
             const int r = R - 1 - rs / S, s = S - 1 - rs % S;
-            out[i] = __float2bfloat16(w[(((long long)co * cin + ci) * R + r) * S + s]);
+            out[i] = ub_f2s(w[(((long long)co * cin + ci) * R + r) * S + s]);
         }
     }
 }
@@ -133,7 +133,7 @@ __global__ void pack_hconv_w_kernel(const float* __restrict__ w, __nv_bfloat16* 
         else v = w[(((long long)c * dim1_total + ci0 + co) * 3 + (2 - r)) * 3 + (2 - s)];
         const unsigned off = (unsigned)(i * 2);
         const unsigned phys = off ^ (((off >> 7) & (row_bytes / 16 - 1)) << 4);
-        out[phys / 2] = __float2bfloat16(v);
+        out[phys / 2] = ub_f2s(v);
     }
 }
 
@@ -146,7 +146,7 @@ __global__ void pack_stem_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
     const int ch = i % 4, px = (i / 4) % 8, r = (i / 32) % 7, co = i / 224;
     float v = 0.f;
     if (ch < 3 && px >= 1) v = w[((co * 3 + ch) * 7 + r) * 7 + (px - 1)];
-    out[i] = __float2bfloat16(v);
+    out[i] = ub_f2s(v);
 }
 
 // Decoder conv1 (nearest-2x upsample + concat fused away): for output parity (ph,pw) the 3x3 taps over the
@@ -182,7 +182,7 @@ __global__ void pack_dec1_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
             for (int r = r0; r <= r1; ++r)
                 for (int s = s0; s <= s1; ++s) v += w[((long long)co * cin + c) * 9 + r * 3 + s];
         }
-        out[i] = __float2bfloat16(v);
+        out[i] = ub_f2s(v);
     }
 }
 
@@ -200,10 +200,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ max-pool 3x3 s2 p1
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) { return ub_max2(a, b); }
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
                                     int H, int W, int C) {
     griddep_launch();
@@ -218,7 +215,7 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
         const int wo = int(t1 - t2 * (unsigned)Wo);
         const int n = int(t2 / (unsigned)Ho);
         const int ho = int(t2 - (unsigned)n * (unsigned)Ho);
-        uint4 m = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);  // -inf pairs
+        uint4 m = make_uint4(kNegInfPair, kNegInfPair, kNegInfPair, kNegInfPair);  // -inf pairs
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int h = ho * 2 - 1 + r;

@@ -102,7 +102,7 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
             dst = (off ^ (((off >> 7) & 1u) << 4)) / 2;
             if (r > 2 || row > 5) return 0.f;
             const float wv = w[ci * 9 + r * 3 + (row >> 1)];
-            const float hi = __bfloat162float(__float2bfloat16(wv));
+            const float hi = ub_s2f(ub_f2s(wv));
             return (row & 1) == 0 ? hi : wv - hi;
         }
         case PK_HPAR: {  // tconv parity operand: cout = rows, cin = cup (<= 64), a = cin_total of the OIHW tensor.
@@ -151,6 +151,53 @@ __device__ __forceinline__ float pack_elem(const PackEntry& E, const float* __re
     }
 }
 
+// The layouts that hold ~22 of the 24.4 M weights — every 3x3 conv of the wide layers, plain [co][(r,s)][ci] for the
+// forward and flipped / transposed [ci][(2-r,2-s)][co] for the data gradient — as tiled transposes through shared memory:
+// 128-byte coalesced fp32 loads, 64-byte coalesced bf16 stores.  (One thread per (co, ci) pair reading its nine taps
+// straight from global memory issued 32 different lines per load instruction: LSU-bound, ~5x above the HBM time.)
+// A block owns 256 (co, ci) pairs either way, so the table's block ranges are unchanged.
+__device__ __forceinline__ bool pack_conv3x3_tiled(const PackEntry& E, const float* __restrict__ w,
+                                                   __nv_bfloat16* __restrict__ out, float* tile /* [32 * 73] */) {
+    if (E.type != PK_CONV || E.a != 3 || E.b != 3 || E.total >= (1ll << 30)) return false;
+    const int tid = threadIdx.x, b = (int)blockIdx.x - E.block_begin;
+    const int npairs = E.cout * E.cin;
+    if (!E.c) {
+        // plain: pair j = co * cin + ci; the block's 256 pairs are 2304 contiguous source floats
+        const int j0 = b * 256, n = min(256, npairs - j0);
+        if (n <= 0) return true;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int idx = k * 256 + tid;
+            if (idx < n * 9) tile[idx] = __ldg(w + (long long)j0 * 9 + idx);
+        }
+        __syncthreads();
+        if (tid < n) {
+            const int j = j0 + tid, co = j / E.cin, ci = j - co * E.cin;
+            __nv_bfloat16* dst = out + (long long)co * 9 * E.cin + ci;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) dst[tap * E.cin] = ub_f2s(tile[tid * 9 + tap]);   // smem stride 9: no conflicts
+        }
+        return true;
+    }
+    if ((E.cin & 7) || (E.cout & 31)) return false;
+    // flipped / transposed: tile = 8 ci x 32 co; per co the 8 ci are 72 contiguous source floats
+    const int tiles_co = E.cout / 32, ci0 = (b / tiles_co) * 8, co0 = (b % tiles_co) * 32;
+    if (ci0 >= E.cin) return true;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int idx = k * 256 + tid, co_l = idx / 72, off = idx - co_l * 72;
+        tile[co_l * 73 + off] = __ldg(w + ((long long)(co0 + co_l) * E.cin + ci0) * 9 + off);
+    }
+    __syncthreads();
+    const int co_l = tid & 31;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int r = k * 8 + (tid >> 5), ci_l = r / 9, tap = r - ci_l * 9;
+        out[((long long)(ci0 + ci_l) * 9 + tap) * E.cout + co0 + co_l] = ub_f2s(tile[co_l * 73 + ci_l * 9 + (8 - tap)]);
+    }
+    return true;
+}
+
 template <typename IdxT>
 __device__ __forceinline__ void pack_entry_block(const PackEntry& E, const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
     const IdxT nloop = E.nloop, ts = (IdxT)E.tap_stride;
@@ -171,7 +218,7 @@ __device__ __forceinline__ void pack_entry_block(const PackEntry& E, const float
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const unsigned off = (unsigned)((j + (IdxT)tap * ts) * 2);
-                out[(off ^ (((off >> 7) & swz) << 4)) / 2] = __float2bfloat16(__ldg(src + (E.c ? 8 - tap : tap)));
+                out[(off ^ (((off >> 7) & swz) << 4)) / 2] = ub_f2s(__ldg(src + (E.c ? 8 - tap : tap)));
             }
             continue;
         }
@@ -181,7 +228,7 @@ __device__ __forceinline__ void pack_entry_block(const PackEntry& E, const float
             const float* src = E.c ? w + ((IdxT)lo * E.cin + hi) * 9 : w + j * 9;
             __nv_bfloat16* dst = out + hi * 9 * ts + lo;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) dst[(IdxT)tap * ts] = __float2bfloat16(__ldg(src + (E.c ? 8 - tap : tap)));
+            for (int tap = 0; tap < 9; ++tap) dst[(IdxT)tap * ts] = ub_f2s(__ldg(src + (E.c ? 8 - tap : tap)));
             continue;
         }
         const IdxT grp = j / ts;
@@ -189,7 +236,7 @@ __device__ __forceinline__ void pack_entry_block(const PackEntry& E, const float
         for (IdxT t = 0; t < nloop; ++t) {
             IdxT d;
             const float v = pack_elem<IdxT>(E, w, i0 + t * ts, d);
-            out[d] = __float2bfloat16(v);
+            out[d] = ub_f2s(v);
         }
     }
 }
@@ -208,6 +255,8 @@ pack_table_kernel(const PackEntry* __restrict__ tab, int n, const float* __restr
     const PackEntry E = tab[lo];
     const float* w = params + E.src_off;
     __nv_bfloat16* out = dst_base + E.dst_off;
+    __shared__ float tile[32 * 73];
+    if (pack_conv3x3_tiled(E, w, out, tile)) return;
     if (E.total < (1ll << 30)) pack_entry_block<int>(E, w, out);
     else pack_entry_block<long long>(E, w, out);
 }

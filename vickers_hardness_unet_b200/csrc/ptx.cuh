@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -198,8 +199,10 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_
                                                               uint32_t b_mn_major) {
     uint32_t d = 0;
     d |= 1u << 4;                    // c_format  = F32
-    d |= 1u << 7;                    // a_format  = BF16
+#ifndef UB_F16
+    d |= 1u << 7;                    // a_format  = BF16 (0 = F16 in the -DUB_F16 build)
     d |= 1u << 10;                   // b_format  = BF16
+#endif
     d |= (a_mn_major & 1u) << 15;    // a_major   (0 = K-major)
     d |= (b_mn_major & 1u) << 16;    // b_major
     d |= ((N >> 3) & 0x3F) << 17;    // n_dim
@@ -309,12 +312,46 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// 16-bit storage format of activations and conv operands.  Default: bfloat16 (training needs its range).  -DUB_F16 builds
+// the SAME kernels with IEEE half operands (libunetb200_f16.so, inference only): tcgen05 kind::f16 runs both at the same
+// rate, half has 10 mantissa bits instead of 7 — the "smallest precision change" of the parity report
+// (profiles/parity_r2.json: logit error 6x smaller, mask IoU and mean-abs criteria of BASELINE.json met).  The helpers
+// keep their bf16 names; pointers stay typed __nv_bfloat16 (a 16-bit container either way).
+#ifdef UB_F16
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFFu))); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+__device__ __forceinline__ __nv_bfloat16 ub_f2s(float x) {
+    __nv_bfloat16_raw r;
+    r.x = __half_as_ushort(__float2half_rn(x));
+    return __nv_bfloat16(r);
+}
+__device__ __forceinline__ float ub_s2f(__nv_bfloat16 b) {
+    return __half2float(__ushort_as_half(static_cast<__nv_bfloat16_raw>(b).x));
+}
+__device__ __forceinline__ uint32_t ub_max2(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+constexpr uint32_t kNegInfPair = 0xFC00FC00u;
+#else
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ __nv_bfloat16 ub_f2s(float x) { return __float2bfloat16(x); }
+__device__ __forceinline__ float ub_s2f(__nv_bfloat16 b) { return __bfloat162float(b); }
+__device__ __forceinline__ uint32_t ub_max2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+constexpr uint32_t kNegInfPair = 0xFF80FF80u;
+#endif
 
 // Host side of PDL: every launch of the library goes through launch_k, which sets the programmatic stream
 // serialization attribute (UNETB200_PDL=0 in the environment turns it off for A/B measurements).

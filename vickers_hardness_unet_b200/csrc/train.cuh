@@ -59,9 +59,6 @@ struct TrainPlan {
     // scratch
     float* stat_part = nullptr;         // conv-epilogue statistic partials [4][num_sms][512][2]
     float* red_part = nullptr;          // reduction partials (BN backward / head / loss)
-    float* fuse_part = nullptr;         // partial rows written by the producers with fused BatchNorm-backward sums
-    BnBwdFuse head_fuse{};              // seg-head data gradient -> decoder.blocks.4 conv2 sums
-    int head_grid = 0, head_fuse_rows = 0;
     WgItem* items = nullptr;            // device work-item arena for all wgrad launches
     size_t items_cap = 0, items_used = 0;
     std::vector<WgItem> host_items;
@@ -654,9 +651,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         plan.bwd_aux[stage].push_back(nm.rfind("wgrad:", 0) == 0 ? 1 : 0);
     };
     // BN backward of unit ui given dA_in (gradient w.r.t. `a`): dz (+ optional masked gradient g_out)
-    // fused_rows > 0: the kernel that produced dA_in already left the per-block sums (fused_rows rows) in fused_part
-    auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out,
-                      int fused_rows = 0, float* fused_part = nullptr) {
+    auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out) {
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
         const BnRef& b = S.bns[c.bn];
@@ -666,8 +661,8 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         long long nb = (npix + ppb - 1) / ppb / 8;   // >= 8 block iterations (2 pixels each 4): few partial rows
         if (nb > 6 * SM) nb = 6 * SM;
         if (nb < 1) nb = 1;
-        const int nblocks = fused_rows > 0 ? fused_rows : (int)nb;
-        float* part = fused_rows > 0 ? fused_part : plan.red_part;
+        const int nblocks = (int)nb;
+        float* part = plan.red_part;
         // ReLU mask: units with a residual input (g_out != nullptr) read the stored activation; the others recompute
         // it from z with the forward's scale / shift; no ReLU (downsample BN) -> no mask
         const __nv_bfloat16* mask = (relu_mask && g_out) ? u.a : nullptr;
@@ -676,11 +671,10 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const float* gm = params + b.gamma;
         float* dgm = grads + b.gamma;
         float* dbt = grads + b.beta;
-        if (fused_rows == 0)
-            add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
-                launch_k(bn_bwd_reduce_kernel, nblocks, 256, 0, st, dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
-                return cudaGetLastError();
-            });
+        add_b(stage, "bn_bwd_reduce:" + c.name, [=](cudaStream_t st) {
+            launch_k(bn_bwd_reduce_kernel, nblocks, 256, 0, st, dA_in, mask, msc, msh, u.z, u.mean, u.invstd, part, npix, C);
+            return cudaGetLastError();
+        });
         add_b(stage, "bn_bwd_finalize:" + c.name, [=](cudaStream_t st) {
             launch_k(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, st, part, nblocks, C, (double)npix, gm, u.mean, u.invstd,
                                                                    dgm, dbt, u.coef);
@@ -692,18 +686,6 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             return cudaGetLastError();
         });
     };
-    // the two element-wise producers of a large dA (seg-head data gradient -> decoder.blocks.4 conv2, max-pool backward ->
-    // stem) accumulate the BatchNorm-backward sums of the consuming unit themselves (train_ops.cuh, BnBwdFuse)
-    plan.fuse_part = plan.red_part + (1u << 20);   // clear of the regular reduce rows (<= 6*SM*512*2) and the head's
-    {
-        const long long npx = (long long)N * H * W;
-        int g = ew_grid(npx, 256, SM);
-        if (g > 6 * SM) g = 6 * SM;
-        plan.head_grid = g;
-        plan.head_fuse_rows = getenv("UNETB200_NO_BN_FUSE") ? 0 : g;
-        const Unit& hu = plan.units[decs[4].u2];
-        plan.head_fuse = BnBwdFuse{plan.head_fuse_rows ? hu.z : nullptr, hu.mean, hu.invstd, hu.scale, hu.shift, plan.fuse_part};
-    }
     std::vector<int> stage_convs[4];
     auto add_wg = [&](int stage, const WgSpec& s) -> std::string {
         if (s.conv >= 0 && std::find(stage_convs[stage].begin(), stage_convs[stage].end(), s.conv) == stage_convs[stage].end())
@@ -811,8 +793,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const DecRec& r = decs[i];
         const Unit u1 = plan.units[r.u1], u2 = plan.units[r.u2];
         const ConvRef& c1 = S.convs[d.c1];
-        if (i == 4 && plan.head_fuse_rows > 0) bn_bwd(0, r.u2, d_cur, true, nullptr, plan.head_fuse_rows, plan.fuse_part);
-        else bn_bwd(0, r.u2, d_cur, true, nullptr);
+        bn_bwd(0, r.u2, d_cur, true, nullptr);
         if (!(err = wg_conv3(0, r.u2, u1.a, d.cout, u1.Ho, u1.Wo)).empty()) return err;
         if (!(err = dgrad3(0, r.u2, dA[r.u1], nullptr)).empty()) return err;
         bn_bwd(0, r.u1, dA[r.u1], true, nullptr);
@@ -1020,16 +1001,12 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         const int Hh = H / 2, Wh = W / 2;
         const __nv_bfloat16* dsk = d_skips[3];
         __nv_bfloat16* dF1 = dA[u_stem];
-        int pg = ew_grid((long long)N * Hh * Wh * 8, 256, SM);
-        if (pg > 6 * SM) pg = 6 * SM;
-        const bool pfuse = !getenv("UNETB200_NO_BN_FUSE");
-        const BnBwdFuse pf{pfuse ? us.z : nullptr, us.mean, us.invstd, us.scale, us.shift, plan.fuse_part};
         add_b(3, "maxpool_bwd:encoder.maxpool", [=](cudaStream_t st) {
-            launch_k(maxpool_bwd_kernel, pg, 256, 0, st, d_p1, pool_idx, dsk, dF1, N, Hh, Wh, 64, pf);
+            launch_k(maxpool_bwd_kernel, ew_grid((long long)N * Hh * Wh * 8, 256, SM), 256, 0, st, d_p1, pool_idx, dsk, dF1, N, Hh,
+                                                                                            Wh, 64);
             return cudaGetLastError();
         });
-        if (pfuse) bn_bwd(3, u_stem, dF1, true, nullptr, pg, plan.fuse_part);
-        else bn_bwd(3, u_stem, dF1, true, nullptr);
+        bn_bwd(3, u_stem, dF1, true, nullptr);
         if (swgrad_ok(H, W)) {
             // all seven filter rows from one pass over dZ (swgrad.cuh)
             SwgradLaunch WL;
@@ -1218,7 +1195,7 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
             if (npx >= (1ll << 31)) return ctx_fail(ctx, "train_backward: N*H*W must be below 2^31 (32-bit pixel arithmetic)");
-            launch_k(head_bwd_data_kernel, P.head_grid, 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W, P.head_fuse);
+            launch_k(head_bwd_data_kernel, ew_grid(npx, 256, SM), 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W);
             const int nb = 2 * SM;
             ctx->prof_mark("head_bwd_w:segmentation_head", st);
             launch_k(head_bwd_weight_kernel, nb, 256, 0, st, P.head_in, dlogits, P.red_part, N, H, W);

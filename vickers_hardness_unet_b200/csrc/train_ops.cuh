@@ -169,35 +169,6 @@ __device__ __forceinline__ void bn_partials_store(const float (&s1)[8], const fl
         partial[((size_t)blockIdx.x * C + c) * 2 + which] = acc;
     }
 }
-// Per-thread constants + accumulation of the fused form (the producer of dA accumulates the sums of the unit that will
-// consume it: no separate bn_bwd_reduce pass, one read of dA and one launch less).  g = bf16(dA) * [z*scale + shift > 0].
-struct BnBwdFuse {
-    const __nv_bfloat16* z;      // nullptr: nothing fused
-    const float* mean; const float* invstd; const float* scale; const float* shift;
-    float* partial;              // [gridDim.x][C][2]
-};
-struct BnBwdAcc {
-    float s1[8], s2[8], mu[8], is[8], sc[8], sh[8];
-    __device__ __forceinline__ void init(const BnBwdFuse& F, int c0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            s1[k] = s2[k] = 0.f;
-            mu[k] = F.mean[c0 + k]; is[k] = F.invstd[c0 + k]; sc[k] = F.scale[c0 + k]; sh[k] = F.shift[c0 + k];
-        }
-    }
-    __device__ __forceinline__ void add(const uint4& dA_bf16, const uint4& zv) {
-        float g[8], zz[8];
-        unpack8(dA_bf16, g);
-        unpack8(zv, zz);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float gg = (zz[k] * sc[k] + sh[k]) > 0.f ? g[k] : 0.f;
-            s1[k] += gg;
-            s2[k] += gg * (zz[k] - mu[k]) * is[k];
-        }
-    }
-};
-
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ a_mask,
                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -413,18 +384,12 @@ __global__ void maxpool3x3s2_idx_kernel(const __nv_bfloat16* __restrict__ in, __
 }
 
 // dF[n,h,w,c] = dSkip[n,h,w,c] + sum over the (<= 4) windows containing (h,w) whose recorded winner is (h,w) of dP[window]
-// fuse.z != nullptr: also accumulates the BatchNorm-backward sums of the unit that produced F (the stem), see BnBwdFuse;
-// blockDim = 256 and C/8 divides 256, so a thread's channel group is loop invariant.
-__global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restrict__ idx,
-                   const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
-                   int H, int W, int C, BnBwdFuse fuse) {
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restrict__ idx,
+                                   const __nv_bfloat16* __restrict__ dSkip, __nv_bfloat16* __restrict__ dF, int N,
+                                   int H, int W, int C) {
     griddep_launch();
     griddep_wait();
-    __shared__ float red[256 * 17];
     const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
-    BnBwdAcc bacc;
-    if (fuse.z) bacc.init(fuse, int(threadIdx.x % C8) * 8);
     const long long total = (long long)N * H * W * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -460,23 +425,17 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dP, const uint8_t* __restri
                 }
             }
         }
-        const uint4 ov = pack8(acc);
-        reinterpret_cast<uint4*>(dF)[i] = ov;
-        if (fuse.z) bacc.add(ov, __ldg(reinterpret_cast<const uint4*>(fuse.z) + i));
+        reinterpret_cast<uint4*>(dF)[i] = pack8(acc);
     }
-    if (fuse.z) bn_partials_store(bacc.s1, bacc.s2, C, fuse.partial, red);
 }
 
 // ------------------------------------------------------------------------------------------------ seg head backward
 // dA[n,h,w,c] = sum_{r,s} dL[n, h+1-r, w+1-s] * w[c][r][s]   (bf16 out, 16 channels per pixel)
 __global__ void __launch_bounds__(256)
 head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
-                     __nv_bfloat16* __restrict__ dA, int N, int H, int W, BnBwdFuse fuse) {
+                     __nv_bfloat16* __restrict__ dA, int N, int H, int W) {
     griddep_launch();
     griddep_wait();
-    __shared__ float red[256 * 17];
-    BnBwdAcc bacc;
-    if (fuse.z) bacc.init(fuse, int(threadIdx.x & 1) * 8);   // C = 16: channel group = half
     // thread = (pixel, 8-channel half): its 72 weights live in registers for the whole grid-stride loop (the first
     // version read 144 weights per pixel from shared memory: LDS-bound)
     const int half = threadIdx.x & 1;
@@ -506,11 +465,8 @@ head_bwd_data_kernel(const float* __restrict__ dL, const float* __restrict__ w,
             for (int k = 0; k < 9; ++k) a += d[k] * wr[c * 9 + k];
             o[c] = a;
         }
-        const uint4 ov = pack8(o);
-        reinterpret_cast<uint4*>(dA)[i * 2 + half] = ov;
-        if (fuse.z) bacc.add(ov, __ldg(reinterpret_cast<const uint4*>(fuse.z) + i * 2 + half));
+        reinterpret_cast<uint4*>(dA)[i * 2 + half] = pack8(o);
     }
-    if (fuse.z) bn_partials_store(bacc.s1, bacc.s2, 16, fuse.partial, red);
 }
 
 // per-block partials of dW[c][r][s] = sum_p A[p + (r-1, s-1)][c] * dL[p] and dbias = sum dL   -> partial[block][145]
@@ -824,7 +780,7 @@ __global__ void pack_dgrad_w_kernel(const float* __restrict__ w, __nv_bfloat16* 
         const int t = int((i / cout) % taps.n);
         const int ci = int(i / ((long long)cout * taps.n));
         out[(long long)ci * ld + col0 + t * cout + co] =
-            __float2bfloat16(w[(((long long)co * cin_total + ci0 + ci) * R + taps.r[t]) * S + taps.s[t]]);
+            ub_f2s(w[(((long long)co * cin_total + ci0 + ci) * R + taps.r[t]) * S + taps.s[t]]);
     }
 }
 // decoder conv1 dLow operand: 16 taps (ph,a,pw,b) -> out[c][t*cout + co] = sum_{r in R(ph,a), s in S(pw,b)} w[co][c][r][s]
@@ -847,7 +803,7 @@ __global__ void pack_dec1_dlow_w_kernel(const float* __restrict__ w, __nv_bfloat
         float v = 0.f;
         for (int r = r0; r <= r1; ++r)
             for (int s = s0; s <= s1; ++s) v += w[((long long)co * cin_total + c) * 9 + r * 3 + s];
-        out[i] = __float2bfloat16(v);
+        out[i] = ub_f2s(v);
     }
 }
 

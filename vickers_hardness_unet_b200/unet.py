@@ -75,8 +75,13 @@ class Unet(nn.Module):
     def __init__(self, encoder_name: str = "resnet34", encoder_depth: int = 5, encoder_weights=None,
                  decoder_use_batchnorm: bool = True, decoder_channels=(256, 128, 64, 32, 16),
                  decoder_attention_type=None, in_channels: int = 3, classes: int = 1, activation=None,
-                 aux_params=None, **kwargs):
+                 aux_params=None, precision: str = "bf16", **kwargs):
         super().__init__()
+        if precision not in _lib.LIB_PATHS:
+            raise ValueError(f"precision must be one of {sorted(_lib.LIB_PATHS)} (got {precision!r})")
+        # 16-bit storage format of activations / conv operands: "bf16" (default, training + inference) or "fp16"
+        # (inference only: same tensor-core rate, 10 instead of 7 mantissa bits).  May be changed before a forward.
+        self.precision = precision
         if encoder_name != "resnet34":
             raise ValueError(f"unet_b200 implements encoder_name='resnet34' only (got {encoder_name!r})")
         if encoder_weights not in (None, "imagenet"):
@@ -236,12 +241,16 @@ class Unet(nn.Module):
         if H % 32 or W % 32:
             raise ValueError(f"H and W must be divisible by 32 (got {H}x{W})")  # same rule as smp>=0.5
         c = self._ctx
-        if c is None or c.H != H or c.W != W or c.max_batch < N or c.device != x.device.index:
+        if self.training and self.precision != "bf16":
+            raise _lib.UnetB200Error("precision='fp16' is an inference mode: training needs bfloat16's range "
+                                     "(set model.precision = 'bf16' or call model.eval())")
+        if (c is None or c.H != H or c.W != W or c.max_batch < N or c.device != x.device.index
+                or c.precision != self.precision):
             if c is not None:
                 torch.cuda.synchronize(x.device)
                 c.close()
             mb = N if c is None or c.H != H or c.W != W else max(N, c.max_batch)
-            self._ctx = c = _lib.Context(x.device.index, mb, H, W)
+            self._ctx = c = _lib.Context(x.device.index, mb, H, W, self.precision)
             self._packed_version = None
         return c
 
@@ -329,11 +338,11 @@ class Unet(nn.Module):
         if H % 32 or W % 32:
             raise ValueError(f"H and W must be divisible by 32 (got {H}x{W})")
         c = self._ctx
-        if c is None or c.H != H or c.W != W or c.max_batch < N or c.device != dev.index:
+        if c is None or c.H != H or c.W != W or c.max_batch < N or c.device != dev.index or c.precision != self.precision:
             if c is not None:
                 torch.cuda.synchronize(dev)
                 c.close()
-            self._ctx = c = _lib.Context(dev.index, N, H, W)
+            self._ctx = c = _lib.Context(dev.index, N, H, W, self.precision)
             self._packed_version = None
         self._sync_weights(c, torch.cuda.current_stream(dev).cuda_stream, fold_bn=True)
         return c

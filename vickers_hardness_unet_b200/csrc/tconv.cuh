@@ -569,23 +569,21 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     op[1] = o[1];
                 }
                 if (P.stats) {
-                    // statistics of the bf16 values just stored (masked pixels contribute 0); fixed summation order
-                    float s1[16], s2[16];
+                    // statistics of the bf16 values just stored (masked pixels contribute 0); fixed summation order;
+                    // sums and sums of squares of the 16 channels share ONE 32-value reduction (hconv.cuh warp_reduce32)
+                    float sv[32];
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t w4[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
                             const float lo = valid[k] ? bf16_lo(w4[m]) : 0.f, hi = valid[k] ? bf16_hi(w4[m]) : 0.f;
-                            s1[j * 8 + 2 * m] = lo; s1[j * 8 + 2 * m + 1] = hi;
-                            s2[j * 8 + 2 * m] = lo * lo; s2[j * 8 + 2 * m + 1] = hi * hi;
+                            sv[j * 8 + 2 * m] = lo; sv[j * 8 + 2 * m + 1] = hi;
+                            sv[16 + j * 8 + 2 * m] = lo * lo; sv[16 + j * 8 + 2 * m + 1] = hi * hi;
                         }
                     }
-                    const float t1 = warp_reduce16(s1, lane), t2 = warp_reduce16(s2, lane);
-                    if (lane < 16) {
-                        cst[2 * (c0 + lane)] += t1;
-                        cst[2 * (c0 + lane) + 1] += t2;
-                    }
+                    const float t = warp_reduce32(sv, lane);   // lane l: sum (l < 16) / sum of squares (l >= 16) of channel l & 15
+                    cst[2 * (c0 + (lane & 15)) + (lane >> 4)] += t;
                 }
             }
             UB_TC_TICK(t_work)

@@ -54,7 +54,17 @@ struct TrainPlan {
     std::vector<LaunchFn> fwd;          // after input pack, before head
     std::vector<LaunchFn> bwd[4];       // stage 0: decoder, 1: layer4, 2: layer3, 3: layer2 + layer1 + stem
     std::vector<std::string> fwd_names, bwd_names[4];  // "<kind>:<layer>" per launch (profiling)
-    std::vector<uint8_t> bwd_aux[4];    // 1: weight-gradient launch, off the dz -> dgrad -> dA critical path (side stream)
+    // forward scheduling: 0 = main stream; 1 = side stream after a fork (first launch of a projection-shortcut branch:
+    // downsample conv -> BN finalize -> BN apply run beside conv1 -> BN of the same block); 2 = side stream, in order;
+    // 3 = main stream after joining the side stream (the block's second BN apply reads the shortcut)
+    std::vector<uint8_t> fwd_aux;
+    float* stat_part_aux = nullptr;     // statistic partials of the shortcut branch (it runs concurrently with conv1's)
+    // how a backward launch is scheduled: 0 = main stream (the dz -> dgrad -> dA critical path); 1 = side stream after a
+    // fork from the main stream (weight gradients, decoder skip gradients: nothing on the path needs them soon);
+    // 2 = side stream without a fork (the stage's gradient unpack: depends only on that stage's weight gradients, which
+    // precede it on the side stream); 3 = main stream, but first wait for the decoder skip gradients (their consumers)
+    std::vector<uint8_t> bwd_aux[4];
+    float* head_part = nullptr;         // partial rows of the seg-head weight gradient (runs on the side stream)
     int n_fwd = 0, n_bwd = 0;
     // scratch
     float* stat_part = nullptr;         // conv-epilogue statistic partials [4][num_sms][512][2]
@@ -93,12 +103,13 @@ struct TrainState {
     // (measured: 8.42 -> 7.82 ms per step).  UNETB200_NO_AUX=1 keeps everything in order.  Running the dgrad operand
     // re-pack there as well, under the forward, was measured and dropped: it slows the forward by what it saves.
     cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_skip = nullptr;
     bool use_aux = true;
     ~TrainState() {
         if (aux) cudaStreamDestroy(aux);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_skip) cudaEventDestroy(ev_skip);
         plans.clear();
         cudaFree(arena);
         cudaFree(gpk);
@@ -342,6 +353,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     plan.dbg.clear();
     plan.fwd.clear();
     plan.fwd_names.clear();
+    plan.fwd_aux.clear();
     for (auto& b : plan.bwd) b.clear();
     for (auto& b : plan.bwd_names) b.clear();
     for (auto& b : plan.bwd_aux) b.clear();
@@ -351,7 +363,9 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     // fp32 scratch carved from the same arena
     auto take_f = [&](size_t n) { return reinterpret_cast<float*>(A.take((long long)n * 2)); };
     plan.stat_part = take_f((size_t)4 * SM * 512 * 2);
+    plan.stat_part_aux = take_f((size_t)SM * 512 * 2);
     plan.red_part = take_f((size_t)2048 * 512 * 2);
+    plan.head_part = take_f((size_t)2 * SM * 145);
 
     auto new_unit = [&](int conv, int Hin, int Win) -> int {
         const ConvRef& c = S.convs[conv];
@@ -365,12 +379,15 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         plan.units.push_back(u);
         return (int)plan.units.size() - 1;
     };
+    int fwd_how = 0;   // scheduling class of the launches being added (TrainPlan::fwd_aux)
     auto add_f = [&](const std::string& nm, LaunchFn f) {
         plan.fwd.push_back(std::move(f));
         plan.fwd_names.push_back(nm);
+        plan.fwd_aux.push_back((uint8_t)fwd_how);
+        if (fwd_how == 1) fwd_how = 2;   // the rest of a side-stream branch follows in order
     };
     // BN finalize + apply after a conv whose statistics partial rows are described by segs
-    auto add_bn_fwd = [&](int ui, StatSegs segs, const __nv_bfloat16* residual, int relu) {
+    auto add_bn_fwd = [&](int ui, StatSegs segs, const __nv_bfloat16* residual, int relu, bool join_side = false) {
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
         const BnRef& b = S.bns[c.bn];
@@ -387,11 +404,14 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                                                                u.scale, u.shift, u.mean, u.invstd);
             return cudaGetLastError();
         });
+        const int how0 = fwd_how;
+        if (join_side) fwd_how = 3;
         add_f("bn_apply:" + c.name, [=](cudaStream_t st) {
             launch_k(bn_apply_kernel, ew_grid2(npix * (C / 8), 256, SM, C / 8), 256, 0, st, u.z, u.scale, u.shift, residual, relu, u.a,
                                                                              npix, C);
             return cudaGetLastError();
         });
+        if (join_side) fwd_how = how0;
     };
 
     // ---------------------------------------------------------------- forward graph
@@ -401,15 +421,16 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     struct DecRec { int u1, u2; __nv_bfloat16* low; __nv_bfloat16* skip; __nv_bfloat16* d_skip; int Hl, Wl; };
     std::vector<DecRec> decs;
 
-    auto fwd_unit = [&](int ui, const void* in, const __nv_bfloat16* residual, int relu) -> std::string {
+    auto fwd_unit = [&](int ui, const void* in, const __nv_bfloat16* residual, int relu, bool join_side = false) -> std::string {
         const Unit u = plan.units[ui];
         const ConvRef& c = S.convs[u.conv];
         if (dry) return "";
+        float* stat_buf = fwd_how ? plan.stat_part_aux : plan.stat_part;   // side-stream branch: its own partial rows
         EpilogueDesc ep;
-        ep.stats = plan.stat_part;
+        ep.stats = stat_buf;
         StatSegs segs;
         memset(&segs, 0, sizeof(segs));
-        segs.n = 1; segs.ptr[0] = plan.stat_part;
+        segs.n = 1; segs.ptr[0] = stat_buf;
         if (u.conv == S.stem) {
             TconvLaunch TL;
             std::string e = tconv_build_stem(TL, in, ctx->wpk + c.wpk, N, H, W, u.z, ep, ctx->d_err, SM);
@@ -445,7 +466,7 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             add_f("conv_fwd:" + c.name, [L](cudaStream_t st) { return igemm_launch(L, st); });
             segs.rows[0] = L.grid;
         }
-        add_bn_fwd(ui, segs, residual, relu);
+        add_bn_fwd(ui, segs, residual, relu, join_side);
         return "";
     };
 
@@ -477,13 +498,16 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
             r.u2 = new_unit(blk.c2, ho, wo);
             r.ud = blk.ds >= 0 ? new_unit(blk.ds, h, w) : -1;
             r.g = A.take((long long)N * ho * wo * S.convs[blk.c2].cout);
-            if (!(err = fwd_unit(r.u1, cur, nullptr, 1)).empty()) return err;
             const __nv_bfloat16* ident = cur;
             if (r.ud >= 0) {
+                // projection shortcut first, on the side stream: conv1x1/s2 -> BN beside conv1 -> BN -> conv2 of this block
+                fwd_how = 1;
                 if (!(err = fwd_unit(r.ud, cur, nullptr, 0)).empty()) return err;
+                fwd_how = 0;
                 ident = plan.units[r.ud].a;
             }
-            if (!(err = fwd_unit(r.u2, plan.units[r.u1].a, ident, 1)).empty()) return err;
+            if (!(err = fwd_unit(r.u1, cur, nullptr, 1)).empty()) return err;
+            if (!(err = fwd_unit(r.u2, plan.units[r.u1].a, ident, 1, r.ud >= 0)).empty()) return err;
             cur = plan.units[r.u2].a;
             h = ho; w = wo;
             blocks.push_back(r);
@@ -648,7 +672,11 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
     auto add_b = [&](int stage, const std::string& nm, LaunchFn f) {
         plan.bwd[stage].push_back(std::move(f));
         plan.bwd_names[stage].push_back(nm);
-        plan.bwd_aux[stage].push_back(nm.rfind("wgrad:", 0) == 0 ? 1 : 0);
+        uint8_t how = 0;
+        if (nm.rfind("wgrad:", 0) == 0 || nm.rfind("dgrad_skip:", 0) == 0) how = 1;
+        else if (nm.rfind("unpack_grads:", 0) == 0) how = 2;
+        else if (nm.rfind("maxpool_bwd:", 0) == 0 || nm.rfind("dgrad_s2+skip:", 0) == 0) how = 3;
+        plan.bwd_aux[stage].push_back(how);
     };
     // BN backward of unit ui given dA_in (gradient w.r.t. `a`): dz (+ optional masked gradient g_out)
     auto bn_bwd = [&](int stage, int ui, const __nv_bfloat16* dA_in, bool relu_mask, __nv_bfloat16* g_out) {
@@ -990,7 +1018,9 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
                 err = igemm_build(L, s, 2, taps.data(), (int)taps.size(), chunk, T.wdg + o, ntap * c1.cout, c1.cin, ov,
                                   ep, ctx->d_err, SM);
                 if (!err.empty()) return c1.name + " dgrad s2: " + err;
-                add_b(stage, "dgrad_s2:" + c1.name + "[parity]", [L](cudaStream_t st) { return igemm_launch(L, st); });
+                // "+skip": reads a decoder skip gradient, which the side stream produces (see TrainPlan::bwd_aux)
+                add_b(stage, std::string(d_skip_in ? "dgrad_s2+skip:" : "dgrad_s2:") + c1.name + "[parity]",
+                      [L](cudaStream_t st) { return igemm_launch(L, st); });
                 o += (long long)c1.cin * ntap * c1.cout;
             }
         }
@@ -1118,6 +1148,7 @@ inline int ctx_train_prepare(Ctx* ctx, int N, const float* params, float* buffer
         UB_CUDA(cudaStreamCreateWithFlags(&T.aux, cudaStreamNonBlocking));
         UB_CUDA(cudaEventCreateWithFlags(&T.ev_fork, cudaEventDisableTiming));
         UB_CUDA(cudaEventCreateWithFlags(&T.ev_join, cudaEventDisableTiming));
+        UB_CUDA(cudaEventCreateWithFlags(&T.ev_skip, cudaEventDisableTiming));
     }
     size_t need = 0;
     {
@@ -1161,9 +1192,33 @@ inline int ctx_train_forward(Ctx* ctx, const float* x, float* logits, const floa
     else
         launch_k(pack_input_kernel, ew_grid((long long)N * H * ((W + 8) / 2), 256, ctx->num_sms), 256, 0, st, x, P->xp, N, H, W);
     UB_CUDA(cudaGetLastError());
-    for (size_t i = 0; i < P->fwd.size(); ++i) {
-        ctx->prof_mark(P->fwd_names[i], st);
-        UB_CUDA(P->fwd[i](st));
+    {
+        TrainState& T = *train_state(ctx);
+        const bool side = T.use_aux && !ctx->prof_on;
+        bool aux_pending = false;
+        for (size_t i = 0; i < P->fwd.size(); ++i) {
+            const int how = side ? P->fwd_aux[i] : 0;
+            if (how == 1 || how == 2) {
+                if (how == 1) {
+                    UB_CUDA(cudaEventRecord(T.ev_fork, st));
+                    UB_CUDA(cudaStreamWaitEvent(T.aux, T.ev_fork, 0));
+                }
+                UB_CUDA(P->fwd[i](T.aux));
+                aux_pending = true;
+                continue;
+            }
+            if (how == 3 && aux_pending) {
+                UB_CUDA(cudaEventRecord(T.ev_join, T.aux));
+                UB_CUDA(cudaStreamWaitEvent(st, T.ev_join, 0));
+                aux_pending = false;
+            }
+            ctx->prof_mark(P->fwd_names[i], st);
+            UB_CUDA(P->fwd[i](st));
+        }
+        if (aux_pending) {   // not expected: every side branch is joined by its block
+            UB_CUDA(cudaEventRecord(T.ev_join, T.aux));
+            UB_CUDA(cudaStreamWaitEvent(st, T.ev_join, 0));
+        }
     }
     ctx->prof_mark("head_fwd:segmentation_head", st);
     UB_CUDA(tconv_launch_head(P->head_fwd, logits, nullptr, nullptr, 0.f, st));
@@ -1181,6 +1236,14 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
     const NetSpec& S = ctx->spec;
     const int H = ctx->H, W = ctx->W, SM = ctx->num_sms;
     if (stage_first < 0 || stage_last > 3 || stage_first > stage_last) return ctx_fail(ctx, "train_backward: bad stage range");
+    const bool side = T.use_aux && !ctx->prof_on;
+    bool aux_pending = false, skip_pending = false;
+    auto fork = [&]() -> int {   // the side stream continues from here: everything enqueued on `st` so far precedes it
+        UB_CUDA(cudaEventRecord(T.ev_fork, st));
+        UB_CUDA(cudaStreamWaitEvent(T.aux, T.ev_fork, 0));
+        aux_pending = true;
+        return 0;
+    };
     for (int stage = stage_first; stage <= stage_last; ++stage) {
         if (stage == 0) {
             if (!dlogits) return ctx_fail(ctx, "train_backward: dlogits is null");
@@ -1191,41 +1254,54 @@ inline int ctx_train_backward(Ctx* ctx, const float* dlogits, int N, int stage_f
             UB_CUDA(cudaMemsetAsync(P.grads + S.convs[S.stem].w, 0, (size_t)64 * 147 * sizeof(float), st));
             ctx->prof_mark("pack_dgrad:all", st);
             if (train_pack_dgrad(ctx, T, P.params, st)) return 1;
-            ctx->prof_mark("head_bwd:segmentation_head", st);
             const ConvRef& hc = S.convs[S.head];
             const long long npx = (long long)N * H * W;
             if (npx >= (1ll << 31)) return ctx_fail(ctx, "train_backward: N*H*W must be below 2^31 (32-bit pixel arithmetic)");
-            launch_k(head_bwd_data_kernel, ew_grid(npx, 256, SM), 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W);
+            // seg-head weight gradient: needs only dlogits and the saved head input -> side stream
             const int nb = 2 * SM;
+            cudaStream_t hs = st;
+            if (side) {
+                if (fork()) return 1;
+                hs = T.aux;
+            }
             ctx->prof_mark("head_bwd_w:segmentation_head", st);
-            launch_k(head_bwd_weight_kernel, nb, 256, 0, st, P.head_in, dlogits, P.red_part, N, H, W);
-            launch_k(sum_rows_kernel, (145 + 7) / 8, 256, 0, st, P.red_part, nb, 145, P.grads + hc.w);
+            launch_k(head_bwd_weight_kernel, nb, 256, 0, hs, P.head_in, dlogits, P.head_part, N, H, W);
+            launch_k(sum_rows_kernel, (145 + 7) / 8, 256, 0, hs, P.head_part, nb, 145, P.grads + hc.w);
+            ctx->prof_mark("head_bwd:segmentation_head", st);
+            launch_k(head_bwd_data_kernel, ew_grid(npx, 256, SM), 256, 0, st, dlogits, ctx->head_w, P.d_head_in, N, H, W);
             UB_CUDA(cudaGetLastError());
         }
-        const bool side = T.use_aux && !ctx->prof_on;
-        bool aux_pending = false;
-        auto join = [&]() -> int {
-            if (!aux_pending) return 0;
-            UB_CUDA(cudaEventRecord(T.ev_join, T.aux));
-            UB_CUDA(cudaStreamWaitEvent(st, T.ev_join, 0));
-            aux_pending = false;
-            return 0;
-        };
         for (size_t i = 0; i < P.bwd[stage].size(); ++i) {
-            if (side && P.bwd_aux[stage][i]) {
-                // everything this weight gradient reads (dz of its unit, saved activations) precedes it on `st`
-                UB_CUDA(cudaEventRecord(T.ev_fork, st));
-                UB_CUDA(cudaStreamWaitEvent(T.aux, T.ev_fork, 0));
+            const int how = side ? P.bwd_aux[stage][i] : 0;
+            if (how == 1) {
+                // everything this launch reads (dz of its unit, saved activations) precedes it on `st`
+                if (fork()) return 1;
+                UB_CUDA(P.bwd[stage][i](T.aux));
+                if (P.bwd_names[stage][i].rfind("dgrad_skip:", 0) == 0) {
+                    UB_CUDA(cudaEventRecord(T.ev_skip, T.aux));
+                    skip_pending = true;
+                }
+                continue;
+            }
+            if (how == 2) {   // in order behind this stage's weight gradients on the side stream
                 UB_CUDA(P.bwd[stage][i](T.aux));
                 aux_pending = true;
                 continue;
             }
-            if (P.bwd_names[stage][i].rfind("unpack_grads:", 0) == 0 && join()) return 1;
+            if (how == 3 && skip_pending) {
+                UB_CUDA(cudaStreamWaitEvent(st, T.ev_skip, 0));   // the latest decoder skip gradient (and all before it)
+                skip_pending = false;
+            }
             ctx->prof_mark(P.bwd_names[stage][i], st);
             UB_CUDA(P.bwd[stage][i](st));
         }
-        if (join()) return 1;   // a stage's parameter gradients are final when the call returns (in stream order)
         if (stage == 3) ctx->prof_mark("end:backward", st);
+    }
+    // the parameter gradients of the stages just run are final when the call returns (in stream order): a data-parallel
+    // caller runs one stage per call and all-reduces its bucket next; a single-GPU caller joins once, after stage 3
+    if (aux_pending) {
+        UB_CUDA(cudaEventRecord(T.ev_join, T.aux));
+        UB_CUDA(cudaStreamWaitEvent(st, T.ev_join, 0));
     }
     return 0;
 }

@@ -433,7 +433,13 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     // cout >= 32: whole sub-tiles leave through swizzled smem staging + TMA store (see TconvParams::stage_out)
     // parity mode: the four parity sub-tiles interleave into one dense hi-res tile (A/B: UNETB200_NO_PARITY_STAGE=1)
     static const bool par_stage = getenv("UNETB200_NO_PARITY_STAGE") == nullptr;
-    const uint32_t out_bytes = ((parity && par_stage) || (!parity && cout >= 32)) ? (uint32_t)nt * 128u * cout * 2u : 0u;
+    // Plain mode stores straight from registers: ONE 256-bit store (STG.E.256) per lane and 16-channel item.  The
+    // swizzled-smem + TMA-store staging it replaces for cout >= 32 was introduced when the two 128-bit stores per item
+    // serialised in the LSU; with 256-bit stores the register path is as fast or faster (layer1 conv2 61.5 -> 58 us,
+    // decoder.blocks.2 [skip] 61.5 -> 57.5 us at batch 32) and frees the staging buffers.  UNETB200_TC_STAGE=1 restores
+    // the staged epilogue for A/B runs.
+    static const bool reg_store = getenv("UNETB200_TC_STAGE") == nullptr;
+    const uint32_t out_bytes = ((parity && par_stage) || (!parity && cout >= 32 && !reg_store)) ? (uint32_t)nt * 128u * cout * 2u : 0u;
     L.occ = 1;
     int stages = 0;
     if (items <= 4 && 2 * acc_cols <= 256) {
@@ -524,9 +530,10 @@ inline std::string tconv_build_stem(TconvLaunch& L, const void* xp, const void* 
     L.iph = 2;                                       // 2 sub-tiles x 4 column groups over 16 epilogue warps
     P.stages = 4;
     P.nacc = 4;
-    P.stage_out = 1;                                 // one output row segment [64 ch x 128 px] per sub-tile through TMA
+    static const bool stem_reg = getenv("UNETB200_STEM_REGSTORE") != nullptr;   // A/B: 256-bit register stores instead
+    P.stage_out = stem_reg ? 0 : 1;                  // one output row segment [64 ch x 128 px] per sub-tile through TMA
     P.spw = 256;
-    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, P.stages, (uint32_t)nt * 128u * 128u).total + 1024;
+    L.smem = tconv_smem(P.w_bytes, P.stage_bytes, P.stages, stem_reg ? 0u : (uint32_t)nt * 128u * 128u).total + 1024;
     {
         uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
         uint64_t str[3] = {128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128};

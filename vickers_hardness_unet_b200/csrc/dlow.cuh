@@ -206,8 +206,7 @@ dlow_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUt
                     o1.y = pack_bf16(__uint_as_float(v[10]), __uint_as_float(v[11]));
                     o1.z = pack_bf16(__uint_as_float(v[12]), __uint_as_float(v[13]));
                     o1.w = pack_bf16(__uint_as_float(v[14]), __uint_as_float(v[15]));
-                    reinterpret_cast<uint4*>(op + c0)[0] = o0;
-                    reinterpret_cast<uint4*>(op + c0)[1] = o1;
+                    st_global_256(op + c0, o0, o1);
                 }
             }
             acc ^= 1;

@@ -353,6 +353,18 @@ __device__ __forceinline__ uint32_t ub_max2(uint32_t a, uint32_t b) {
 constexpr uint32_t kNegInfPair = 0xFF80FF80u;
 #endif
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): a thread's 16 channels of one pixel in ONE instruction (the
+// address must be 32-byte aligned).  For the conv epilogues' per-lane row accesses (a lane owns a pixel, lanes sit a
+// whole pixel row apart) this halves the LSU instructions and requests of the two-16-byte form.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 // Host side of PDL: every launch of the library goes through launch_k, which sets the programmatic stream
 // serialization attribute (UNETB200_PDL=0 in the environment turns it off for A/B measurements).
 inline bool pdl_enabled() {

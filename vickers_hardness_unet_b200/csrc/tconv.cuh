@@ -454,10 +454,8 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 valid[k] = k < n_mine && h0 + it_dh[k] < P.H && w0 + it_dw[k] < P.W;
                 if (kStack) valid[k] = valid[k] && lane >= 1 && lane <= 30;
                 if (P.residual && valid[k]) {  // issued before the accumulator wait: the loads overlap the tile's MMAs
-                    const uint4* rp = reinterpret_cast<const uint4*>(
-                        P.residual + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + it_c0[k]);
-                    rv[k][0] = __ldg(rp);
-                    rv[k][1] = __ldg(rp + 1);
+                    ld_global_nc_256(P.residual + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + it_c0[k],
+                                     rv[k][0], rv[k][1]);
                 }
             }
             UB_TC_TICK(t_a)
@@ -564,9 +562,7 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     so += 16;
                     *reinterpret_cast<uint4*>(sp + (so ^ (((so >> 7) & out_swz) << 4))) = o[1];
                 } else if (valid[k]) {
-                    uint4* op = reinterpret_cast<uint4*>(P.out + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + c0);
-                    op[0] = o[0];
-                    op[1] = o[1];
+                    st_global_256(P.out + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + c0, o[0], o[1]);
                 }
                 if (P.stats) {
                     // statistics of the bf16 values just stored (masked pixels contribute 0); fixed summation order;

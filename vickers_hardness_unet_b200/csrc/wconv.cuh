@@ -264,9 +264,8 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 uint32_t r[32];
                 uint4 rv[4];
                 if (!kRes32 && P.residual && valid) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        rv[j] = __ldg(reinterpret_cast<const uint4*>(P.residual + off + half * 32) + j);
+                    ld_global_nc_256(P.residual + off + half * 32, rv[0], rv[1]);
+                    ld_global_nc_256(P.residual + off + half * 32 + 16, rv[2], rv[3]);
                 }
                 tmem_ld32(taddr + half * 32, r);
                 tmem_ld_wait();
@@ -275,6 +274,7 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty(acc));
                 }
+                uint4 o_prev = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {  // 4 x 8 channels
                     const int c = cbase + half * 32 + j * 8;
@@ -293,10 +293,11 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     v[7] = __uint_as_float(r[j * 8 + 7]) * sc1.w + sh1.w;
                     if (kRes32) {
                         if (valid) {
-                            const float4 r0 = __ldg(reinterpret_cast<const float4*>(P.residual32 + off + half * 32 + j * 8));
-                            const float4 r1 = __ldg(reinterpret_cast<const float4*>(P.residual32 + off + half * 32 + j * 8) + 1);
-                            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                            uint4 r0, r1;
+                            ld_global_nc_256(P.residual32 + off + half * 32 + j * 8, r0, r1);
+                            v[0] += __uint_as_float(r0.x); v[1] += __uint_as_float(r0.y); v[2] += __uint_as_float(r0.z);
+                            v[3] += __uint_as_float(r0.w); v[4] += __uint_as_float(r1.x); v[5] += __uint_as_float(r1.y);
+                            v[6] += __uint_as_float(r1.z); v[7] += __uint_as_float(r1.w);
                         }
                     } else if (P.residual && valid) {
                         v[0] += bf16_lo(rv[j].x); v[1] += bf16_hi(rv[j].x);
@@ -313,7 +314,11 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     o.y = pack_bf16(v[2], v[3]);
                     o.z = pack_bf16(v[4], v[5]);
                     o.w = pack_bf16(v[6], v[7]);
-                    if (valid) *reinterpret_cast<uint4*>(P.out + off + half * 32 + j * 8) = o;
+                    if (j & 1) {   // two 8-channel groups = 32 bytes: one 256-bit store per pair
+                        if (valid) st_global_256(P.out + off + half * 32 + (j - 1) * 8, o_prev, o);
+                    } else {
+                        o_prev = o;
+                    }
                     if (P.stats) {
                         // statistics of the bf16 values just stored; 8 channels at a time over the warp's 32 pixels
                         const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
@@ -578,6 +583,7 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty);
                     }
+                    uint4 o_prev = make_uint4(0, 0, 0, 0);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int c = nt * 64 + half * 32 + j * 8;
@@ -585,11 +591,16 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         const float4 sc1 = *reinterpret_cast<const float4*>(ss + c + 4);
                         if (kOut32) {
                             if (valid) {
-                                float4* o32 = reinterpret_cast<float4*>(P.out32 + ooff + half * 32 + j * 8);
-                                o32[0] = make_float4(__uint_as_float(r[j * 8 + 0]) * sc0.x, __uint_as_float(r[j * 8 + 1]) * sc0.y,
-                                                     __uint_as_float(r[j * 8 + 2]) * sc0.z, __uint_as_float(r[j * 8 + 3]) * sc0.w);
-                                o32[1] = make_float4(__uint_as_float(r[j * 8 + 4]) * sc1.x, __uint_as_float(r[j * 8 + 5]) * sc1.y,
-                                                     __uint_as_float(r[j * 8 + 6]) * sc1.z, __uint_as_float(r[j * 8 + 7]) * sc1.w);
+                                uint4 lo, hi;   // 8 fp32 channels = one 256-bit store
+                                lo.x = __float_as_uint(__uint_as_float(r[j * 8 + 0]) * sc0.x);
+                                lo.y = __float_as_uint(__uint_as_float(r[j * 8 + 1]) * sc0.y);
+                                lo.z = __float_as_uint(__uint_as_float(r[j * 8 + 2]) * sc0.z);
+                                lo.w = __float_as_uint(__uint_as_float(r[j * 8 + 3]) * sc0.w);
+                                hi.x = __float_as_uint(__uint_as_float(r[j * 8 + 4]) * sc1.x);
+                                hi.y = __float_as_uint(__uint_as_float(r[j * 8 + 5]) * sc1.y);
+                                hi.z = __float_as_uint(__uint_as_float(r[j * 8 + 6]) * sc1.z);
+                                hi.w = __float_as_uint(__uint_as_float(r[j * 8 + 7]) * sc1.w);
+                                st_global_256(P.out32 + ooff + half * 32 + j * 8, lo, hi);
                             }
                             continue;
                         }
@@ -598,7 +609,11 @@ wpconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         o.y = pack_bf16(__uint_as_float(r[j * 8 + 2]) * sc0.z, __uint_as_float(r[j * 8 + 3]) * sc0.w);
                         o.z = pack_bf16(__uint_as_float(r[j * 8 + 4]) * sc1.x, __uint_as_float(r[j * 8 + 5]) * sc1.y);
                         o.w = pack_bf16(__uint_as_float(r[j * 8 + 6]) * sc1.z, __uint_as_float(r[j * 8 + 7]) * sc1.w);
-                        if (valid) *reinterpret_cast<uint4*>(op + half * 32 + j * 8) = o;
+                        if (j & 1) {   // 16 channels = one 256-bit store
+                            if (valid) st_global_256(op + half * 32 + (j - 1) * 8, o_prev, o);
+                        } else {
+                            o_prev = o;
+                        }
                     }
                 }
             }

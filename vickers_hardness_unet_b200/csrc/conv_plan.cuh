@@ -375,7 +375,8 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
         P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
         P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
         P.out = reinterpret_cast<__nv_bfloat16*>(out);
-        P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+        P.residual = ep.residual_f32 ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+        P.residual32 = ep.residual_f32 ? reinterpret_cast<const float*>(ep.residual.ptr) : nullptr;
         P.stats = ep.stats;
         P.err = err;
         L.occ = stack_occ2 ? 2 : 1;
@@ -422,7 +423,8 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     P.wpk = reinterpret_cast<const __nv_bfloat16*>(wpk);
     P.scale = ep.scale; P.shift = ep.shift; P.relu = ep.relu;
     P.out = reinterpret_cast<__nv_bfloat16*>(out);
-    P.residual = reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.residual = ep.residual_f32 ? nullptr : reinterpret_cast<const __nv_bfloat16*>(ep.residual.ptr);
+    P.residual32 = ep.residual_f32 ? reinterpret_cast<const float*>(ep.residual.ptr) : nullptr;
     P.stats = ep.stats;
     P.err = err;
     // occupancy: two CTAs per SM (8 epilogue warps each) when TMEM (<= 256 columns each), the accumulator column
@@ -431,8 +433,11 @@ inline std::string tconv_build(TconvLaunch& L, const void* src, int cin, bool pa
     if (items > 8) return "tconv: too many accumulator column groups";
     const int acc_cols = nt * cout;
     // cout >= 32: whole sub-tiles leave through swizzled smem staging + TMA store (see TconvParams::stage_out)
-    // parity mode: the four parity sub-tiles interleave into one dense hi-res tile (A/B: UNETB200_NO_PARITY_STAGE=1)
-    static const bool par_stage = getenv("UNETB200_NO_PARITY_STAGE") == nullptr;
+    // parity mode: with 256-bit stores the four parity sub-tiles also leave straight from registers (a lane writes the 32
+    // bytes of its pixel, every second pixel of a row: full 32-byte sectors that the L2 merges with the other parity's);
+    // decoder.blocks.4.conv1 96 -> 88 us, decoder.blocks.3.conv1 [up] 63 -> 57 us at batch 32.  UNETB200_PARITY_STAGE=1
+    // restores the interleaved smem tile + single TMA store of round 1 for A/B runs.
+    static const bool par_stage = getenv("UNETB200_PARITY_STAGE") != nullptr;
     // Plain mode stores straight from registers: ONE 256-bit store (STG.E.256) per lane and 16-channel item.  The
     // swizzled-smem + TMA-store staging it replaces for cout >= 32 was introduced when the two 128-bit stores per item
     // serialised in the LSU; with 256-bit stores the register path is as fast or faster (layer1 conv2 61.5 -> 58 us,

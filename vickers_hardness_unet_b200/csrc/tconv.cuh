@@ -46,6 +46,8 @@ struct TconvParams {
     int relu;
     __nv_bfloat16* out;             // [N, H, W, cout]
     const __nv_bfloat16* residual;  // same shape or nullptr
+    const float* residual32;        // fp32 residual of the same shape (training forward of decoder.blocks.2.conv1: the
+                                    // partial over the up-sampled channels stays fp32), or nullptr
     float* stats;                   // [gridDim.x][cout][2] or nullptr
     int stage_out;                  // 1: the epilogue transposes through swizzled smem and stores whole sub-tiles with TMA
                                     // (cout >= 32: a register store of 16 channels per pixel touches 32 different 128-byte
@@ -523,6 +525,17 @@ tconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) * sc.y + sh.y;
                     v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) * sc.z + sh.z;
                     v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) * sc.w + sh.w;
+                }
+                if (P.residual32 && valid[k]) {   // 16 fp32 channels = two 256-bit loads (one launch per train step: not prefetched)
+                    const float* rp = P.residual32 + (size_t)(pix0 + it_dh[k] * P.W + it_dw[k]) * P.cout + c0;
+                    uint4 f[4];
+                    ld_global_nc_256(rp, f[0], f[1]);
+                    ld_global_nc_256(rp + 8, f[2], f[3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[4 * j + 0] += __uint_as_float(f[j].x); v[4 * j + 1] += __uint_as_float(f[j].y);
+                        v[4 * j + 2] += __uint_as_float(f[j].z); v[4 * j + 3] += __uint_as_float(f[j].w);
+                    }
                 }
                 if (P.residual && valid[k]) {
 #pragma unroll

@@ -528,9 +528,11 @@ inline std::string build_train_plan(Ctx* ctx, TrainState& T, int N, TrainPlan& p
         r.u2 = new_unit(d.c2, 2 * h, 2 * w);
         // The wide blocks' split (tc == 4: wpconv over the up-sampled channels, then wconv over the skip channels with
         // the partial as residual) with an fp32 partial: a bf16 partial (what inference stores) moved the 10-step
-        // training loss from 7e-4 to 1.04e-3 relative (north_star asks 1e-3).  decoder.blocks.2 (skip part on tconv,
-        // bf16 residual only) keeps the four parity launches of the tap-table kernel.
-        const bool wide_split = S.convs[d.c1].tc == 4 && wconv_ok(d.cskip, d.cout) && !getenv("UNETB200_NO_TRAIN_SPLIT");
+        // training loss from 7e-4 to 1.04e-3 relative (north_star asks 1e-3).  decoder.blocks.2 takes the same route with
+        // its skip part on tconv (fp32 residual, TconvParams::residual32) instead of four parity launches of the
+        // tap-table kernel (176 -> ~70 us per step; UNETB200_NO_TRAIN_SPLIT2=1 restores them).
+        const bool wide_split = S.convs[d.c1].tc == 4 && !getenv("UNETB200_NO_TRAIN_SPLIT") &&
+                                (wconv_ok(d.cskip, d.cout) || !getenv("UNETB200_NO_TRAIN_SPLIT2"));
         __nv_bfloat16* zup = nullptr;
         if (wide_split) zup = A.take(2ll * N * (2 * h) * (2 * w) * d.cout);   // fp32
         else if (S.convs[d.c1].tc == 3) zup = A.take((long long)N * (2 * h) * (2 * w) * d.cout);

@@ -201,53 +201,37 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 
 // ------------------------------------------------------------------------------------------------ max-pool 3x3 s2 p1
 __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) { return ub_max2(a, b); }
-// A thread owns 8 channels of FOUR vertically adjacent outputs: the 9 input rows they touch are reduced along the
-// window columns once (3 loads each) and every second row maximum is shared by two outputs: 27 loads per 4 outputs
-// instead of 36 (the kernel is bound by L1 / L2 requests, not DRAM: 2.25x window overlap).  Ho % 4 == 0 is not required.
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int N,
                                     int H, int W, int C) {
     griddep_launch();
     griddep_wait();
-    const int Ho = H / 2, Wo = W / 2, C8 = C / 8, Hq = (Ho + 3) / 4;
-    const long long total = (long long)N * Hq * Wo * C8;
+    const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+    const long long total = (long long)N * Ho * Wo * C8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         // 32-bit index arithmetic (the host keeps element counts below 2^32): 64-bit div/mod per element is ~100 instructions
         const unsigned u = (unsigned)i, t1 = u / (unsigned)C8, t2 = t1 / (unsigned)Wo;
         const int c8 = int(u - t1 * (unsigned)C8);
         const int wo = int(t1 - t2 * (unsigned)Wo);
-        const int n = int(t2 / (unsigned)Hq);
-        const int ho0 = int(t2 - (unsigned)n * (unsigned)Hq) * 4;
-        uint4 rm[9];   // maximum over the window columns of input rows 2*ho0 - 1 .. 2*ho0 + 7
+        const int n = int(t2 / (unsigned)Ho);
+        const int ho = int(t2 - (unsigned)n * (unsigned)Ho);
+        uint4 m = make_uint4(kNegInfPair, kNegInfPair, kNegInfPair, kNegInfPair);  // -inf pairs
 #pragma unroll
-        for (int r = 0; r < 9; ++r) {
-            uint4 m = make_uint4(kNegInfPair, kNegInfPair, kNegInfPair, kNegInfPair);  // -inf pairs
-            const int h = ho0 * 2 - 1 + r;
-            if (h >= 0 && h < H) {
+        for (int r = 0; r < 3; ++r) {
+            const int h = ho * 2 - 1 + r;
+            if (h < 0 || h >= H) continue;
 #pragma unroll
-                for (int s2 = 0; s2 < 3; ++s2) {
-                    const int w = wo * 2 - 1 + s2;
-                    if (w < 0 || w >= W) continue;
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((long long)n * H + h) * W + w) * C) + c8);
-                    m.x = bf16x2_max(m.x, v.x);
-                    m.y = bf16x2_max(m.y, v.y);
-                    m.z = bf16x2_max(m.z, v.z);
-                    m.w = bf16x2_max(m.w, v.w);
-                }
+            for (int s = 0; s < 3; ++s) {
+                const int w = wo * 2 - 1 + s;
+                if (w < 0 || w >= W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((long long)n * H + h) * W + w) * C) + c8);
+                m.x = bf16x2_max(m.x, v.x);
+                m.y = bf16x2_max(m.y, v.y);
+                m.z = bf16x2_max(m.z, v.z);
+                m.w = bf16x2_max(m.w, v.w);
             }
-            rm[r] = m;
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int ho = ho0 + k;
-            if (ho >= Ho) break;
-            uint4 m = rm[2 * k];
-            m.x = bf16x2_max(bf16x2_max(m.x, rm[2 * k + 1].x), rm[2 * k + 2].x);
-            m.y = bf16x2_max(bf16x2_max(m.y, rm[2 * k + 1].y), rm[2 * k + 2].y);
-            m.z = bf16x2_max(bf16x2_max(m.z, rm[2 * k + 1].z), rm[2 * k + 2].z);
-            m.w = bf16x2_max(bf16x2_max(m.w, rm[2 * k + 1].w), rm[2 * k + 2].w);
-            reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * C)[c8] = m;
-        }
+        reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * C)[c8] = m;
     }
 }
 

@@ -319,18 +319,19 @@ wconv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     } else {
                         o_prev = o;
                     }
-                    if (P.stats) {
-                        // statistics of the bf16 values just stored; 8 channels at a time over the warp's 32 pixels
-                        const uint32_t w4[4] = {o.x, o.y, o.z, o.w};
-                        float s1[16];
+                    if (P.stats && (j & 1)) {
+                        // statistics of the bf16 values just stored, 16 channels (this group and the previous one) at a
+                        // time over the warp's 32 pixels: [16 sums | 16 sums of squares] in ONE 32-value reduction
+                        const uint32_t w8[8] = {o_prev.x, o_prev.y, o_prev.z, o_prev.w, o.x, o.y, o.z, o.w};
+                        float sv[32];
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const float lo = valid ? bf16_lo(w4[m]) : 0.f, hi = valid ? bf16_hi(w4[m]) : 0.f;
-                            s1[2 * m] = lo; s1[2 * m + 1] = hi;
-                            s1[8 + 2 * m] = lo * lo; s1[8 + 2 * m + 1] = hi * hi;
+                        for (int m = 0; m < 8; ++m) {
+                            const float lo = valid ? bf16_lo(w8[m]) : 0.f, hi = valid ? bf16_hi(w8[m]) : 0.f;
+                            sv[2 * m] = lo; sv[2 * m + 1] = hi;
+                            sv[16 + 2 * m] = lo * lo; sv[16 + 2 * m + 1] = hi * hi;
                         }
-                        const float t = warp_reduce16(s1, lane);  // lane l < 8: sum of channel l; 8 <= l < 16: sum of squares
-                        if (lane < 16) cst[2 * (c + (lane & 7)) + (lane >> 3)] += t;
+                        const float t = warp_reduce32(sv, lane);  // lane l: sum (l < 16) / sum of squares (l >= 16) of channel l & 15
+                        cst[2 * (c - 8 + (lane & 15)) + (lane >> 4)] += t;
                     }
                 }
             }

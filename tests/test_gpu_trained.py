@@ -454,7 +454,7 @@ def test_first_200_steps_track_the_fp32_oracle(trained):
           f"oracle {d_o:.4f} cuda {d_c:.4f}")
     _record("trajectory_200_steps", res)
     assert res["first_10_steps_rel_gap_max"] <= 5e-3, res["first_10_steps_rel_gap_max"]   # measured 2.4e-3
-    assert max(rel) <= 0.03, rel                                                            # measured <= 1.9e-2
+    assert max(rel) <= 0.05, rel                                                            # measured 1.3e-2 .. 2.7e-2
     assert m._ctx.device_error_flag() == 0
 
 

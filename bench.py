@@ -208,7 +208,8 @@ def bench_train(a, dev, rank, world, barrier):
     model = vb.Unet("resnet34", encoder_weights=None, in_channels=3, classes=1, activation=None).to(dev).train()
     if world > 1:
         vb.distributed.enable_data_parallel(model)
-    opt = vb.FusedAdamW(model, lr=5e-5, weight_decay=1e-4)  # /root/reference/train.py:606, RECOMMENDED_CFG lr
+    # /root/reference/train.py:606, RECOMMENDED_CFG lr; with N > 1 the update runs bucket by bucket as the all-reduces land
+    opt = vb.FusedAdamW(model, lr=5e-5, weight_decay=1e-4, overlap_allreduce=world > 1)
     crit = vb.losses.BCEDiceLoss()
     g = torch.Generator(device=dev).manual_seed(4321 + rank)
     xs = [torch.randn(B, 3, S, S, device=dev, generator=g) for _ in range(2)]

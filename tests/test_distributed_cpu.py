@@ -31,7 +31,12 @@ def _worker(rank, world, port, n, ranges, out):
         # stage order == backward completion order; buckets are launched one by one, then waited for together
         for stage in range(len(ranges)):
             red.reduce(stage)
+        # bucket-by-bucket waits (what FusedAdamW(overlap_allreduce=True) does), then finish() for whatever is left
+        red.wait(0)
+        red.wait(2)
+        assert sorted(st for _, _, st in red._pending) == [1, 3]
         red.finish()
+        assert not red._pending
         others = [torch.randn(n, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
         want = sum(others) / world
         ok = torch.allclose(flat, want, atol=1e-6) and not torch.equal(flat, mine)

@@ -29,6 +29,10 @@ class GradBucketReducer:
         backend = dist.get_backend(group)
         self._avg = backend == "nccl"  # gloo has no ReduceOp.AVG: sum, then scale
         self._pending = []
+        # True: the backward leaves the all-reduces in flight and the optimizer waits bucket by bucket
+        # (FusedAdamW(overlap_allreduce=True)): the update of buckets 0-2 (95 % of the parameters) then runs while the
+        # last, smallest bucket — which can only start when the backward ends — is still being reduced.
+        self.defer_finish = False
         covered = sorted(self.ranges)
         assert covered[0][0] == 0 and covered[-1][1] == flat_grads.numel() and all(
             a[1] == b[0] for a, b in zip(covered, covered[1:])), "buckets must tile the flat gradient array"
@@ -41,14 +45,23 @@ class GradBucketReducer:
         t = self.bucket(stage)
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         work = dist.all_reduce(t, op=op, group=self.group, async_op=True)
-        self._pending.append((work, t))
+        self._pending.append((work, t, stage))
 
-    def finish(self):
-        for work, t in self._pending:
+    def wait(self, stage: int):
+        """Wait for the all-reduce of one bucket (no-op if it is not in flight)."""
+        keep = []
+        for work, t, st in self._pending:
+            if st != stage:
+                keep.append((work, t, st))
+                continue
             work.wait()  # CUDA: makes the current stream wait for the collective; CPU (gloo): blocks
             if not self._avg:
                 t.mul_(1.0 / self.world)
-        self._pending.clear()
+        self._pending = keep
+
+    def finish(self):
+        for stage in sorted({st for _, _, st in self._pending}):
+            self.wait(stage)
 
 
 def _high_priority_nccl_group():

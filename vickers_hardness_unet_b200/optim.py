@@ -14,7 +14,7 @@ from . import _lib
 
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 grad_scale: float = 1.0, zero_grad: bool = False):
+                 grad_scale: float = 1.0, zero_grad: bool = False, overlap_allreduce: bool = False):
         if not hasattr(model, "flat_params"):
             raise TypeError("FusedAdamW takes the unet_b200.Unet module itself (it updates its flat parameter array)")
         super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
@@ -23,6 +23,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self._m = self._v = None
         self.grad_scale = float(grad_scale)
         self._zero = bool(zero_grad)
+        # data parallel only: leave the bucketed gradient all-reduces in flight at the end of backward and update bucket
+        # by bucket as they land (nothing may read `.grad` between loss.backward() and step(): no clipping / unscale_)
+        self._overlap = bool(overlap_allreduce)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -41,9 +44,21 @@ class FusedAdamW(torch.optim.Optimizer):
             raise _lib.UnetB200Error("FusedAdamW.step() before any forward/backward")
         stream = torch.cuda.current_stream(p.device).cuda_stream
         b1, b2 = grp["betas"]
-        ctx.check(ctx.lib.unetb200_adamw_step(ctx.handle, p.data_ptr(), g.data_ptr(), self._m.data_ptr(),
-                                              self._v.data_ptr(), p.numel(), float(grp["lr"]), float(b1), float(b2),
-                                              float(grp["eps"]), float(grp["weight_decay"]), self._step,
-                                              self.grad_scale, int(self._zero), stream), "adamw_step")
+        dp = getattr(model, "_dp", None)
+        if dp is not None and self._overlap:
+            dp.defer_finish = True              # from the next backward on
+            ranges = [(stage, b, e) for stage, (b, e) in enumerate(dp.ranges)]
+        else:
+            if dp is not None:
+                dp.finish()                     # a previous deferred backward may have left buckets in flight
+            ranges = [(None, 0, p.numel())]
+        for stage, b, e in ranges:              # bucket order = backward completion order = all-reduce launch order
+            if stage is not None:
+                dp.wait(stage)
+            ctx.check(ctx.lib.unetb200_adamw_step(ctx.handle, p.data_ptr() + 4 * b, g.data_ptr() + 4 * b,
+                                                  self._m.data_ptr() + 4 * b, self._v.data_ptr() + 4 * b, e - b,
+                                                  float(grp["lr"]), float(b1), float(b2), float(grp["eps"]),
+                                                  float(grp["weight_decay"]), self._step, self.grad_scale,
+                                                  int(self._zero), stream), "adamw_step")
         model._params_epoch += 1  # the library wrote the parameters: the bf16 operand caches are stale
         return loss

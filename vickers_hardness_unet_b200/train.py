@@ -66,8 +66,11 @@ class _UnetTrainFn(torch.autograd.Function):
                 ctx.check(ctx.lib.unetb200_train_backward(ctx.handle, dl.data_ptr(), N, stage, stage, stream),
                           "train_backward")
                 dp.reduce(stage)  # async all-reduce of this stage's bucket, overlapped with the next stage
-            dp.finish()
+            if not dp.defer_finish:
+                dp.finish()
         if prev is not None:
+            if dp is not None:
+                dp.finish()   # accumulation reads / writes the buckets: the all-reduces must have landed
             g.add_(prev)
         for p, v, a in zip(params, model._grad_views, attached):
             if p.grad is None:

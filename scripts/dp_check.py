@@ -20,8 +20,12 @@ def main():
     if rank == 0:
         print(f"dp_check world={world}: reduced-vs-emulated gradient rel-L2 {rel:.3e} max-abs {mx:.3e}; "
               f"identical across ranks: {same}")
+    ndiff = vb.distributed.dp_overlap_update_parity(dev, rank, world)
+    if rank == 0:
+        print(f"dp_check world={world}: parameters after 3 updates, bucket-wise overlapped vs joined all-reduce: "
+              f"{ndiff} of {vb.Unet('resnet34').flat_params.numel()} differ")
     dist.destroy_process_group()
-    if not (rel < 1e-3 and same):
+    if not (rel < 1e-3 and same and ndiff == 0):
         sys.exit(1)
     if rank == 0:
         print("DP_CHECK_OK")

@@ -146,3 +146,39 @@ def dp_gradient_parity(dev, rank: int, world: int, batch: int = 2, size: int = 1
         out[1] = float((got - acc).abs().max())
     dist.broadcast(out, 0)
     return float(out[0]), float(out[1]), bool(int(same.item()))
+
+
+def dp_overlap_update_parity(dev, rank: int, world: int, steps: int = 3):
+    """Second multi-GPU self-check: with FusedAdamW(overlap_allreduce=True) the optimizer updates bucket by bucket while
+    later all-reduces are still in flight; the parameters must be BITWISE what the joined path gives.  The gradients are
+    synthetic (seeded per rank and step, written into the flat gradient array; a real backward sums weight gradients with
+    fp32 atomics and AdamW turns last-bit noise of near-zero gradients into full-size steps, which would drown the
+    comparison), the buckets are reduced in backward-completion order exactly as `_UnetTrainFn.backward` does.
+    Returns the number of parameters that differ (max over ranks): must be 0."""
+    from .optim import FusedAdamW
+    from .unet import Unet
+
+    finals = []
+    for overlap in (False, True):
+        torch.manual_seed(11)
+        model = Unet("resnet34").to(dev).eval()
+        with torch.no_grad():
+            model(torch.zeros(1, 3, 64, 64, device=dev))     # creates the native context the optimizer call needs
+        enable_data_parallel(model)
+        dp = model._dp
+        opt = FusedAdamW(model, lr=1e-3, weight_decay=1e-4, overlap_allreduce=overlap)
+        dp.defer_finish = overlap
+        g = model.flat_grads
+        for s in range(steps):
+            gen = torch.Generator(device=dev).manual_seed(1000 * s + rank)
+            g.copy_(torch.randn(g.shape, device=dev, generator=gen))
+            for stage in range(len(dp.ranges)):
+                dp.reduce(stage)
+            if not dp.defer_finish:
+                dp.finish()
+            opt.step()
+        torch.cuda.synchronize(dev)
+        finals.append(model.flat_params.clone())
+    t = torch.tensor([float((finals[0] != finals[1]).sum())], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t)

@@ -1,10 +1,11 @@
 """GPU parity tests (B200): CUDA path through the C ABI vs the fp32 oracle.
 
-Per-kernel tests are point-wise (one bf16 output ulp).  Whole-model tests compare against the fp32 oracle AND against
-the oracle with the CUDA path's bf16 rounding points emulated in fp32 (oracle/bf16_emulation.py): BASELINE.json's
-north_star tolerance (2e-2 max-abs / 1e-3 mean-abs / IoU 0.999 vs fp32) is below what bf16 operands can deliver on this
-random-init network, so it is asserted only in the regime where bf16 can represent it (damped head) and the measured
-distances are printed for every case.
+Per-kernel tests are point-wise (one bf16 output ulp).  Whole-model tests on RANDOM-INIT weights compare against the
+fp32 oracle AND against the oracle with the CUDA path's bf16 rounding points emulated in fp32
+(oracle/bf16_emulation.py): such a network is ill-conditioned (rounding only weights and input to bf16 moves the fp32
+oracle by 0.08 mean-abs), so BASELINE.json's north_star tolerance (2e-2 max-abs / 1e-3 mean-abs / IoU 0.999 vs fp32) is
+evaluated where it was meant to hold — on a TRAINED network and the reference's own micrographs — in
+tests/test_gpu_trained.py, which also persists every distance (profiles/parity_r2.json).
 """
 import ctypes
 import os
@@ -99,6 +100,39 @@ def test_conv_kernel_parity(cfg):
     ctx.close()
 
 
+@pytest.mark.parametrize("cfg", [(2, 32, 32, 64, 64, 3, 1, True, True), (1, 16, 48, 128, 256, 3, 2, False, True)])
+def test_conv_kernel_parity_fp16_operand_build(cfg):
+    """The same kernel-level check through libunetb200_f16.so: IEEE-half operands and outputs (one half ulp = 2^-10)."""
+    N, H, W, cin, cout, k, stride, res, relu = cfg
+    lib = _lib.load("fp16")
+    ctx = _lib.Context(0, 1, 32, 32, "fp16")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
+    sc = torch.rand(cout, device="cuda", generator=g) + 0.5
+    sh = torch.randn(cout, device="cuda", generator=g) * 0.1
+    Ho, Wo = H // stride, W // stride
+    r = torch.randn(N, cout, Ho, Wo, device="cuda", generator=g) if res else None
+    xh = x.permute(0, 2, 3, 1).contiguous().to(torch.float16)
+    rh = r.permute(0, 2, 3, 1).contiguous().to(torch.float16) if res else None
+    out = torch.empty(N, Ho, Wo, cout, device="cuda", dtype=torch.float16)
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.check(lib.unetb200_conv_nhwc(ctx.handle, xh.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(),
+                                     rh.data_ptr() if res else None, int(relu), out.data_ptr(), None,
+                                     N, H, W, cin, cout, k, stride, st), "conv_nhwc")
+    torch.cuda.synchronize()
+    assert ctx.device_error_flag() == 0
+    ref = F.conv2d(xh.float().permute(0, 3, 1, 2), w.to(torch.float16).float(), None, stride, k // 2)
+    ref = ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    if res:
+        ref = ref + rh.float().permute(0, 3, 1, 2)
+    if relu:
+        ref = ref.relu()
+    err = (out.float().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err <= 2 ** -10 * ref.abs().max().item() + 2e-4, err
+    ctx.close()
+
+
 def _report(tag, got, emu, ref):
     d_ge, d_gr, d_er = (got - emu).abs(), (got - ref).abs(), (emu - ref).abs()
     print(f"\n[{tag}] |logit| max {ref.abs().max():.3f} mean {ref.abs().mean():.3f} | "
@@ -155,26 +189,6 @@ def test_model_parity(models, shape):
     assert _iou(got >= 0, ref >= 0) >= _iou(emu >= 0, ref >= 0) - 0.02
     assert torch.equal(mask > 0, torch.sigmoid(got) >= 0.5)
     assert m._ctx.device_error_flag() == 0
-
-
-def test_smooth_regime_meets_north_star_tolerance(models):
-    """With a damped head (logits O(0.05), i.e. the regime where 2e-2 / 1e-3 is representable in bf16) the
-    north_star tolerance itself is asserted against the fp32 oracle."""
-    o, m = models
-    _calibrate(o, m)
-    with torch.no_grad():
-        o.segmentation_head[0].weight.mul_(0.01)
-    m.load_state_dict(o.state_dict(), strict=True)
-    m.eval()
-    x = torch.randn(2, 3, 128, 128, generator=torch.Generator().manual_seed(9))
-    with torch.no_grad():
-        ref = o(x)
-        got = m(x.cuda()).cpu()
-    err = (got - ref).abs()
-    print(f"\n[damped head] |logit| max {ref.abs().max():.4f} max-abs err {err.max():.5f} mean-abs {err.mean():.6f}")
-    assert err.max().item() <= 2e-2 and err.mean().item() <= 1e-3  # BASELINE.json north_star tolerance
-    with torch.no_grad():
-        o.segmentation_head[0].weight.mul_(100.0)
 
 
 def test_structured_input(models):

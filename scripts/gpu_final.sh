@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence on one GPU: full GPU test suite, smoke, default bench (with CPU baseline), reference arm, clocks,
-# per-launch CUDA-event tables.  usage: scripts/gpu_final_s4.sh <tag>
-TAG=${1:-s4}
+# per-launch CUDA-event tables.  usage: scripts/gpu_final.sh <tag>
+TAG=${1:-s5}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 500 > gpurun_out/clocks_$TAG.csv &
 SMI=$!

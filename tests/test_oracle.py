@@ -111,3 +111,51 @@ def test_train_step_decreases_loss():
     losses = [oracle_train_step(m, opt, x, y) for _ in range(4)]
     assert losses[-1] < losses[0]
     assert int(m.encoder.bn1.num_batches_tracked) == 4
+
+
+def test_round_mantissa_matches_torch_casts():
+    """oracle.bf16_emulation.round_mantissa (the storage-precision sweep of tests/test_gpu_trained.py): 7 explicit mantissa
+    bits == bfloat16, 10 == float16 (inside half's exponent range), 23 == identity; round-to-nearest-even."""
+    from oracle.bf16_emulation import round_mantissa
+    g = torch.Generator().manual_seed(0)
+    t = torch.randn(4096, generator=g) * torch.logspace(-3, 3, 4096)
+    assert torch.equal(round_mantissa(t, 7), t.to(torch.bfloat16).float())
+    n = t[t.abs() > 1e-3]                                         # half is subnormal below 6.1e-5: mantissa bits only
+    assert torch.equal(round_mantissa(n, 10), n.to(torch.float16).float())
+    assert torch.equal(round_mantissa(t, 23), t)
+    tie = torch.tensor([1.0 + 2.0 ** -8, 1.0 + 3 * 2.0 ** -8])   # exactly half way between two bf16 values
+    assert torch.equal(round_mantissa(tie, 7), torch.tensor([1.0, 1.0 + 2.0 ** -6]))
+
+
+def test_emulated_forward_with_identity_rounding_is_the_oracle_forward():
+    """emulated_forward(rnd = identity) re-implements the oracle's forward with the CUDA path's structure (parity-folded
+    decoder conv1, explicit block wiring): it must reproduce OracleUnet.forward, and its taps name every activation the
+    CUDA path materialises (47 conv outputs + the max-pool)."""
+    from oracle.bf16_emulation import emulated_forward
+    o = build_oracle(42).eval()
+    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(2))
+    taps = {}
+    with torch.no_grad():
+        a = o(x)
+        b = emulated_forward(o, x, False, rnd=lambda t: t, taps=taps)
+    assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-5
+    assert len(taps) == 47 and "encoder.maxpool/out" in taps and "decoder.blocks.4.conv2.0.weight/out" in taps
+
+
+def test_vickers_fixture_is_the_reference_dataset_split():
+    """tests/golden/vickers_512.npz (built from /root/reference/data by tests/golden/make_vickers_fixture.py): 182
+    annotated micrographs, 10 % validation (train.py:560-565), 512 x 512 after centred padding, binary masks with the
+    foreground fraction the survey measured (mean 4.4 %)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import vickers_data as vd
+    d = vd.load_vickers()
+    assert d["train_u8"].shape == (164, 512, 512, 3) and d["val_u8"].shape == (18, 512, 512, 3)
+    assert d["train_y"].shape == (164, 1, 512, 512) and set(d["val_y"].unique().tolist()) <= {0.0, 1.0}
+    fg = float(torch.cat([d["train_y"], d["val_y"]]).mean())
+    assert 0.025 < fg < 0.05, fg            # 4.4 % of the 410 x 512 image area = 3.5 % of the padded square
+    x = vd.normalise(d["val_u8"][:1])
+    assert x.shape == (1, 3, 512, 512) and abs(float(x[:, :, 200:300, 200:300].mean())) < 3.0
+    sched = vd.batches(164, 16, 12, 1234)
+    assert len(sched) == 12 and all(len(set(i.tolist())) == 16 for i, _ in sched)
+    assert abs(vd.lr_at(30, 2000, 3e-4) - 3e-4 * 0.5 * (1 + __import__("math").cos(__import__("math").pi * 30 / 2000))) < 1e-12
